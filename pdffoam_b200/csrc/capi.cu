@@ -1,0 +1,224 @@
+// capi.cu — the extern "C" entry points of include/pdfb200.h, plus handle
+// construction. No exception crosses the ABI: every call returns a status and
+// stores the message for pdfb200_last_error().
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "cloud.hpp"
+
+struct pdfb200_cloud { Cloud c; };
+
+static thread_local std::string g_err;
+
+template <class F>
+static int guarded(F &&f) {
+    try {
+        f();
+        return PDFB200_OK;
+    } catch (const CudaError &e) { g_err = e.what(); return PDFB200_ERR_CUDA; }
+    catch (const std::length_error &e) { g_err = e.what(); return PDFB200_ERR_CAPACITY; }
+    catch (const std::logic_error &e) { g_err = e.what(); return dynamic_cast<const std::invalid_argument *>(&e) ? PDFB200_ERR_INVALID : PDFB200_ERR_STATE; }
+    catch (const std::bad_alloc &) { g_err = "out of host memory"; return PDFB200_ERR_CAPACITY; }
+    catch (const std::exception &e) { g_err = e.what(); return PDFB200_ERR_INVALID; }
+}
+
+void commDestroy(Cloud &c);   // comm.cu
+
+Cloud::~Cloud() {
+    if (device >= 0) cudaSetDevice(device);
+    commDestroy(*this);
+    for (void *p : stateAllocs) cudaFree(p);
+    if (hScal) cudaFreeHost(hScal);
+    if (hFinal) cudaFreeHost(hFinal);
+    if (evStart) cudaEventDestroy(evStart);
+    if (evStop) cudaEventDestroy(evStop);
+    if (evArA) cudaEventDestroy(evArA);
+    if (evArB) cudaEventDestroy(evArB);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+static void validateParams(const pdfb200_params &p) {
+    if (p.nPhi < 0 || p.nPhi > PDFB200_MAX_PHI) throw std::invalid_argument("nPhi out of range");
+    if (p.nMixed < 0 || p.nMixed > p.nPhi || p.nConserved < 0 || p.nConserved > p.nPhi) throw std::invalid_argument("too many mixed/conserved scalars");
+    for (int i = 0; i < p.nMixed; ++i) if (p.mixed[i] < 0 || p.mixed[i] >= p.nPhi) throw std::invalid_argument("No such scalar field (mixedScalars)");
+    for (int i = 0; i < p.nConserved; ++i) if (p.conserved[i] < 0 || p.conserved[i] >= p.nPhi) throw std::invalid_argument("No such scalar field (conservedScalars)");
+    if (!(p.cloneAt >= 0 && p.cloneAt < 1.)) throw std::invalid_argument("cloneAt must be in the range [0, 1)");      // mcSolution.C:146-152
+    if (!(p.eliminateAt > 1)) throw std::invalid_argument("eliminateAt must be > 1");                                   // mcSolution.C:155-161
+    if (p.particlesPerCell <= 0) throw std::invalid_argument("particlesPerCell must be positive");
+    if (p.velocityModel < 0 || p.velocityModel > PDFB200_VELOCITY_SLMFULL) throw std::invalid_argument("Unknown mcVelocityModel type");
+    if (p.mixingModel < 0 || p.mixingModel > PDFB200_MIXING_IEM) throw std::invalid_argument("Unknown mcMixingModel type");
+    if (p.omegaModel < 0 || p.omegaModel > PDFB200_OMEGA_RAS) throw std::invalid_argument("Unknown mcOmegaModel type");
+    if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_STEADY_FLAMELET) throw std::invalid_argument("Unknown mcReactionModel type");
+    if (p.positionCorrection < 0 || p.positionCorrection > PDFB200_POSCORR_LIMITED_SIMPLE) throw std::invalid_argument("Unknown mcPositionCorrection type");
+    if (p.localTimeStepping < 0 || p.localTimeStepping > PDFB200_LTS_PARTICLE) throw std::invalid_argument("Unknown mcLocalTimeStepping type");
+    if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET)
+        if (p.zIdx < 0 || p.zIdx >= p.nPhi) throw std::invalid_argument("reaction model: zIdx out of range");
+    if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN && (p.TIdx < 0 || p.TIdx >= p.nPhi)) throw std::invalid_argument("BurkeSchumann: TIdx out of range");
+    if (p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET) {
+        if (p.chiIdx < 0 || p.chiIdx >= p.nPhi) throw std::invalid_argument("SteadyFlamelet: chiIdx out of range");
+        if (p.nAdded < 0 || p.nAdded > PDFB200_MAX_ADDED) throw std::invalid_argument("SteadyFlamelet: too many added scalars");
+        for (int i = 0; i < p.nAdded; ++i) if (p.addedIdx[i] < 0 || p.addedIdx[i] >= p.nPhi) throw std::invalid_argument("SteadyFlamelet: added scalar out of range");
+    }
+}
+
+void Cloud::setParams(const pdfb200_params &p) {
+    validateParams(p);
+    if (haveCloudFields && p.nPhi != prm.nPhi) throw std::invalid_argument("set_params: nPhi cannot change after the fields were uploaded");
+    prm = p;
+    prm.C0 = fmax(0.0, prm.C0);                    // mcSLMFullVelocityModel.C:97-98
+    prm.C1 = fmax(0.0, fmin(1.0, prm.C1));
+    nCov = prm.nPhi * (prm.nPhi + 1) / 2;
+    nMom = 12 + prm.nPhi + nCov;
+    cellAuxStride = 2 + prm.nPhi;
+}
+
+void Cloud::create(const pdfb200_mesh &m, const pdfb200_params &p, int dev, int64_t cap) {
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0) throw CudaError(e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount (libpdfb200 has no CPU fallback)", __FILE__, __LINE__);
+    if (dev < 0 || dev >= nDev) throw std::invalid_argument("create: no such CUDA device");
+    if (cap <= 0) throw std::invalid_argument("create: capacity must be positive");
+    if (cap > 2000000000LL) throw std::invalid_argument("create: capacity above 2e9 particles per GPU");
+    device = dev;
+    capacity = cap;
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    numSMs = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&evStart)); CUDA_CHECK(cudaEventCreate(&evStop));
+    CUDA_CHECK(cudaEventCreate(&evArA)); CUDA_CHECK(cudaEventCreate(&evArB));
+    setParams(p);
+    CUDA_CHECK(cudaMallocHost((void **)&hScal, sizeof(StepScalars)));
+    CUDA_CHECK(cudaMallocHost((void **)&hFinal, 64 * sizeof(double)));
+    std::memset(hScal, 0, sizeof(StepScalars));
+    hScal->deltaT = p.deltaT0 > 0 ? p.deltaT0 : 100 * PDF_SMALL;
+    hScal->omegaClip = 1.7976931348623157e308;
+    scal.alloc(1);
+    CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
+    deltaTHost = hScal->deltaT;
+    finalSums.alloc(256); finalSums.zero(stream);
+    k1PartMax.alloc((size_t)numSMs * 64);
+    buildMesh(m);
+}
+
+void Cloud::setTables(int nChi_, int nZ_, const double *chi, const double *z, int nFields, const double *const *fields) {
+    // sanity checks of mcSteadyFlamelet's constructor (mcSteadyFlamelet.C:222-286)
+    if (nZ_ < 2) throw std::invalid_argument("flamelet z must have at least 2 elements");
+    if (nChi_ < 1) throw std::invalid_argument("flamelet chi must have at least 1 element");
+    for (int i = 1; i < nZ_; ++i) if (!(z[i] - z[i - 1] > 0)) throw std::invalid_argument("flamelet z not strictly monotonically increasing");
+    for (int i = 1; i < nChi_; ++i) if (!(chi[i] - chi[i - 1] > 0)) throw std::invalid_argument("flamelet chi not strictly monotonically increasing");
+    if (nFields < 1) throw std::invalid_argument("flamelet tables: at least rho is required");
+    nChi = nChi_; nZ = nZ_; nFlFields = nFields;
+    flChi.upload(chi, nChi, stream); flZ.upload(z, nZ, stream);
+    flFields.alloc((size_t)nFields * nChi * nZ);
+    for (int f = 0; f < nFields; ++f)
+        CUDA_CHECK(cudaMemcpyAsync(flFields.p + (size_t)f * nChi * nZ, fields[f], (size_t)nChi * nZ * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+#define H(c) (&(c)->c)
+#define USE_DEVICE(c) cudaSetDevice((c)->c.device)
+
+extern "C" {
+
+const char *pdfb200_last_error(void) { return g_err.c_str(); }
+
+int pdfb200_create(const pdfb200_mesh *mesh, const pdfb200_params *params, int device, int64_t capacity, pdfb200_cloud **out) {
+    if (!mesh || !params || !out) { g_err = "create: null argument"; return PDFB200_ERR_INVALID; }
+    pdfb200_cloud *h = new (std::nothrow) pdfb200_cloud();
+    if (!h) { g_err = "out of host memory"; return PDFB200_ERR_CAPACITY; }
+    const int rc = guarded([&] { h->c.create(*mesh, *params, device, capacity); });
+    if (rc != PDFB200_OK) { delete h; return rc; }
+    *out = h;
+    return PDFB200_OK;
+}
+
+void pdfb200_destroy(pdfb200_cloud *c) { if (c) { USE_DEVICE(c); delete c; } }
+
+int pdfb200_set_params(pdfb200_cloud *c, const pdfb200_params *p) { USE_DEVICE(c); return guarded([&] { H(c)->setParams(*p); }); }
+
+int pdfb200_set_flamelet_tables(pdfb200_cloud *c, int32_t nChi, int32_t nZ, const double *chi, const double *z, int32_t nFields,
+                                const double *const *fields) {
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->setTables(nChi, nZ, chi, z, nFields, fields); });
+}
+
+int pdfb200_upload_fv_fields(pdfb200_cloud *c, const pdfb200_fv_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->uploadFv(*f); }); }
+int pdfb200_upload_cloud_fields(pdfb200_cloud *c, const pdfb200_cloud_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->uploadCloudFields(*f); }); }
+int pdfb200_init_moments(pdfb200_cloud *c) { USE_DEVICE(c); return guarded([&] { H(c)->initMoments(); }); }
+int pdfb200_seed_particles(pdfb200_cloud *c) { USE_DEVICE(c); return guarded([&] { H(c)->seedParticles(); }); }
+int pdfb200_upload_particles(pdfb200_cloud *c, int64_t n, const pdfb200_particles *p) { USE_DEVICE(c); return guarded([&] { H(c)->uploadParticles(n, *p); }); }
+int64_t pdfb200_num_particles(pdfb200_cloud *c) { return c->c.nParticlesHost; }
+int pdfb200_download_particles(pdfb200_cloud *c, int64_t maxn, pdfb200_particles *out, int64_t *n) {
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->downloadParticles(maxn, *out, n); });
+}
+int pdfb200_evolve(pdfb200_cloud *c, int32_t nSteps, pdfb200_step_report *reports) { USE_DEVICE(c); return guarded([&] { H(c)->evolve(nSteps, reports); }); }
+int pdfb200_download_cell_fields(pdfb200_cloud *c, pdfb200_cell_fields *o) { USE_DEVICE(c); return guarded([&] { H(c)->downloadCellFields(*o); }); }
+
+double pdfb200_delta_t(pdfb200_cloud *c) { return c->c.deltaTHost; }
+int pdfb200_set_delta_t(pdfb200_cloud *c, double dt) {
+    USE_DEVICE(c);
+    return guarded([&] {
+        Cloud &C = c->c;
+        C.deltaTHost = dt;
+        CUDA_CHECK(cudaMemcpy(&C.scal.p->deltaT, &dt, sizeof(double), cudaMemcpyHostToDevice));
+    });
+}
+
+int pdfb200_comm_init(pdfb200_cloud *c, int32_t nRanks, int32_t rank, const char id[128]) {
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->commInit(nRanks, rank, id); });
+}
+
+int pdfb200_mesh_info_get(pdfb200_cloud *c, pdfb200_mesh_info *info) {
+    const Cloud &C = c->c;
+    info->nTets = C.nTets; info->maxTetsPerCell = C.maxTetsPerCell; info->isAxiSymmetric = C.axisym;
+    for (int k = 0; k < 3; ++k) { info->axis[k] = C.axis[k]; info->centrePlaneNormal[k] = C.centreNormal[k]; }
+    info->openingAngle = C.openingAngle;
+    return PDFB200_OK;
+}
+
+int pdfb200_download_tets(pdfb200_cloud *c, double *gradN, int32_t *nbr, int32_t *faceLabel, int32_t *ptB, int32_t *ptC, int32_t *cell) {
+    USE_DEVICE(c);
+    return guarded([&] {
+        Cloud &C = c->c;
+        std::vector<TetRec> h((size_t)C.nTets);
+        CUDA_CHECK(cudaMemcpy(h.data(), C.tets.p, h.size() * sizeof(TetRec), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < h.size(); ++t) {
+            if (gradN) for (int k = 0; k < 9; ++k) gradN[9 * t + k] = h[t].g[k];
+            if (nbr) for (int k = 0; k < 4; ++k) nbr[4 * t + k] = h[t].nbr[k];
+            if (faceLabel) faceLabel[t] = h[t].face;
+            if (ptB) ptB[t] = h[t].ptB;
+            if (ptC) ptC[t] = h[t].ptC;
+            if (cell) cell[t] = h[t].cell;
+        }
+    });
+}
+
+int pdfb200_download_geometry(pdfb200_cloud *c, double *fc, double *fa, double *cc, double *cv, double *co, double *hn) {
+    USE_DEVICE(c);
+    return guarded([&] {
+        Cloud &C = c->c;
+        const size_t nf = C.nFaces, nc = C.nCells;
+        if (fc) CUDA_CHECK(cudaMemcpy(fc, C.faceCentres.p, nf * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (fa) CUDA_CHECK(cudaMemcpy(fa, C.faceAreas.p, nf * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (co) CUDA_CHECK(cudaMemcpy(co, C.courantCoeffs.p, nf * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (cv) CUDA_CHECK(cudaMemcpy(cv, C.cellVolumes.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+        if (cc || hn) {
+            std::vector<double4> h(nc);
+            CUDA_CHECK(cudaMemcpy(h.data(), C.cellCentre4.p, nc * sizeof(double4), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nc; ++i) {
+                if (cc) { cc[3 * i] = h[i].x; cc[3 * i + 1] = h[i].y; cc[3 * i + 2] = h[i].z; }
+                if (hn) hn[i] = h[i].w;
+            }
+        }
+    });
+}
+
+int64_t pdfb200_kernel_launches(pdfb200_cloud *c) { return c->c.launches; }
+double pdfb200_last_evolve_ms(pdfb200_cloud *c) { return c->c.lastEvolveMs; }
+
+}  // extern "C"

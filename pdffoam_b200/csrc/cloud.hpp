@@ -1,0 +1,177 @@
+// cloud.hpp — host-side state of one device cloud (libpdfb200).
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CUDA_CHECK(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void zero(cudaStream_t s) { if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(const T *h, size_t count, cudaStream_t s) {
+        if (count > n) alloc(count);
+        if (count) CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t count, cudaStream_t s) const {
+        if (count) CUDA_CHECK(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DBuf() { release(); }
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+};
+
+struct HostPatch { int start, size, geom, handler, reflecting; };
+
+// number of doubles in the trailing global section of the moment block
+#define BLOCK_TAIL 32
+
+// layout of the particle kernel's per-thread accumulators
+#define K1_THREADS 128
+#define K1_MAXCONS 3
+#define K1_NC1 (1 + K1_MAXCONS)
+// thread-private shared-memory accumulators
+#define ACC_DM_MINUS 0
+#define ACC_DM_PLUS (ACC_DM_MINUS + K1_NC1)
+#define ACC_MASS_IN (ACC_DM_PLUS + K1_NC1)
+#define ACC_MASS_OUT (ACC_MASS_IN + K1_NC1)
+#define ACC_N_DELETED (ACC_MASS_OUT + K1_NC1)
+#define ACC_N_LOST (ACC_N_DELETED + 1)
+#define ACC_N_ALIVE (ACC_N_LOST + 1)
+#define ACC_NSUM (ACC_N_ALIVE + 1)
+#define ACC_UMAX 0
+#define ACC_UCORRMAX 1
+#define ACC_ETAMAX 2
+#define ACC_NEG_ETAMIN 3
+#define ACC_COMAX 4
+#define ACC_NMAX 5
+
+struct NcclApi;   // dlopen'ed NCCL entry points (comm.cu)
+
+struct Cloud {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evArA = nullptr, evArB = nullptr;
+    int64_t capacity = 0;
+    pdfb200_params prm{};
+    int nMom = 0, nCov = 0, cellAuxStride = 0;
+    long long launches = 0;
+    double lastEvolveMs = 0;
+    int numSMs = 148;
+
+    // ---- host copies of the small mesh tables ----
+    int nCells = 0, nFaces = 0, nInternalFaces = 0, nPoints = 0, nBnd = 0;
+    long long nTets = 0;
+    int maxTetsPerCell = 0, tetBits = 0, keyBits = 0;
+    std::vector<HostPatch> patches;
+    std::vector<int> hOwner, hFaceStart, hFacePoints;   // needed for inlet tables
+    bool axisym = false;
+    double axis[3] = {0, 0, 0}, centreNormal[3] = {0, 0, 0}, openingAngle = 0;
+    bool hasOpen = false, hasInlet = false;
+
+    // ---- device mesh ----
+    DMesh dm{};
+    DBuf<double> points, faceCentres, faceAreas, magSf, cellVolumes, volumeOrArea, bbMin, bbMax, courantCoeffs, cellCo,
+        linWeights, pointWeights, patchFaceT;
+    DBuf<double4> cellCentre4, bfNormal;
+    DBuf<int> faceStart, facePoints, owner, neighbour, cellFaceStart, cellFaces, cellTetStart, faceTetStartOwn,
+        faceTetStartNei, pointCellStart, pointCells, bfInfo, openCellStart, openCellFaces;
+    DBuf<TetRec> tets;
+
+    // ---- fields ----
+    // FV-owned
+    DBuf<double> Ufv_c, Ufv_b, p_c, p_b, kfv_c, kfv_b, eps_c, eps_b, R_c, R_b;
+    DBuf<uint8_t> UbFixed, kbFixed, rhoFixed;
+    // cloud fields (cell + boundary)
+    DBuf<double> rho_c, rho_b, rhoInst_c, pnd_c, pndInst_c, Updf_c, Updf_b, Tau_c, Tau_b, kpdf_c, kpdf_b;
+    DBuf<double> Phi_c, Phi_b, Cov_c, Cov_b;       // [nPhi][nCells] etc.
+    DBuf<uint8_t> PhiFixed, CovFixed;              // [nPhi][nBnd]
+    DBuf<double> PaNIC, lostMass, lostShare;
+    // time-averaged moments
+    DBuf<double> mMom, VMom, UMom, UUMom, PhiMom, PhiPhiMom;
+    DBuf<double> momentBlock;                      // [nCells*nMom + BLOCK_TAIL]
+    // step work arrays
+    DBuf<double> phiPC, UPC_c, OmegaRaw_c, etaRaw_c;
+    DBuf<double> nodeMid, nodePC, cellAux;
+    DBuf<double> Un, inletU, inletR, fwdTrans, probVec;
+    bool inletCached = false;
+    // flamelet tables
+    DBuf<double> flChi, flZ, flFields;
+    int nChi = 0, nZ = 0, nFlFields = 0;
+
+    // ---- particles ----
+    PState S[2]{};
+    std::vector<void *> stateAllocs;
+    int cur = 0;
+    DBuf<uint32_t> keysA, keysB, valsA, valsB, iota;
+    DBuf<int> injPatchTail;
+    DBuf<unsigned char> cubTemp;
+    DBuf<int> cellStart, cellEnd, ncFlag, ncCount, ncOffset, scanTmp;
+    DBuf<int> injCount, injOffset;
+    DBuf<double> injSums;
+    DBuf<double> k1PartSum, k1PartMax, cellPartSum, finalSums;   // deterministic reductions
+    DBuf<double> ncDelta;
+    DBuf<StepScalars> scal;
+    StepScalars *hScal = nullptr;     // pinned mirror
+    double *hFinal = nullptr;         // pinned reduction results
+    int64_t nParticlesHost = 0;       // alive particles after the last step
+    int64_t nSlotsHost = 0;           // slots used in the current buffer (upper bound for launches)
+    bool haveFv = false, haveCloudFields = false, haveMoments = false, sortedValid = false;
+    uint32_t stepHost = 0;
+    double deltaTHost = 1e-13;
+
+    // ---- multi-GPU ----
+    int nRanks = 1, rank = 0;
+    NcclApi *nccl = nullptr;
+    void *comm = nullptr;
+
+    ~Cloud();
+    void create(const pdfb200_mesh &m, const pdfb200_params &p, int device, int64_t capacity);
+    void buildMesh(const pdfb200_mesh &m);            // mesh_build.cu
+    void setParams(const pdfb200_params &p);
+    void setTables(int nChi, int nZ, const double *chi, const double *z, int nFields, const double *const *fields);
+    void uploadFv(const pdfb200_fv_fields &f);
+    void uploadCloudFields(const pdfb200_cloud_fields &f);
+    void initMoments();
+    void allocParticles();
+    void seedParticles();
+    void uploadParticles(int64_t n, const pdfb200_particles &p);
+    void downloadParticles(int64_t maxn, pdfb200_particles &out, int64_t *n);
+    void evolve(int nSteps, pdfb200_step_report *reports);
+    void downloadCellFields(pdfb200_cell_fields &o);
+    void commInit(int nRanks, int rank, const char id[128]);
+
+    // step pieces (fields.cu / particles.cu)
+    void prepareFields();
+    void stepParticles(pdfb200_step_report *rep);
+    void sortAndMoments();
+    void finaliseStep(pdfb200_step_report *rep);
+    void numberControl();
+    void inject();
+    void syncScalars();
+    DMesh &mesh() { return dm; }
+};
+
+// launch helper counting this library's kernel launches
+#define LAUNCH(cloud, kernel, grid, block, smem, ...)                                      \
+    do {                                                                                   \
+        kernel<<<(grid), (block), (smem), (cloud)->stream>>>(__VA_ARGS__);                  \
+        ++(cloud)->launches;                                                               \
+        CUDA_CHECK(cudaGetLastError());                                                    \
+    } while (0)
+
+static inline int gridFor(long long n, int block, int cap = 1 << 30) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}

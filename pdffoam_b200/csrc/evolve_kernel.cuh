@@ -1,0 +1,590 @@
+// evolve_kernel.cuh — the fused per-particle kernel of one time step.
+//
+// One thread carries one particle through steps E1(cull)–E11 of
+// mcParticleCloud::evolve (mcParticle/mcParticleCloud/mcParticleCloud.C:1226-1352):
+//   open-boundary cull (mcOpenBoundary.C:84-141), mass bookkeeping (:1238-1249),
+//   position-correction gather (mcLimitedSimplePositionCorrection.C:187-192),
+//   constrainParticle (:76-101), half-step tet walk (mcParticle.C:100-179),
+//   Courant number (:2120-2148), Omega / IEM / reaction / SLM / local time step
+//   (mcRASOmegaModel.C:125-147, mcIEMMixingModel.C:68-83, mcSteadyFlamelet.C:304-329,
+//   mcBurkeSchumannReactionModel.C:77-91, mcColdReactionModel.C:62-65,
+//   mcSLMFullVelocityModel.C:146-185, mc*LocalTimeStepping), the mid-point rule
+//   with numerical diffusion (:1297-1331), the full-step walk and the
+//   open-boundary velocity fix-up (mcOpenBoundary.C:142-155).
+// The particle is read through the permutation of the previous step's sort and
+// written in sorted order, so the state is read once and written once per step.
+//
+// Compiled with -fmad=false: every fused multiply-add below is explicit. The
+// fma chains of the tet walk are the ones the CPU oracle evaluates, which makes
+// cell/tet decisions bit-identical.
+#pragma once
+
+#include "common.cuh"
+
+struct K1Args {
+    DMesh M;
+    pdfb200_params P;
+    PState in, out;
+    const uint32_t *perm;
+    uint32_t *keyOut;
+    const StepScalars *sc;
+    const double *nodeMid, *nodePC, *cellAux;
+    int auxStride;
+    const double *Un;
+    const double *lostShare;
+    double *lostMass;
+    const int *injPatchTail;
+    const double *flChi, *flZ, *flFields;
+    int nChi, nZ;
+    RngKey key;
+    double *partSum, *partMax;
+    int hasOpen;
+};
+
+struct TetL {   // a tet record in registers
+    int nbr[4];
+    int face, ptB, ptC, cell;
+    double g[9];
+};
+
+__device__ inline void loadTet(const TetRec *tets, int t, TetL &T) {
+    const int4 *pi = reinterpret_cast<const int4 *>(tets + t);
+    const int4 a = __ldg(pi), b = __ldg(pi + 1);
+    T.nbr[0] = a.x; T.nbr[1] = a.y; T.nbr[2] = a.z; T.nbr[3] = a.w;
+    T.face = b.x; T.ptB = b.y; T.ptC = b.z; T.cell = b.w;
+    const double2 *pd = reinterpret_cast<const double2 *>(tets + t) + 2;
+    const double2 g0 = __ldg(pd), g1 = __ldg(pd + 1), g2 = __ldg(pd + 2), g3 = __ldg(pd + 3), g4 = __ldg(pd + 4);
+    T.g[0] = g0.x; T.g[1] = g0.y; T.g[2] = g1.x; T.g[3] = g1.y; T.g[4] = g2.x; T.g[5] = g2.y;
+    T.g[6] = g3.x; T.g[7] = g3.y; T.g[8] = g4.x;
+}
+
+__device__ inline V3 cellCentre(const DMesh &M, int c) {
+    const double2 *p = reinterpret_cast<const double2 *>(M.cellCentre4 + c);
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    return mk(a.x, a.y, b.x);
+}
+
+__device__ inline void baryAt(const TetL &T, V3 r, double w[4]) {
+    w[0] = dotf(T.g[0], T.g[1], T.g[2], r);
+    w[1] = dotf(T.g[3], T.g[4], T.g[5], r);
+    w[2] = dotf(T.g[6], T.g[7], T.g[8], r);
+    w[3] = 1.0 - ((w[0] + w[1]) + w[2]);
+}
+
+__device__ inline double clamp01(double x) { return fmax(0.0, fmin(1.0, x)); }
+
+__device__ inline double massPerDepth(const DMesh &M, V3 pos, double m) {
+    if (M.axisym) {
+        const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
+        const double r = mag3(pos - dot3(pos, ax) * ax);
+        return m / (fmax(r, PDF_SMALL) * M.openingAngle);
+    }
+    return m;
+}
+
+__device__ inline V3 reflectVec(V3 v, V3 n) {
+    const double d = dot3(v, n);
+    return v - (2.0 * d) * n;
+}
+
+__device__ inline void constrainDir(const int d[3], V3 &v) {
+    if (d[0] < 0) v.x = 0;
+    if (d[1] < 0) v.y = 0;
+    if (d[2] < 0) v.z = 0;
+}
+
+// constrainParticle (mcParticleCloud.C:76-101)
+__device__ inline void constrainParticle(const DMesh &M, double dt, V3 pos, V3 &U, V3 &Ucorr, V3 &Utrack) {
+    constrainDir(M.solD, Utrack);
+    if (M.axisym) {
+        V3 dest = pos + dt * Utrack;
+        const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
+        V3 n = cross3(ax, dest);
+        n = n / mag3(n);
+        double T[9];
+        rotationTensor(n, mk(M.centreNormal[0], M.centreNormal[1], M.centreNormal[2]), T);
+        U = xform(T, U); Ucorr = xform(T, Ucorr);
+        dest = xform(T, dest);
+        constrainDir(M.geoD, dest);
+        Utrack = (dest - pos) / dt;
+    }
+}
+
+struct PartFlags {
+    bool reflected, reflOpen;
+    V3 reflBV;
+    int nSteps;
+};
+
+// status: 0 alive, 1 deleted at an open boundary, 2 lost
+// mcParticle::move on the tet walk (see oracle/src/cloud.cpp Cloud::move for the
+// algorithm statement; both evaluate identical expressions).
+__device__ inline int trackParticle(const K1Args &A, double trackTime, double stepFraction, V3 &pos, int &tet, TetL &T,
+                                    V3 &Utrack, V3 &U, V3 &Ucorr, PartFlags &fl, double w[4], double m,
+                                    const double *phi, double *acc) {
+    const DMesh &M = A.M;
+    double tEnd = (1.0 - stepFraction) * trackTime;
+    const double dtMax = tEnd;
+    int entry = -1;
+    bool haveW = false;
+    while (tEnd > 0) {
+        double dt = fmin(dtMax, tEnd);
+        V3 dest = pos + dt * Utrack;
+        constrainDir(M.geoD, dest);
+        const V3 x0 = pos;
+        const V3 dx = dest - x0;
+        double tf = 1.0;
+        int status = 0;
+        bool hit = false;
+        for (;;) {
+            const V3 r = x0 - cellCentre(M, T.cell);
+            double p[4], q[4];
+            baryAt(T, r, p);
+            q[0] = dotf(T.g[0], T.g[1], T.g[2], dx);
+            q[1] = dotf(T.g[3], T.g[4], T.g[5], dx);
+            q[2] = dotf(T.g[6], T.g[7], T.g[8], dx);
+            q[3] = -((q[0] + q[1]) + q[2]);
+            int best = -1;
+            double pb = 0, qb = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool cand = (i != entry) && (q[i] < 0) && (p[i] + q[i] < 0);
+                if (cand && (best < 0 || p[i] * qb > pb * q[i])) { best = i; pb = p[i]; qb = q[i]; }
+            }
+            if (best < 0) {
+                pos = dest;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = p[i] + q[i];
+                haveW = true;
+                tf = 1.0;
+                break;
+            }
+            ++fl.nSteps;
+            if (fl.nSteps > 1000) { status = 2; break; }
+            if (best != 3 || T.face < M.nInternalFaces) {
+                tet = T.nbr[best];
+                loadTet(M.tets, tet, T);
+                entry = (best == 1) ? 2 : (best == 2 ? 1 : best);
+                continue;
+            }
+            // boundary face
+            double s = p[3] / (-q[3]);
+            s = fmin(1.0, fmax(0.0, s));
+            pos = x0 + s * dx;
+            tf = s;
+            hit = true;
+            const int bf = T.face - M.nInternalFaces;
+            const int info = __ldg(M.bfInfo + bf);
+            const int handler = BF_HANDLER(info);
+            if (BF_GEOM(info) != PDFB200_PATCH_GENERIC || handler == PDFB200_BC_EMPTY) { status = 2; break; }
+            const double4 n4 = M.bfNormal[bf];
+            const V3 nw = mk(n4.x, n4.y, n4.z);
+            if (handler == PDFB200_BC_SLIP) {
+                U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
+                fl.reflected = true;
+            } else {
+                const double Un = A.Un[bf];
+                if (Un < 0 || !BF_REFLECTING(info)) {
+                    const double mpd = massPerDepth(M, pos, m);
+                    const int base = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
+                    acc[(base)*K1_THREADS] -= mpd;
+                    for (int cs = 0; cs < A.P.nConserved; ++cs) acc[(base + 1 + cs) * K1_THREADS] -= mpd * phi[A.P.conserved[cs]];
+                    status = 1;
+                    break;
+                }
+                U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
+                fl.reflected = true; fl.reflOpen = true;
+                fl.reflBV = nw * Un;
+            }
+            entry = 3;
+            break;
+        }
+        if (status != 0) return status;
+        (void)hit;
+        dt *= tf;
+        tEnd -= dt;
+    }
+    if (!haveW) {   // zero-length track (or it ended on a boundary): weights at the current position
+        const V3 r = pos - cellCentre(M, T.cell);
+        baryAt(T, r, w);
+    }
+    return 0;
+}
+
+// mcSteadyFlamelet helpers (mcSteadyFlamelet.C:44-93)
+__device__ inline void findCoeffsDev(const double *lst, int n, double v, int &i, double &w) {
+    int lo = 0, hi = n;   // lower_bound
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lst[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) { i = 0; w = 0.; }
+    else if (lo == n) { i = n - 2; w = 1.; }
+    else { i = lo - 1; w = (v - lst[lo - 1]) / (lst[lo] - lst[lo - 1]); }
+}
+__device__ inline double binterpDev(const double *v, int nRows, int nCols, int ix, double wx, int iy, double wy) {
+    const int r0 = min(max(ix, 0), nRows - 1), r1 = min(max(ix + 1, 0), nRows - 1);
+    const double v00 = v[r0 * nCols + iy], v10 = v[r0 * nCols + iy + 1], v01 = v[r1 * nCols + iy], v11 = v[r1 * nCols + iy + 1];
+    const double wxm = 1. - wx, wym = 1. - wy;
+    // transposed weights of the reference, kept verbatim
+    return v00 * wxm * wym + v10 * wx * wym + v01 * wxm * wy + v11 * wx * wy;
+}
+
+__device__ inline double stabilise(double x, double y) { return x < 0 ? x - y : x + y; }
+
+// Reaction models on one particle: mcColdReactionModel.C:62-65,
+// mcBurkeSchumannReactionModel.C:77-91, mcSteadyFlamelet.C:304-329.
+struct FlameletTables { const double *chi, *z, *fields; int nChi, nZ; };
+__device__ inline void reactionCorrect(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
+                                       double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho) {
+    if (P.reactionModel == PDFB200_REACTION_COLD) {
+        rho = P.coldDensity;
+    } else if (P.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN) {
+        double z = 0;
+#pragma unroll
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.zIdx) z = phi[k];
+        const double RTox = P.bsRox * P.bsTox, RTfuel = P.bsRfuel * P.bsTfuel, RTstoi = P.bsRstoi * P.bsTstoi;
+        const double RT = z < P.bsZstoi ? (RTstoi - RTox) / P.bsZstoi * z + RTox
+                                        : (RTfuel - RTstoi) / (1 - P.bsZstoi) * (z - P.bsZstoi) + RTstoi;
+        const double Tt = z < P.bsZstoi ? (P.bsTstoi - P.bsTox) / P.bsZstoi * z + P.bsTox
+                                        : (P.bsTfuel - P.bsTstoi) / (1 - P.bsZstoi) * (z - P.bsZstoi) + P.bsTstoi;
+        rho = pCell / RT;
+#pragma unroll
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.TIdx) phi[k] = Tt;
+    } else if (P.reactionModel == PDFB200_REACTION_STEADY_FLAMELET) {
+        double z = 0;
+#pragma unroll
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.zIdx) z = phi[k];
+        const double chi = fmax(P.Cchi * Omega * zVar, PDF_SMALL);
+        int iz, ichi; double wz, wchi;
+        findCoeffsDev(F.z, F.nZ, z, iz, wz);
+        findCoeffsDev(F.chi, F.nChi, chi, ichi, wchi);
+        rho = binterpDev(F.fields, F.nChi, F.nZ, ichi, wchi, iz, wz);
+#pragma unroll
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.chiIdx) phi[k] = chi;
+        for (int a = 0; a < P.nAdded; ++a) {
+            const double v = binterpDev(F.fields + (size_t)(1 + a) * F.nChi * F.nZ, F.nChi, F.nZ, ichi, wchi, iz, wz);
+#pragma unroll
+            for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.addedIdx[a]) phi[k] = v;
+        }
+    }
+}
+
+// interpolationCellPointFace of every mid-point field at once: the four node
+// records of the tet (points b and c, face centre, cell centre) blended with
+// the clamped barycentric weights; pst receives the four p* node values for
+// gradInterpolationConstantTet (order a, b, c, d).
+__device__ inline void interpMid(const DMesh &M, const pdfb200_params &P, const double *nodeMid, const TetL &T,
+                                 const double w[4], double (&val)[NODE_MID_STRIDE], double (&pst)[4]) {
+    const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
+    const double2 *nb = reinterpret_cast<const double2 *>(nodeMid + (nodeP + T.ptB) * NODE_MID_STRIDE);
+    const double2 *nc = reinterpret_cast<const double2 *>(nodeMid + (nodeP + T.ptC) * NODE_MID_STRIDE);
+    const double2 *na = reinterpret_cast<const double2 *>(nodeMid + (nodeF + T.face) * NODE_MID_STRIDE);
+    const double2 *nd = reinterpret_cast<const double2 *>(nodeMid + (size_t)T.cell * NODE_MID_STRIDE);
+    const double fb = clamp01(w[1]), fc = clamp01(w[2]), fa = clamp01(w[0]), fd = clamp01(w[3]);
+    double cv[NODE_MID_STRIDE];
+#pragma unroll
+    for (int k = 0; k < NODE_MID_STRIDE / 2; ++k) {
+        const double2 vb = __ldg(nb + k), vc = __ldg(nc + k), va = __ldg(na + k), vd = __ldg(nd + k);
+        val[2 * k] = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
+        val[2 * k + 1] = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
+        cv[2 * k] = vd.x; cv[2 * k + 1] = vd.y;
+        if (2 * k == NM_PSTAR) { pst[0] = va.x; pst[1] = vb.x; pst[2] = vc.x; pst[3] = vd.x; }
+    }
+    // interpolation scheme "cell": the cell value
+    if (P.interpU == PDFB200_INTERP_CELL) { val[NM_U] = cv[NM_U]; val[NM_U + 1] = cv[NM_U + 1]; val[NM_U + 2] = cv[NM_U + 2]; }
+    if (P.interpk == PDFB200_INTERP_CELL) val[NM_K] = cv[NM_K];
+    if (P.interpDiffU == PDFB200_INTERP_CELL) { val[NM_DU] = cv[NM_DU]; val[NM_DU + 1] = cv[NM_DU + 1]; val[NM_DU + 2] = cv[NM_DU + 2]; }
+    if (P.interpOmega == PDFB200_INTERP_CELL) val[NM_OMEGA] = cv[NM_OMEGA];
+    if (P.interpEta == PDFB200_INTERP_CELL) val[NM_ETA] = cv[NM_ETA];
+    if (P.interpZVar == PDFB200_INTERP_CELL) val[NM_ZVAR] = cv[NM_ZVAR];
+}
+
+// shared locate rule (oracle Mesh::locate): the tet of `cell` with the largest
+// minimum barycentric coordinate, first maximum wins
+__device__ inline int locateTet(const DMesh &M, V3 pos, int cell) {
+    const V3 r = pos - cellCentre(M, cell);
+    int best = -1;
+    double bestMin = -PDF_VGREAT;
+    const int ts = M.cellTetStart[cell], te = M.cellTetStart[cell + 1];
+    for (int t = ts; t < te; ++t) {
+        const double *g = M.tets[t].g;
+        const double pa = dotf(g[0], g[1], g[2], r), pb = dotf(g[3], g[4], g[5], r), pc = dotf(g[6], g[7], g[8], r);
+        const double pd = 1.0 - ((pa + pb) + pc);
+        const double mn = fmin(fmin(pa, pb), fmin(pc, pd));
+        if (mn > bestMin) { bestMin = mn; best = t; }
+    }
+    return best;
+}
+
+// primitiveMesh::pointInCell (face-plane test)
+__device__ inline bool pointInCell(const DMesh &M, V3 pt, int cell) {
+    for (int j = M.cellFaceStart[cell]; j < M.cellFaceStart[cell + 1]; ++j) {
+        const int f = M.cellFaces[j];
+        const V3 proj = pt - ld3(M.faceCentres, f);
+        V3 normal = ld3(M.faceAreas, f);
+        normal = normal / mag3(normal);
+        if (M.owner[f] != cell) normal = -normal;
+        if (dot3(normal, proj) > 0) return false;
+    }
+    return true;
+}
+
+// mcParticleCloud::randomPointsInCell (mcParticleCloud.C:2040-2085), one point
+__device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uint32_t entity, uint32_t purpose, uint32_t stepCtr) {
+    const V3 minb = ld3(M.bbMin, cell);
+    const V3 dimb = ld3(M.bbMax, cell) - minb;
+    V3 position = minb;
+    for (uint32_t attempt = 0;; ++attempt) {
+        double ux, uy, uz, dummy;
+        rngUniform2(key, entity, stepCtr, purpose, 2 * attempt, ux, uy);
+        rngUniform2(key, entity, stepCtr, purpose, 2 * attempt + 1, uz, dummy);
+        const double rx = fmin(fmax(10.0 * PDF_SMALL, ux), 1.0 - 10.0 * PDF_SMALL);
+        const double ry = fmin(fmax(10.0 * PDF_SMALL, uy), 1.0 - 10.0 * PDF_SMALL);
+        const double rz = fmin(fmax(10.0 * PDF_SMALL, uz), 1.0 - 10.0 * PDF_SMALL);
+        position = minb + mk(rx * dimb.x, ry * dimb.y, rz * dimb.z);
+        if (M.nGeoD <= 2) constrainDir(M.geoD, position);
+        if (pointInCell(M, position, cell) || attempt > 10000) break;
+    }
+    return position;
+}
+
+// computeCourantNo (mcParticleCloud.C:2120-2148)
+__device__ inline double courantNo(const DMesh &M, int cell, V3 Utrack) {
+    double Co = 0.;
+    const int js = __ldg(M.cellFaceStart + cell), je = __ldg(M.cellFaceStart + cell + 1);
+    for (int j = js; j < je; ++j) Co = fmax(Co, fabs(dot3(ld3(M.cellCo, j), Utrack)));
+    return Co;
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
+    extern __shared__ double smem[];
+    double *accS = smem + threadIdx.x;                         // sums: accS[k*K1_THREADS]
+    double *accM = smem + ACC_NSUM * K1_THREADS + threadIdx.x;  // maxima
+#pragma unroll
+    for (int k = 0; k < ACC_NSUM; ++k) accS[k * K1_THREADS] = 0.0;
+#pragma unroll
+    for (int k = 0; k < ACC_NMAX; ++k) accM[k * K1_THREADS] = -PDF_VGREAT;
+
+    const DMesh &M = A.M;
+    const pdfb200_params &P = A.P;
+    const StepScalars sc = *A.sc;
+    const int nSorted = sc.nSorted, total = sc.nSorted + sc.nTail;
+    const double deltaT = sc.deltaT;
+    const int nPhi = P.nPhi;
+    const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
+
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int slot = (i < nSorted) ? (int)A.perm[i] : sc.nSlots + (i - nSorted);
+        int cell = A.in.cell[slot];
+        if (cell < 0) { A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
+        V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
+        V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
+        double m = A.in.m[slot], Omega = A.in.omega[slot], rho = A.in.rho[slot], eta = A.in.eta[slot];
+        double phi[PDFB200_MAX_PHI];
+#pragma unroll
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) phi[k] = (k < nPhi) ? A.in.phi[k][slot] : 0.0;
+        int tet = A.in.tet[slot];
+        const uint32_t id = A.in.id[slot];
+        if (sc.anyLost) m += A.lostShare[cell];
+        const bool injected = (i >= nSorted + sc.nInjStart);
+        const int injPatch = injected ? A.injPatchTail[i - nSorted] : -1;
+
+        int status = 0;
+        // ---- E1: mcOpenBoundary::correct(false), cull behind the moving outflow plane ----
+        if (A.hasOpen) {
+            const int ks = __ldg(M.openCellStart + cell), ke = __ldg(M.openCellStart + cell + 1);
+            for (int k = ks; k < ke && status == 0; ++k) {
+                const int bf = M.openCellFaces[k];
+                const int info = M.bfInfo[bf];
+                if (BF_PATCH(info) <= injPatch || !BF_REFLECTING(info)) continue;
+                const double Un = A.Un[bf];
+                if (!(Un < 0.)) {
+                    const double4 n4 = M.bfNormal[bf];
+                    const V3 Cf = ld3(M.faceCentres, M.nInternalFaces + bf);
+                    const double xp = dot3(mk(n4.x, n4.y, n4.z), Cf - pos);
+                    if (xp < eta * (Un * deltaT)) {
+                        const double mpd = massPerDepth(M, pos, m);
+                        accS[ACC_MASS_OUT * K1_THREADS] -= mpd;
+                        for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * phi[P.conserved[cs]];
+                        status = 1;
+                    }
+                }
+            }
+        }
+        if (status != 0) { accS[ACC_N_DELETED * K1_THREADS] += 1; A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
+
+        // ---- E2 ----
+        {
+            const double mpd = massPerDepth(M, pos, m);
+            accS[ACC_DM_MINUS * K1_THREADS] -= mpd;
+            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * phi[P.conserved[cs]];
+        }
+        // ---- E3: position correction gather ----
+        TetL T;
+        loadTet(M.tets, tet, T);
+        V3 Ucorr = mk(0, 0, 0);
+        if (P.positionCorrection != PDFB200_POSCORR_NONE) {
+            if (P.interpUPosCorr == PDFB200_INTERP_CELL) {
+                const double *q = A.nodePC + (size_t)T.cell * 4;
+                Ucorr = mk(q[0], q[1], q[2]);
+            } else {
+                double w0[4];
+                baryAt(T, pos - cellCentre(M, T.cell), w0);
+                const double fb = clamp01(w0[1]), fc = clamp01(w0[2]), fa = clamp01(w0[0]), fd = clamp01(w0[3]);
+                const double2 *qb = reinterpret_cast<const double2 *>(A.nodePC + (nodeP + T.ptB) * 4);
+                const double2 *qc = reinterpret_cast<const double2 *>(A.nodePC + (nodeP + T.ptC) * 4);
+                const double2 *qa = reinterpret_cast<const double2 *>(A.nodePC + (nodeF + T.face) * 4);
+                const double2 *qd = reinterpret_cast<const double2 *>(A.nodePC + (size_t)T.cell * 4);
+                const double2 b0 = __ldg(qb), b1 = __ldg(qb + 1), c0 = __ldg(qc), c1 = __ldg(qc + 1);
+                const double2 a0 = __ldg(qa), a1 = __ldg(qa + 1), d0 = __ldg(qd), d1 = __ldg(qd + 1);
+                Ucorr.x = fma(fd, d0.x, fma(fa, a0.x, fma(fc, c0.x, fb * b0.x)));
+                Ucorr.y = fma(fd, d0.y, fma(fa, a0.y, fma(fc, c0.y, fb * b0.y)));
+                Ucorr.z = fma(fd, d1.x, fma(fa, a1.x, fma(fc, c1.x, fb * b1.x)));
+            }
+        }
+        // ---- E4 ----
+        V3 Utrack = U + Ucorr;
+        constrainParticle(M, deltaT / 2, pos, U, Ucorr, Utrack);
+        PartFlags fl;
+        fl.reflected = false; fl.reflOpen = false; fl.reflBV = mk(0, 0, 0); fl.nSteps = 0;
+        const V3 Uold = U, posOld = pos;
+        const int tetOld = tet;
+        // ---- E5: first tracking pass over eta*deltaT/2 ----
+        double w[4];
+        double stepFraction = 0.0;
+        if (injected) { double u0, u1; rngUniform2(A.key, id, sc.step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
+        status = trackParticle(A, eta * (deltaT / 2.), stepFraction, pos, tet, T, Utrack, U, Ucorr, fl, w, m, phi, accS);
+        if (status != 0) {
+            if (status == 2) { atomicAdd(A.lostMass + T.cell, m); accS[ACC_N_LOST * K1_THREADS] += 1; }
+            else accS[ACC_N_DELETED * K1_THREADS] += 1;
+            A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1;
+            continue;
+        }
+        cell = T.cell;
+        // ---- E6: Courant number ----
+        fl.nSteps = 0;
+        double Co = courantNo(M, cell, Utrack);
+        // ---- E7: models at the mid-point ----
+        {
+            double val[NODE_MID_STRIDE];
+            double pst[4];
+            interpMid(M, P, A.nodeMid, T, w, val, pst);
+            const double *aux = A.cellAux + (size_t)cell * A.auxStride;
+            // mcRASOmegaModel::correct
+            if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
+            // mcIEMMixingModel::correct
+            if (P.mixingModel != PDFB200_MIXING_NONE) {
+                const double Cmix2 = 0.5 * P.Cmix;
+                const double fac = 1.0 - exp(-Cmix2 * Omega * eta * deltaT);
+                for (int mI = 0; mI < P.nMixed; ++mI) {
+                    const int s = P.mixed[mI];
+#pragma unroll
+                    for (int k = 0; k < PDFB200_MAX_PHI; ++k)
+                        if (k == s) phi[k] -= fac * (phi[k] - aux[2 + k]);
+                }
+            }
+            // reaction model
+            {
+                FlameletTables FT;
+                FT.chi = A.flChi; FT.z = A.flZ; FT.fields = A.flFields; FT.nChi = A.nChi; FT.nZ = A.nZ;
+                reactionCorrect(P, FT, Omega, val[NM_ZVAR], aux[1], phi, rho);
+            }
+            // the six normals of the step
+            double xi0, xi1, xi2, gd0, gd1, gd2;
+            rngNormal2(A.key, id, sc.step, RNG_STEP_NORMALS, 0, xi0, xi1);
+            rngNormal2(A.key, id, sc.step, RNG_STEP_NORMALS, 1, xi2, gd0);
+            rngNormal2(A.key, id, sc.step, RNG_STEP_NORMALS, 2, gd1, gd2);
+            // mcSLMFullVelocityModel::correct
+            if (P.velocityModel != PDFB200_VELOCITY_NONE) {
+                const double dTp = eta * deltaT;
+                const V3 UFap = mk(val[NM_U], val[NM_U + 1], val[NM_U + 2]);
+                // gradInterpolationConstantTet: g_d*cell + g_b*ptB + g_c*ptC + g_a*face
+                const V3 ga = mk(T.g[0], T.g[1], T.g[2]), gb = mk(T.g[3], T.g[4], T.g[5]), gc = mk(T.g[6], T.g[7], T.g[8]);
+                const V3 gdv = -((ga + gb) + gc);
+                V3 gradP = (gdv * pst[3] + gb * pst[1]) + gc * pst[2];
+                gradP = gradP + ga * pst[0];
+                const double kFap = fmax(val[NM_K], P.kMin);
+                const V3 diffUap = mk(val[NM_DU], val[NM_DU + 1], val[NM_DU + 2]);
+                const double Acoef = -(0.5 * P.C1 + 0.75 * P.C0) * Omega;
+                const V3 B = -(gradP / rho + Acoef * UFap);
+                const double sq = sqrt(P.C0 * kFap * Omega * dTp);
+                const V3 deltaU = (B + Acoef * U) * dTp + sq * mk(xi0, xi1, xi2);
+                const V3 Ubefore = U;
+                U = U + (((deltaU + 0.5 * Acoef * deltaU * dTp) + diffUap * deltaT) + (Ubefore - UFap) * aux[0] * deltaT);
+                Co = fmax(Co, Omega);
+            }
+            // local time stepping
+            if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
+            else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) eta = fmin(P.CFL / stabilise(deltaT * Co, PDF_VSMALL), P.ltsUpperBound);
+            else eta = 1.0;
+
+            // ---- E9: mid-point rule from the old position ----
+            pos = posOld;
+            if (tet != tetOld) { tet = tetOld; loadTet(M.tets, tet, T); }
+            if (fl.reflected) Utrack = Uold; else Utrack = 0.5 * (Uold + U);
+            const double hNum = __ldg(reinterpret_cast<const double *>(M.cellCentre4 + T.cell) + 3);
+            const double C = P.DNum * sqrt(hNum * deltaT * mag3(Utrack)) / deltaT;
+            Utrack = Utrack + mk(C * gd0, C * gd1, C * gd2);
+            Utrack = Utrack + Ucorr;
+            constrainParticle(M, deltaT, pos, U, Ucorr, Utrack);
+        }
+        // ---- E10: second tracking pass over eta*deltaT ----
+        status = trackParticle(A, eta * deltaT, 0.0, pos, tet, T, Utrack, U, Ucorr, fl, w, m, phi, accS);
+        if (status != 0) {
+            if (status == 2) { atomicAdd(A.lostMass + T.cell, m); accS[ACC_N_LOST * K1_THREADS] += 1; }
+            else accS[ACC_N_DELETED * K1_THREADS] += 1;
+            A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1;
+            continue;
+        }
+        cell = T.cell;
+        // ---- E11: mcOpenBoundary::correct(true) ----
+        if (fl.reflOpen) U = U + 2 * fl.reflBV;
+
+        // ---- write back in sorted order ----
+        A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
+        A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
+        A.out.m[i] = m; A.out.omega[i] = Omega; A.out.rho[i] = rho; A.out.eta[i] = eta;
+#pragma unroll
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
+        A.out.cell[i] = cell; A.out.tet[i] = tet; A.out.id[i] = id;
+        A.keyOut[i] = ((uint32_t)cell << M.tetBits) | (uint32_t)(tet - __ldg(M.cellTetStart + cell));
+
+        // ---- E15 particle sums / maxima (before particle-number control) ----
+        {
+            const double mpd = massPerDepth(M, pos, m);
+            accS[ACC_DM_PLUS * K1_THREADS] += mpd;
+            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * phi[P.conserved[cs]];
+            accS[ACC_N_ALIVE * K1_THREADS] += 1;
+            accM[ACC_UMAX * K1_THREADS] = fmax(accM[ACC_UMAX * K1_THREADS], mag3(U));
+            accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
+            accM[ACC_ETAMAX * K1_THREADS] = fmax(accM[ACC_ETAMAX * K1_THREADS], eta);
+            accM[ACC_NEG_ETAMIN * K1_THREADS] = fmax(accM[ACC_NEG_ETAMIN * K1_THREADS], -eta);
+            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], Co);
+        }
+    }
+
+    // ---- deterministic CTA reduction of the thread-private accumulators ----
+    __syncthreads();
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // warp w reduces rows w, w+4, ...
+        for (int k = warp; k < ACC_NSUM + ACC_NMAX; k += K1_THREADS / 32) {
+            const bool isMax = k >= ACC_NSUM;
+            double x = isMax ? -PDF_VGREAT : 0.0;
+            for (int t = lane; t < K1_THREADS; t += 32) {
+                const double y = smem[k * K1_THREADS + t];
+                x = isMax ? fmax(x, y) : x + y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double y = __shfl_down_sync(0xffffffffu, x, o);
+                x = isMax ? fmax(x, y) : x + y;
+            }
+            if (lane == 0) {
+                if (isMax) A.partMax[blockIdx.x * ACC_NMAX + (k - ACC_NSUM)] = x;
+                else A.partSum[blockIdx.x * ACC_NSUM + k] = x;
+            }
+        }
+    }
+}

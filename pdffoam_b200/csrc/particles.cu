@@ -1,0 +1,929 @@
+// particles.cu — particle-side kernels and the step orchestration:
+//   k_evolve (evolve_kernel.cuh), radix sort by (cell, tet), segmented per-cell
+//   moment reduction, particle-number control, injection, seeding, I/O.
+// Compiled with -fmad=false (see evolve_kernel.cuh).
+//
+// Reference: mcParticleCloud::evolve (mcParticle/mcParticleCloud/mcParticleCloud.C:1226-1530),
+// updateCloudPDF first half (:929-956), particleNumberControl (:1014-1221),
+// initReleaseParticles (:1534-1629), mcInletOutletBoundary::correct
+// (mcBoundary/mcInletOutletBoundary/mcInletOutletBoundary.C:232-354).
+#include <algorithm>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "cloud.hpp"
+#include "evolve_kernel.cuh"
+
+void fieldsFinalise(Cloud &c, double *partSum, double *partMax, int grid);   // fields.cu
+void commAllreduceMoments(Cloud &c, float *ms);                                // comm.cu
+
+// ---------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------
+__global__ void k_iota(uint32_t *v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+
+__global__ void k_locate(DMesh M, int n, PState S) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S.tet[i] = locateTet(M, mk(S.px[i], S.py[i], S.pz[i]), S.cell[i]);
+}
+
+// fold per-CTA partial rows in index order (one thread per column)
+__global__ void k_fold_rows(int nRows, int nCols, const double *rows, double *out, int isMax) {
+    const int k = threadIdx.x;
+    if (k >= nCols) return;
+    double x = isMax ? -PDF_VGREAT : 0.0;
+    for (int r = 0; r < nRows; ++r) { const double y = rows[(size_t)r * nCols + k]; x = isMax ? fmax(x, y) : x + y; }
+    out[k] = x;
+}
+
+// exclusive scan of an int array in a single CTA (n up to a few million)
+__global__ void k_scan_single(int n, const int *in, int *out, int *total) {
+    __shared__ int warpSums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warpSums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int s = lane < nw ? warpSums[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            warpSums[lane] = s;
+        }
+        __syncthreads();
+        const int before = carry + (warp > 0 ? warpSums[warp - 1] : 0) + (x - v);
+        if (i < n) out[i] = before;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// ---------------------------------------------------------------------------
+// segment bounds of the sorted keys and the per-cell moment reduction
+// ---------------------------------------------------------------------------
+__global__ void k_cell_bounds(int n, const uint32_t *keys, int tetBits, int *cellStart, int *cellEnd, StepScalars *sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    if (k == KEY_DEAD) { if (i == 0) sc->nSorted = 0; return; }
+    const uint32_t c = k >> tetBits;
+    if (i == 0 || (keys[i - 1] >> tetBits) != c) cellStart[c] = i;
+    const uint32_t kn = (i + 1 < n) ? keys[i + 1] : KEY_DEAD;
+    if (kn == KEY_DEAD || (kn >> tetBits) != c) cellEnd[c] = i + 1;
+    if (kn == KEY_DEAD) sc->nSorted = i + 1;
+}
+
+// updateCloudPDF first half (mcParticleCloud.C:929-956): one warp per cell,
+// lanes stride over the cell's segment of the sorted order, butterfly reduction
+// in a fixed order -> deterministic sums without atomics.
+// Block layout per cell: N, M, V, MU(3), MPhi(nPhi), MPhiPhi(nCov), MUU(6).
+template <int NPHI>
+__global__ void k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
+                          double *block, int nMom) {
+    constexpr int NCOV = NPHI * (NPHI + 1) / 2;
+    constexpr int NACC = 11 + NPHI + NCOV;   // all but the count
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    for (int c = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); c < M.nCells; c += gridDim.x * warpsPerBlock) {
+        const int s = cellStart[c], e = cellEnd[c];
+        double a[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+        for (int j = s + lane; j < e; j += 32) {
+            const int slot = (int)perm[j];
+            const V3 U = mk(S.ux[slot], S.uy[slot], S.uz[slot]);
+            double mpd = S.m[slot];
+            if (M.axisym) mpd = massPerDepth(M, mk(S.px[slot], S.py[slot], S.pz[slot]), mpd);
+            mpd = S.eta[slot] * mpd;
+            a[0] += mpd;
+            a[1] += mpd / S.rho[slot];
+            a[2] += mpd * U.x; a[3] += mpd * U.y; a[4] += mpd * U.z;
+            double ph[NPHI > 0 ? NPHI : 1];
+#pragma unroll
+            for (int k = 0; k < NPHI; ++k) { ph[k] = S.phi[k][slot]; a[5 + k] += mpd * ph[k]; }
+            int pp = 0;
+#pragma unroll
+            for (int k = 0; k < NPHI; ++k)
+#pragma unroll
+                for (int l = k; l < NPHI; ++l, ++pp) a[5 + NPHI + pp] += mpd * ph[k] * ph[l];
+            double *uu = a + 5 + NPHI + NCOV;
+            uu[0] += mpd * (U.x * U.x); uu[1] += mpd * (U.x * U.y); uu[2] += mpd * (U.x * U.z);
+            uu[3] += mpd * (U.y * U.y); uu[4] += mpd * (U.y * U.z); uu[5] += mpd * (U.z * U.z);
+        }
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            double x = a[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            a[k] = x;
+        }
+        double *b = block + (size_t)c * nMom;
+        if (lane == 0) b[0] = (double)(e - s);
+        // lanes share the stores
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) if (lane == (k & 31)) b[1 + k] = a[k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// initReleaseParticles (mcParticleCloud.C:1534-1629): one thread per cell
+// ---------------------------------------------------------------------------
+__global__ void k_seed(DMesh M, pdfb200_params P, PState S, RngKey key, int rank, int nRanks, const double *rho_c,
+                       const double *Ufv_c, const double *kfv_c, const double *Phi_c) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M.nCells) return;
+    const int Npc = P.particlesPerCell;
+    const int nLoc = (Npc - rank + nRanks - 1) / nRanks;
+    const double m = M.cellVolumes[c] * rho_c[c] / Npc;
+    const V3 Updf = ld3(Ufv_c, c);
+    const double urms = sqrt(2. / 3. * kfv_c[c]);
+    const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
+    double sumR = 0.;
+    size_t o = (size_t)c * nLoc;
+    for (int j = rank; j < Npc; j += nRanks, ++o) {
+        const uint32_t idx = (uint32_t)((long long)c * Npc + j);
+        const V3 pos = randomPointInCell(M, key, c, idx, RNG_SEED, 0);
+        double g0, g1, g2, g3;
+        rngNormal2(key, idx, 0, RNG_SEED, 1000000, g0, g1);
+        rngNormal2(key, idx, 0, RNG_SEED, 1000001, g2, g3);
+        const V3 U = mk(g0 * urms, g1 * urms, g2 * urms) + Updf;
+        S.px[o] = pos.x; S.py[o] = pos.y; S.pz[o] = pos.z;
+        S.ux[o] = U.x; S.uy[o] = U.y; S.uz[o] = U.z;
+        S.m[o] = m; S.omega[o] = 0; S.rho[o] = 0; S.eta[o] = 1;
+        for (int k = 0; k < P.nPhi; ++k) S.phi[k][o] = Phi_c[(size_t)k * M.nCells + c];
+        S.cell[o] = c; S.tet[o] = locateTet(M, pos, c); S.id[o] = idx;
+        if (M.axisym) sumR += mag3(pos - dot3(pos, ax) * ax);
+    }
+    if (M.axisym) {   // adjustAxiSymmetricMass (:2095-2117)
+        const double alpha = nLoc / sumR;
+        for (size_t q = (size_t)c * nLoc; q < (size_t)(c + 1) * nLoc; ++q) {
+            const V3 pos = mk(S.px[q], S.py[q], S.pz[q]);
+            S.m[q] *= alpha * mag3(pos - dot3(pos, ax) * ax);
+        }
+    }
+}
+
+// localTimeStepping/Omega/reaction correct() on freshly created particles
+// (mcParticleCloud.C:1554-1561)
+__global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const double *nodeMid, const double *cellAux,
+                              int auxStride, const StepScalars *sc, FlameletTables FT) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 pos = mk(S.px[i], S.py[i], S.pz[i]);
+    TetL T;
+    loadTet(M.tets, S.tet[i], T);
+    double w[4];
+    baryAt(T, pos - cellCentre(M, T.cell), w);
+    double val[NODE_MID_STRIDE], pst[4];
+    interpMid(M, P, nodeMid, T, w, val, pst);
+    double eta = 1.0;
+    if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
+    else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
+        V3 Ut = mk(S.ux[i], S.uy[i], S.uz[i]);
+        constrainDir(M.geoD, Ut);
+        eta = fmin(P.CFL / stabilise(sc->deltaT * courantNo(M, T.cell, Ut), PDF_VSMALL), P.ltsUpperBound);
+    }
+    S.eta[i] = eta;
+    S.m[i] = S.m[i] / eta;
+    double Omega = S.omega[i];
+    if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
+    S.omega[i] = Omega;
+    double phi[PDFB200_MAX_PHI];
+#pragma unroll
+    for (int k = 0; k < PDFB200_MAX_PHI; ++k) phi[k] = k < P.nPhi ? S.phi[k][i] : 0.0;
+    double rho = S.rho[i];
+    reactionCorrect(P, FT, Omega, val[NM_ZVAR], cellAux[(size_t)T.cell * auxStride + 1], phi, rho);
+    S.rho[i] = rho;
+#pragma unroll
+    for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k < P.nPhi) S.phi[k][i] = phi[k];
+}
+
+// ---------------------------------------------------------------------------
+// boundaries before the move
+// ---------------------------------------------------------------------------
+// Un_ = n & U_patch on reflecting open patches (mcOpenBoundary.C:92-99)
+__global__ void k_open_un(DMesh M, const double *Ufv_b, double *Un) {
+    const int bf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bf >= M.nBnd) return;
+    const int info = M.bfInfo[bf], h = BF_HANDLER(info);
+    if ((h == PDFB200_BC_OPEN || h == PDFB200_BC_INLET_OUTLET) && BF_REFLECTING(info)) {
+        const double4 n = M.bfNormal[bf];
+        Un[bf] = dot3(mk(n.x, n.y, n.z), ld3(Ufv_b, bf));
+    }
+}
+
+// mcInletOutletBoundary ctor + getU()/getR() (.C:57-151): transforms, fan-triangle
+// probabilities, and the inflow U / R in the face-normal frame, cached at first use
+__global__ void k_inlet_cache(DMesh M, double k0, const double *Ufv_b, const double *Tau_b, double *fwdTrans,
+                              double *probVec, double *inletU, double *inletR) {
+    const int bf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bf >= M.nBnd) return;
+    if (BF_HANDLER(M.bfInfo[bf]) != PDFB200_BC_INLET_OUTLET) return;
+    const int f = M.nInternalFaces + bf;
+    const int s = M.faceStart[f], n = M.faceStart[f + 1] - s;
+    const int s0 = M.faceStart[M.nInternalFaces];
+    const V3 C = ld3(M.faceCentres, f);
+    double area = 0;
+    for (int i1 = 0, i2 = 1; i1 < n; ++i1, ++i2) {
+        if (i2 == n) i2 = 0;
+        const V3 v1 = ld3(M.points, M.facePoints[s + i1]) - C, v2 = ld3(M.points, M.facePoints[s + i2]) - C;
+        area += mag3(cross3(v1, v2));
+        probVec[s - s0 + i1] = area;
+    }
+    for (int i = 0; i < n; ++i) probVec[s - s0 + i] /= area;
+    const double4 nn = M.bfNormal[bf];
+    double T[9];
+    rotationTensor(mk(-nn.x, -nn.y, -nn.z), mk(1.0, 0.0, 0.0), T);
+    for (int k = 0; k < 9; ++k) fwdTrans[9 * (size_t)bf + k] = T[k];
+    st3(inletU, bf, xform(T, ld3(Ufv_b, bf)));
+    const double *tb = Tau_b + 6 * (size_t)bf;
+    const double Sm[9] = {tb[0], tb[1], tb[2], tb[1], tb[3], tb[4], tb[2], tb[4], tb[5]};
+    double TS[9], R[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double v = 0; for (int k = 0; k < 3; ++k) v += T[3 * i + k] * Sm[3 * k + j]; TS[3 * i + j] = v; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double v = 0; for (int k = 0; k < 3; ++k) v += TS[3 * i + k] * T[3 * j + k]; R[3 * i + j] = v; }
+    double *r = inletR + 6 * (size_t)bf;
+    r[0] = fmax(R[0], k0); r[1] = fmax(R[1], -PDF_GREAT); r[2] = fmax(R[2], -PDF_GREAT);
+    r[3] = fmax(R[4], k0); r[4] = fmax(R[5], -PDF_GREAT); r[5] = fmax(R[8], k0);
+}
+
+// mcInletRandom (mcInletRandom.C:92-108, mcInletRandomI.H:28-39) + inversion
+// generator (mcInversionInletRandom.C:63-119)
+struct InletRnd {
+    double UMean, b, b2, expmU2b2, UbSqrtPi, erfUb, denom, b22denom, Q, m;
+    __device__ void updateCoeffs(double UMean_, double uRms) {
+        UMean = UMean_;
+        b = 0.70710678118654752440 / uRms;
+        b2 = b * b;
+        expmU2b2 = exp(-UMean * UMean * b2);
+        UbSqrtPi = UMean * b * sqrt(3.14159265358979323846);
+        erfUb = erf(UMean * b);
+        denom = expmU2b2 + UbSqrtPi * (1. + erfUb);
+        b22denom = 2. * b2 / denom;
+        Q = 0.5 * (UMean + expmU2b2 / (b * sqrt(3.14159265358979323846)) + UMean * erfUb);
+        m = 0.5 * (UMean * b + sqrt(2.0 + UMean * UMean * b2)) / b;
+    }
+    __device__ double PDF(double x) const { const double xp = x - UMean; return b22denom * exp(-b2 * xp * xp) * x; }
+    __device__ double CDF(double x) const { x -= UMean; return (expmU2b2 - exp(-b2 * x * x) + UbSqrtPi * (erfUb + erf(b * x))) / denom; }
+    __device__ double value(double U01) const {
+        const double d = ((U01 - CDF(m)) >= 0 ? 1.0 : -1.0) * PDF_SMALL;
+        double x0 = m + d;
+        int nIter = 0;
+        do {
+            const double fval = CDF(x0) - U01, fder = PDF(x0);
+            if (fabs(fder) < PDF_VSMALL) return x0;
+            const double x = x0 - fval / fder;
+            if (fabs(x - x0) < 1e-8) return x;
+            x0 = x;
+            ++nIter;
+        } while (nIter < 50);
+        return x0;
+    }
+};
+
+// mcInletOutletBoundary::correct(false) (.C:232-354): one thread per boundary
+// face runs the sequential `while (mGen < mIn)` loop; pass 0 counts, pass 1
+// regenerates the same particles (counter-based RNG) and writes them at the
+// offsets of an exclusive scan, so slots and ids are deterministic.
+__global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey key, StepScalars *sc, const double *Un,
+                         const double *rho_b, const double *Phi_b, const double *inletU, const double *inletR,
+                         const double *fwdTrans, const double *probVec, const double *nodeMid, int *count,
+                         const int *offset, int *injPatchTail, double *injSums, int nRanks, int rank, long long capacity) {
+    const int bf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bf >= M.nBnd) return;
+    const int info = M.bfInfo[bf];
+    if (pass == 0) count[bf] = 0;
+    if (pass == 1) for (int k = 0; k < K1_NC1; ++k) injSums[(size_t)bf * K1_NC1 + k] = 0;
+    if (BF_HANDLER(info) != PDFB200_BC_INLET_OUTLET) return;
+    if ((bf % nRanks) != rank) return;          // inflow faces are dealt round-robin to the ranks
+    if (Un[bf] > 0) return;                     // outlet face
+    if (pass == 1 && count[bf] == 0) return;
+    const int f = M.nInternalFaces + bf, cellI = M.owner[f];
+    const double deltaT = sc->deltaT;
+    const uint32_t step = sc->step;
+    InletRnd inrnd;
+    const V3 Uloc = ld3(inletU, bf);
+    const double *R = inletR + 6 * (size_t)bf;
+    inrnd.updateCoeffs(Uloc.x, sqrt(R[0]));
+    const double mp = rho_b[bf] * M.cellVolumes[cellI] / P.particlesPerCell;
+    const double mIn = rho_b[bf] * inrnd.Q * M.magSf[f] * deltaT;
+    const double *T = fwdTrans + 9 * (size_t)bf;
+    const int s = M.faceStart[f], n = M.faceStart[f + 1] - s, s0 = M.faceStart[M.nInternalFaces];
+    const double *wv = probVec + (s - s0);
+    const V3 C = ld3(M.faceCentres, f), Sf = ld3(M.faceAreas, f);
+    const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
+    const int nGen = pass == 1 ? count[bf] : 0;
+    // pass 1 needs sum(r) of the batch first (adjustAxiSymmetricMass)
+    double sumR = 0.;
+    const int loops = (pass == 1 && M.axisym) ? 2 : 1;
+    for (int loop = 0; loop < loops; ++loop) {
+        const bool writing = pass == 1 && loop == loops - 1;
+        double mGen = 0;
+        uint32_t kDraw = 0;
+        int made = 0;
+        while (mGen < mIn) {
+            double uVal, uTri, n1, n2, a1, a2, uAcc, dummy;
+            rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 0, uVal, uTri);
+            rngNormal2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 1, n1, n2);
+            rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 2, a1, a2);
+            rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 3, uAcc, dummy);
+            ++kDraw;
+            // randomVelocity (.C:215-229): U_global = revTrans & Up = fwdTrans^T & Up
+            const V3 UpL = mk(inrnd.value(uVal), Uloc.y + sqrt(R[3]) * n1, Uloc.z + sqrt(R[5]) * n2);
+            const V3 Up = mk(T[0] * UpL.x + T[3] * UpL.y + T[6] * UpL.z, T[1] * UpL.x + T[4] * UpL.y + T[7] * UpL.z,
+                             T[2] * UpL.x + T[5] * UpL.y + T[8] * UpL.z);
+            // randomPoint (.C:179-212)
+            int idx1 = 0;
+            while (idx1 < n && wv[idx1] < uTri) ++idx1;   // lower_bound
+            int idx2 = idx1 + 1;
+            if (idx2 == n) idx2 = 0;
+            if (idx1 == n) idx1 = n - 1;                  // uTri beyond the last entry (== 1 up to round-off)
+            if (a1 + a2 > 1.0) { a1 = 1.0 - a1; a2 = 1.0 - a2; }
+            V3 pos = ((a1 * ld3(M.points, M.facePoints[s + idx1]) + a2 * ld3(M.points, M.facePoints[s + idx2])) + (1.0 - a1 - a2) * C) - PDF_SMALL * Sf;
+            if (M.nGeoD <= 2) constrainDir(M.geoD, pos);
+            // local time stepping of the new particle
+            const int tet = locateTet(M, pos, cellI);
+            double eta = 1.0;
+            if (P.localTimeStepping == PDFB200_LTS_CELL) {
+                TetL TL;
+                loadTet(M.tets, tet, TL);
+                double w[4], val[NODE_MID_STRIDE], pst[4];
+                baryAt(TL, pos - cellCentre(M, cellI), w);
+                interpMid(M, P, nodeMid, TL, w, val, pst);
+                eta = val[NM_ETA];
+            } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
+                V3 Ut = Up;
+                constrainDir(M.geoD, Ut);
+                eta = fmin(P.CFL / stabilise(deltaT * courantNo(M, cellI, Ut), PDF_VSMALL), P.ltsUpperBound);
+            }
+            const double m = mp / eta;
+            if (mGen + m > mIn) {
+                if (uAcc > (mIn - mGen) / m) break;
+            }
+            if (pass == 1 && loop == 0 && M.axisym) sumR += mag3(pos - dot3(pos, ax) * ax);
+            if (writing) {
+                const long long tailIdx = (long long)sc->nInjStart + offset[bf] + made;
+                const long long slot = (long long)sc->nSlots + tailIdx;
+                if (slot < capacity) {
+                    double mm = m;
+                    if (M.axisym) mm *= (nGen / sumR) * mag3(pos - dot3(pos, ax) * ax);
+                    S.px[slot] = pos.x; S.py[slot] = pos.y; S.pz[slot] = pos.z;
+                    S.ux[slot] = Up.x; S.uy[slot] = Up.y; S.uz[slot] = Up.z;
+                    S.m[slot] = mm; S.omega[slot] = 0; S.rho[slot] = 0; S.eta[slot] = eta;
+                    const double mpd = massPerDepth(M, pos, mm);
+                    injSums[(size_t)bf * K1_NC1] += mpd;
+                    for (int k = 0; k < P.nPhi; ++k) {
+                        const double ph = Phi_b[(size_t)k * M.nBnd + bf];
+                        S.phi[k][slot] = ph;
+                    }
+                    for (int cs = 0; cs < P.nConserved; ++cs) injSums[(size_t)bf * K1_NC1 + 1 + cs] += mpd * Phi_b[(size_t)P.conserved[cs] * M.nBnd + bf];
+                    S.cell[slot] = cellI; S.tet[slot] = tet;
+                    S.id[slot] = sc->nextId + (uint32_t)(offset[bf] + made) * (uint32_t)nRanks;
+                    injPatchTail[tailIdx] = BF_PATCH(info);
+                }
+            }
+            mGen += m;
+            ++made;
+        }
+        if (pass == 0) count[bf] = made;
+    }
+}
+
+__global__ void k_inject_finish(int nBnd, const int *total, StepScalars *sc, long long capacity, int nRanks) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int t = *total;
+    if ((long long)sc->nSlots + sc->nTail + t > capacity) { sc->overflow = 1; t = max(0, (int)(capacity - sc->nSlots - sc->nTail)); }
+    sc->nTail += t;
+    sc->nextId += (uint32_t)t * (uint32_t)nRanks;
+}
+
+// ---------------------------------------------------------------------------
+// particle-number control (mcParticleCloud.C:1014-1221)
+// ---------------------------------------------------------------------------
+__global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, const int *cellStart, const int *cellEnd,
+                              int *flag, int *nClone, int nRanks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M.nCells) return;
+    const int Npc = P.particlesPerCell;
+    const int np = (int)round(PaNIC[c]);
+    int fl = 0, n = 0;
+    if (np < 1) fl = -1;
+    else if (np < round(Npc * P.cloneAt)) fl = 1;
+    else if (np > round(Npc * P.eliminateAt)) fl = 2;
+    if (fl == 1) {
+        n = min(np, Npc - np);
+        const int nLocal = cellEnd[c] - cellStart[c];
+        if (nRanks > 1) n = (int)fmin((double)nLocal, floor((double)n * nLocal / np + 0.5));
+        n = min(n, nLocal);
+    }
+    flag[c] = fl; nClone[c] = n;
+}
+
+// one warp per flagged cell
+__global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
+                           const int *cellEnd, const int *flag, const int *nClone, const int *cloneOffset,
+                           double *PaNIC, StepScalars *sc, RngKey key, int rank, int nRanks, long long capacity,
+                           double *ncDelta, int *ncCounts /* [2]: cloned, eliminated */) {
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const uint32_t step = sc->step;
+    for (int c = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); c < M.nCells; c += gridDim.x * warpsPerBlock) {
+        const int fl = flag[c];
+        if (fl <= 0) continue;
+        const int s = cellStart[c], e = cellEnd[c];
+        double dsum[K1_NC1];
+#pragma unroll
+        for (int k = 0; k < K1_NC1; ++k) dsum[k] = 0;
+        if (fl == 1) {
+            // cloneParticles (:1107-1139): the n heaviest by eta*m (ties by id) are split
+            const int n = nClone[c];
+            unsigned long long split[2] = {0ull, 0ull};   // which of this lane's entries get halved (<= 128 per lane)
+            int it = 0;
+            for (int j = s + lane; j < e; j += 32, ++it) {
+                const int slot = (int)perm[j];
+                const double key_i = S.eta[slot] * S.m[slot];
+                const uint32_t id_i = S.id[slot];
+                int rk = 0;
+                for (int q = s; q < e; ++q) {
+                    const int sq = (int)perm[q];
+                    const double kq = S.eta[sq] * S.m[sq];
+                    if (kq > key_i || (kq == key_i && S.id[sq] < id_i)) ++rk;
+                }
+                if (rk < n && it < 128) {
+                    split[it >> 6] |= 1ull << (it & 63);
+                    const long long tailIdx = cloneOffset[c] + rk;
+                    const long long dst = (long long)sc->nSlots + tailIdx;
+                    if (dst >= capacity) { sc->overflow = 1; continue; }
+                    const V3 posOld = mk(S.px[slot], S.py[slot], S.pz[slot]);
+                    const V3 pos = randomPointInCell(M, key, c, id_i, RNG_CLONE_POS, step);
+                    const double mOld = S.m[slot];
+                    const double mHalf = mOld / 2.0;
+                    S.px[dst] = pos.x; S.py[dst] = pos.y; S.pz[dst] = pos.z;
+                    S.ux[dst] = S.ux[slot]; S.uy[dst] = S.uy[slot]; S.uz[dst] = S.uz[slot];
+                    S.m[dst] = mHalf; S.omega[dst] = S.omega[slot]; S.rho[dst] = S.rho[slot]; S.eta[dst] = S.eta[slot];
+                    for (int k = 0; k < P.nPhi; ++k) S.phi[k][dst] = S.phi[k][slot];
+                    S.cell[dst] = c; S.tet[dst] = locateTet(M, pos, c);
+                    S.id[dst] = sc->nextId + (uint32_t)tailIdx * (uint32_t)nRanks;
+                    if (M.axisym) {
+                        const double d = massPerDepth(M, pos, mHalf) + massPerDepth(M, posOld, mHalf) - massPerDepth(M, posOld, mOld);
+                        dsum[0] += d;
+                        for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
+                    }
+                }
+            }
+            __syncwarp();
+            // halve the sources only after every lane has ranked against the old masses
+            it = 0;
+            for (int j = s + lane; j < e; j += 32, ++it) {
+                if (it < 128 && ((split[it >> 6] >> (it & 63)) & 1ull)) {
+                    const int slot = (int)perm[j];
+                    S.m[slot] = S.m[slot] / 2.0;
+                }
+            }
+            if (lane == 0) { PaNIC[c] += n; atomicAdd(ncCounts, n); }
+        } else {
+            // eliminateParticles (:1143-1221)
+            const int ncur = (int)round(PaNIC[c]);
+            const int nx = ncur - P.particlesPerCell;
+            const double Psel = (2. * nx) / ncur;
+            double mA = 0., mB = 0.;
+            for (int j = s + lane; j < e; j += 32) {
+                const int slot = (int)perm[j];
+                double u1, u2;
+                rngUniform2(key, S.id[slot], step, RNG_NC_PARTICLE, 0, u1, u2);
+                if (u1 < Psel) {
+                    const double meta = S.eta[slot] * S.m[slot];
+                    if (u2 < 0.5) mA += meta; else mB += meta;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { mA += __shfl_xor_sync(0xffffffffu, mA, o); mB += __shfl_xor_sync(0xffffffffu, mB, o); }
+            if (mA > 0 || mB > 0) {
+                const double Pd = mB / (mA + mB);
+                double u, dummy;
+                rngUniform2(key, (uint32_t)c, step, RNG_NC_CELL, (uint32_t)rank, u, dummy);
+                const bool delA = u < Pd;
+                const double sfac = delA ? 1. / Pd : (mA + mB) / mA;
+                int nKilled = 0;
+                for (int j = s + lane; j < e; j += 32) {
+                    const int slot = (int)perm[j];
+                    double u1, u2;
+                    rngUniform2(key, S.id[slot], step, RNG_NC_PARTICLE, 0, u1, u2);
+                    if (u1 < Psel) {
+                        const bool inA = u2 < 0.5;
+                        const V3 pos = mk(S.px[slot], S.py[slot], S.pz[slot]);
+                        const double mOld = S.m[slot];
+                        double d;
+                        if (inA == delA) { S.cell[slot] = -1; ++nKilled; d = -massPerDepth(M, pos, mOld); }
+                        else { const double mNew = mOld * sfac; S.m[slot] = mNew; d = massPerDepth(M, pos, mNew) - massPerDepth(M, pos, mOld); }
+                        dsum[0] += d;
+                        for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nKilled += __shfl_xor_sync(0xffffffffu, nKilled, o);
+                if (lane == 0) { PaNIC[c] -= nKilled; atomicAdd(ncCounts + 1, nKilled); }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K1_NC1; ++k) {
+            double x = dsum[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) ncDelta[(size_t)c * K1_NC1 + k] = x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// end of step: lost-mass shares, report scalars, next deltaT
+// ---------------------------------------------------------------------------
+struct DevReport {
+    double v[64];
+};
+// layout of DevReport.v
+#define RP_K1SUM 0                       // ACC_NSUM entries
+#define RP_K1MAX (RP_K1SUM + ACC_NSUM)   // ACC_NMAX entries
+#define RP_CELLSUM (RP_K1MAX + ACC_NMAX) // 3: sum|rhoErr|, totalMass, totalParticleMass
+#define RP_CELLMAX (RP_CELLSUM + 3)      // 2: -rhoErrMin, rhoErrMax
+#define RP_NCDELTA (RP_CELLMAX + 2)      // K1_NC1
+#define RP_INJ (RP_NCDELTA + K1_NC1)     // K1_NC1
+#define RP_LOSTSUM (RP_INJ + K1_NC1)     // 1: total lost mass re-spread
+#define RP_END (RP_LOSTSUM + 1)
+static_assert(RP_END <= 64, "DevReport too small");
+
+// lostMass_/max(PaNIC,1) (mcParticleCloud.C:1363-1369); partial sums of what is re-spread
+__global__ void k_lost_share(int nCells, const double *lostMass, const double *PaNIC, const int *cellStart,
+                             const int *cellEnd, const int *nClone, double *lostShare, double *partial) {
+    __shared__ double sm[32];
+    double v[1] = {0.0};
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
+        const double sh = lostMass[c] / fmax(PaNIC[c], 1.);
+        lostShare[c] = sh;
+        v[0] += sh * (double)((cellEnd[c] - cellStart[c]) + (nClone ? nClone[c] : 0));
+    }
+    blockReduce<1, false>(v, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
+}
+
+// column sums of an [n][K1_NC1] array: per-CTA partial rows (folded by k_fold_rows)
+__global__ void k_colsum_nc1(int n, const double *in, double *partial) {
+    __shared__ double sm[K1_NC1 * 32];
+    double v[K1_NC1];
+#pragma unroll
+    for (int k = 0; k < K1_NC1; ++k) v[k] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < K1_NC1; ++k) v[k] += in[(size_t)i * K1_NC1 + k];
+    blockReduce<K1_NC1, false>(v, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < K1_NC1; ++k) partial[blockIdx.x * K1_NC1 + k] = v[k];
+}
+
+__global__ void k_set_slots(StepScalars *sc, int total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSlots = total;
+}
+
+__global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int nTailClones, const int *ncCounts,
+                           int total, int nRanksForId) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double CoMax = rp->v[RP_K1MAX + ACC_COMAX];
+    if (CoMax > 0) sc->deltaT = P.CFL / CoMax;
+    sc->step += 1;
+    sc->nSlots = total;
+    const int nCl = ncCounts ? ncCounts[0] : 0;
+    sc->nTail = nCl;
+    sc->nInjStart = nCl;
+    sc->nextId += (uint32_t)nCl * (uint32_t)nRanksForId;
+    sc->anyLost = rp->v[RP_K1SUM + ACC_N_LOST] > 0 ? 1 : 0;
+    sc->nLostTotal += (long long)rp->v[RP_K1SUM + ACC_N_LOST];
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+static RngKey makeKey(uint64_t seed) {
+    RngKey k;
+    k.k0 = (uint32_t)(seed & 0xffffffffu);
+    k.k1 = (uint32_t)(seed >> 32);
+    return k;
+}
+
+static FlameletTables tablesOf(const Cloud &c) {
+    FlameletTables f;
+    f.chi = c.flChi.p; f.z = c.flZ.p; f.fields = c.flFields.p; f.nChi = c.nChi; f.nZ = c.nZ;
+    return f;
+}
+
+void Cloud::allocParticles() {
+    if (!stateAllocs.empty()) return;
+    const size_t cap = (size_t)capacity;
+    auto allocD = [&](double *&p) { CUDA_CHECK(cudaMalloc((void **)&p, cap * sizeof(double))); stateAllocs.push_back(p); };
+    auto allocI = [&](int *&p) { CUDA_CHECK(cudaMalloc((void **)&p, cap * sizeof(int))); stateAllocs.push_back(p); };
+    for (int b = 0; b < 2; ++b) {
+        PState &s = S[b];
+        allocD(s.px); allocD(s.py); allocD(s.pz); allocD(s.ux); allocD(s.uy); allocD(s.uz);
+        allocD(s.m); allocD(s.omega); allocD(s.rho); allocD(s.eta);
+        for (int k = 0; k < PDFB200_MAX_PHI; ++k) { s.phi[k] = nullptr; if (k < prm.nPhi) allocD(s.phi[k]); }
+        allocI(s.cell); allocI(s.tet);
+        int *idp; allocI(idp); s.id = reinterpret_cast<uint32_t *>(idp);
+    }
+    keysA.alloc(cap); keysB.alloc(cap); valsB.alloc(cap); iota.alloc(cap);
+    LAUNCH(this, k_iota, gridFor((long long)cap, 256), 256, 0, iota.p, (int)cap);
+    injPatchTail.alloc(cap);
+    size_t tempBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, (int)cap, 0, keyBits + 1, stream);
+    cubTemp.alloc(tempBytes + 256);
+    cellStart.alloc(nCells); cellEnd.alloc(nCells); ncFlag.alloc(nCells); ncCount.alloc(nCells + 1); ncOffset.alloc(nCells + 1);
+    scanTmp.alloc(8);
+    injCount.alloc(std::max(nBnd, 1)); injOffset.alloc(std::max(nBnd, 1) + 1); injSums.alloc((size_t)std::max(nBnd, 1) * K1_NC1);
+    ncDelta.alloc((size_t)nCells * K1_NC1);
+    Un.alloc(std::max(nBnd, 1)); Un.zero(stream);
+    inletU.alloc((size_t)std::max(nBnd, 1) * 3); inletR.alloc((size_t)std::max(nBnd, 1) * 6); fwdTrans.alloc((size_t)std::max(nBnd, 1) * 9);
+    probVec.alloc(std::max<size_t>(hFaceStart[nFaces] - hFaceStart[nInternalFaces], 1));
+    const int maxGrid = numSMs * 16;
+    k1PartSum.alloc((size_t)maxGrid * ACC_NSUM); k1PartMax.alloc((size_t)std::max(maxGrid * ACC_NMAX, numSMs * 64));
+    cellPartSum.alloc((size_t)maxGrid * 8); finalSums.alloc(256);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void Cloud::seedParticles() {
+    if (!haveMoments) throw std::logic_error("seed_particles: init_moments first");
+    allocParticles();
+    const int Npc = prm.particlesPerCell;
+    const int nLoc = (Npc - rank + nRanks - 1) / nRanks;
+    const long long n = (long long)nCells * nLoc;
+    if (n > capacity) throw std::length_error("seed_particles: capacity too small");
+    cur = 0;
+    prepareFields();
+    LAUNCH(this, k_seed, gridFor(nCells, 64), 64, 0, dm, prm, S[cur], makeKey(prm.seed), rank, nRanks, rho_c.p, Ufv_c.p, kfv_c.p, Phi_c.p);
+    LAUNCH(this, k_init_models, gridFor(n, 128), 128, 0, dm, prm, S[cur], (int)n, nodeMid.p, cellAux.p, cellAuxStride, scal.p, tablesOf(*this));
+    StepScalars h = *hScal;
+    h.nSorted = 0; h.nTail = (int)n; h.nInjStart = (int)n; h.nSlots = 0; h.anyLost = 0;
+    h.nextId = (uint32_t)((long long)nCells * Npc + rank);
+    *hScal = h;
+    CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    nParticlesHost = n; nSlotsHost = 0; sortedValid = false;
+}
+
+void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
+    allocParticles();
+    if (n > capacity) throw std::length_error("upload_particles: capacity too small");
+    if (!p.pos || !p.U || !p.m || !p.Omega || !p.rho || !p.eta || !p.cell) throw std::invalid_argument("upload_particles: null column");
+    cur = 0;
+    PState &s = S[cur];
+    std::vector<double> tmp((size_t)n);
+    auto upStrided = [&](double *dst, const double *src, int comp) {
+        for (int64_t i = 0; i < n; ++i) tmp[i] = src[3 * i + comp];
+        CUDA_CHECK(cudaMemcpy(dst, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    };
+    upStrided(s.px, p.pos, 0); upStrided(s.py, p.pos, 1); upStrided(s.pz, p.pos, 2);
+    upStrided(s.ux, p.U, 0); upStrided(s.uy, p.U, 1); upStrided(s.uz, p.U, 2);
+    auto up = [&](double *dst, const double *src) { CUDA_CHECK(cudaMemcpy(dst, src, n * sizeof(double), cudaMemcpyHostToDevice)); };
+    up(s.m, p.m); up(s.omega, p.Omega); up(s.rho, p.rho); up(s.eta, p.eta);
+    for (int k = 0; k < prm.nPhi; ++k) { if (!p.Phi[k]) throw std::invalid_argument("upload_particles: null scalar column"); up(s.phi[k], p.Phi[k]); }
+    CUDA_CHECK(cudaMemcpy(s.cell, p.cell, n * sizeof(int), cudaMemcpyHostToDevice));
+    if (p.id) CUDA_CHECK(cudaMemcpy(s.id, p.id, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    else CUDA_CHECK(cudaMemcpy(s.id, iota.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    if (p.tet) CUDA_CHECK(cudaMemcpy(s.tet, p.tet, n * sizeof(int), cudaMemcpyHostToDevice));
+    else LAUNCH(this, k_locate, gridFor(n, 128), 128, 0, dm, (int)n, s);
+    StepScalars h = *hScal;
+    h.nSorted = 0; h.nTail = (int)n; h.nInjStart = (int)n; h.nSlots = 0; h.anyLost = 0;
+    h.nextId = (uint32_t)n + (uint32_t)rank;
+    *hScal = h;
+    CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    nParticlesHost = n; nSlotsHost = 0; sortedValid = false;
+}
+
+// gathers column `src` through idx (or identity for the tail) into `dst`
+__global__ void k_gather_d(int n, int nSorted, int nSlots, const uint32_t *perm, const double *src, double *dst, const int *cell, int *alive) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = i < nSorted ? (int)perm[i] : nSlots + (i - nSorted);
+    dst[i] = src[slot];
+    if (alive) alive[i] = cell[slot] >= 0;
+}
+__global__ void k_gather_i(int n, int nSorted, int nSlots, const uint32_t *perm, const int *src, int *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = i < nSorted ? (int)perm[i] : nSlots + (i - nSorted);
+    dst[i] = src[slot];
+}
+
+void Cloud::downloadParticles(int64_t maxn, pdfb200_particles &out, int64_t *nOut) {
+    CUDA_CHECK(cudaMemcpy(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost));
+    const int nSorted = hScal->nSorted, nTail = hScal->nTail, nSlots = hScal->nSlots;
+    const int n = nSorted + nTail;
+    // logical order: sorted particles, then the tail; eliminated ones (cell < 0) are skipped
+    DBuf<double> d; d.alloc(std::max(n, 1));
+    DBuf<int> di, alive; di.alloc(std::max(n, 1)); alive.alloc(std::max(n, 1));
+    std::vector<double> h(n);
+    std::vector<int> hi(n), hal(n);
+    const uint32_t *perm = valsB.p;
+    const PState &s = S[cur];
+    const int B = 256, G = gridFor(n, B);
+    auto col = [&](const double *src) {
+        if (n) { LAUNCH(this, k_gather_d, G, B, 0, n, nSorted, nSlots, perm, src, d.p, s.cell, alive.p); d.download(h.data(), n, stream); alive.download(hal.data(), n, stream); }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    };
+    auto coli = [&](const int *src) {
+        if (n) { LAUNCH(this, k_gather_i, G, B, 0, n, nSorted, nSlots, perm, src, di.p); di.download(hi.data(), n, stream); }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    };
+    col(s.m);
+    int64_t na = 0;
+    for (int i = 0; i < n; ++i) na += hal[i] != 0;
+    if (na > maxn) throw std::length_error("download_particles: buffer too small");
+    std::vector<int> aliveIdx; aliveIdx.reserve(na);
+    for (int i = 0; i < n; ++i) if (hal[i]) aliveIdx.push_back(i);
+    auto put = [&](double *dst, int stride, int comp) { if (dst) for (int64_t k = 0; k < na; ++k) dst[stride * k + comp] = h[aliveIdx[k]]; };
+    put(out.m, 1, 0);
+    col(s.px); put(out.pos, 3, 0); col(s.py); put(out.pos, 3, 1); col(s.pz); put(out.pos, 3, 2);
+    col(s.ux); put(out.U, 3, 0); col(s.uy); put(out.U, 3, 1); col(s.uz); put(out.U, 3, 2);
+    col(s.omega); put(out.Omega, 1, 0); col(s.rho); put(out.rho, 1, 0); col(s.eta); put(out.eta, 1, 0);
+    for (int k = 0; k < prm.nPhi; ++k) { col(s.phi[k]); put(out.Phi[k], 1, 0); }
+    coli(s.cell); if (out.cell) for (int64_t k = 0; k < na; ++k) out.cell[k] = hi[aliveIdx[k]];
+    coli(s.tet); if (out.tet) for (int64_t k = 0; k < na; ++k) out.tet[k] = hi[aliveIdx[k]];
+    coli(reinterpret_cast<const int *>(s.id)); if (out.id) for (int64_t k = 0; k < na; ++k) out.id[k] = (uint32_t)hi[aliveIdx[k]];
+    *nOut = na;
+}
+
+// ---------------------------------------------------------------------------
+// one time step
+// ---------------------------------------------------------------------------
+template <int N>
+static void launchMoments(Cloud &c, const PState &S, const uint32_t *perm) {
+    const int B = 256, warps = B / 32;
+    const int G = std::min(gridFor(c.nCells, warps), c.numSMs * 16);
+    LAUNCH(&c, k_moments<N>, G, B, 0, c.dm, S, perm, c.cellStart.p, c.cellEnd.p, c.momentBlock.p, c.nMom);
+}
+
+void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
+    if (!haveMoments) throw std::logic_error("evolve: fields/moments not initialised");
+    if (stateAllocs.empty()) throw std::logic_error("evolve: no particles (seed_particles or upload_particles first)");
+    if (prm.nConserved > K1_MAXCONS) throw std::invalid_argument("evolve: at most 3 conserved scalars are supported");
+    const RngKey key = makeKey(prm.seed);
+    DevReport *dRep = reinterpret_cast<DevReport *>(finalSums.p + 128);
+    DBuf<int> ncCounts; ncCounts.alloc(2);
+    CUDA_CHECK(cudaEventRecord(evStart, stream));
+    int k1Blocks = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k_evolve, K1_THREADS, (ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double)));
+    k1Blocks = std::max(1, std::min(k1Blocks, 16));
+
+    for (int st = 0; st < nSteps; ++st) {
+        // ---- cell-side preparation (all updateInternals) ----
+        prepareFields();
+        int nInjected = 0;
+        if (hasOpen) LAUNCH(this, k_open_un, gridFor(nBnd, 128), 128, 0, dm, Ufv_b.p, Un.p);
+        if (hasInlet) {
+            if (!inletCached) {
+                LAUNCH(this, k_inlet_cache, gridFor(nBnd, 128), 128, 0, dm, prm.k0, Ufv_b.p, Tau_b.p, fwdTrans.p, probVec.p, inletU.p, inletR.p);
+                inletCached = true;
+            }
+            for (int pass = 0; pass < 2; ++pass) {
+                LAUNCH(this, k_inject, gridFor(nBnd, 64), 64, 0, dm, prm, pass, S[cur], key, scal.p, Un.p, rho_b.p, Phi_b.p, inletU.p,
+                       inletR.p, fwdTrans.p, probVec.p, nodeMid.p, injCount.p, injOffset.p, injPatchTail.p, injSums.p, nRanks, rank,
+                       (long long)capacity);
+                if (pass == 0) LAUNCH(this, k_scan_single, 1, 1024, 0, nBnd, injCount.p, injOffset.p, scanTmp.p);
+            }
+            LAUNCH(this, k_inject_finish, 1, 32, 0, nBnd, scanTmp.p, scal.p, (long long)capacity, nRanks);
+            const int gI = std::min(gridFor(nBnd, 256), numSMs * 2);
+            LAUNCH(this, k_colsum_nc1, gI, 256, 0, nBnd, injSums.p, k1PartSum.p);
+            LAUNCH(this, k_fold_rows, 1, 32, 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
+        } else {
+            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_INJ, 0, K1_NC1 * sizeof(double), stream));
+        }
+        // the host needs the entry count to size the sort
+        CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
+        const int nSorted = hScal->nSorted, nTail = hScal->nTail;
+        const int total = nSorted + nTail;
+        nInjected = nTail - hScal->nInjStart;
+        if (total > capacity) throw std::length_error("evolve: particle capacity exceeded");
+        const double dtUsed = hScal->deltaT;
+
+        // ---- the fused particle kernel ----
+        K1Args A;
+        A.M = dm; A.P = prm; A.in = S[cur]; A.out = S[cur ^ 1];
+        A.perm = valsB.p; A.keyOut = keysA.p; A.sc = scal.p;
+        A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride;
+        A.Un = Un.p; A.lostShare = lostShare.p; A.lostMass = lostMass.p; A.injPatchTail = injPatchTail.p;
+        A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ;
+        A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
+        const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
+        CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
+        LAUNCH(this, k_evolve, gridK1, K1_THREADS, (ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double), A);
+        LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
+        LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
+        cur ^= 1;
+
+        // ---- radix sort by (cell, tet) + segment bounds + moments ----
+        size_t tempBytes = cubTemp.n;
+        if (total > 0)
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
+        CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
+        CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
+        if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellStart.p, cellEnd.p, scal.p);
+        else { hScal->nSorted = 0; }
+        switch (prm.nPhi) {
+        case 0: launchMoments<0>(*this, S[cur], valsB.p); break;
+        case 1: launchMoments<1>(*this, S[cur], valsB.p); break;
+        case 2: launchMoments<2>(*this, S[cur], valsB.p); break;
+        case 3: launchMoments<3>(*this, S[cur], valsB.p); break;
+        case 4: launchMoments<4>(*this, S[cur], valsB.p); break;
+        case 5: launchMoments<5>(*this, S[cur], valsB.p); break;
+        default: launchMoments<6>(*this, S[cur], valsB.p); break;
+        }
+        // ---- cross-GPU sum of the moment block ----
+        float arMs = 0;
+        if (nRanks > 1) commAllreduceMoments(*this, &arMs);
+
+        // ---- time-averaging, mean fields, boundary conditions ----
+        const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
+        fieldsFinalise(*this, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, gF);
+        LAUNCH(this, k_fold_rows, 1, 32, 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
+        LAUNCH(this, k_fold_rows, 1, 32, 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
+
+        // ---- particle-number control ----
+        CUDA_CHECK(cudaMemsetAsync(ncCounts.p, 0, 2 * sizeof(int), stream));
+        const bool nc = prm.particleNumberControl != 0;
+        if (nc) {
+            LAUNCH(this, k_nc_classify, gridFor(nCells, 256), 256, 0, dm, prm, PaNIC.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, nRanks);
+            LAUNCH(this, k_scan_single, 1, 1024, 0, nCells, ncCount.p, ncOffset.p, scanTmp.p + 1);
+            CUDA_CHECK(cudaMemsetAsync(ncDelta.p, 0, (size_t)nCells * K1_NC1 * sizeof(double), stream));
+            // nSlots for the clones = this step's entry count
+            LAUNCH(this, k_set_slots, 1, 32, 0, scal.p, total);
+            const int gN = std::min(gridFor(nCells, 8), numSMs * 16);
+            LAUNCH(this, k_nc_apply, gN, 256, 0, dm, prm, S[cur], valsB.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, ncOffset.p,
+                   PaNIC.p, scal.p, key, rank, nRanks, (long long)capacity, ncDelta.p, ncCounts.p);
+            // fold ncDelta over cells deterministically: per-CTA partials, then rows
+            const int gR = std::min(gridFor(nCells, 256), numSMs * 4);
+            LAUNCH(this, k_colsum_nc1, gR, 256, 0, nCells, ncDelta.p, k1PartSum.p);
+            LAUNCH(this, k_fold_rows, 1, 32, 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
+        } else {
+            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_NCDELTA, 0, K1_NC1 * sizeof(double), stream));
+        }
+        // ---- lost mass shares ----
+        {
+            const int gL = std::min(gridFor(nCells, 256), numSMs * 4);
+            LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, nc ? ncCount.p : nullptr, lostShare.p, k1PartMax.p);
+            LAUNCH(this, k_fold_rows, 1, 32, 0, gL, 1, k1PartMax.p, dRep->v + RP_LOSTSUM, 0);
+        }
+        LAUNCH(this, k_step_end, 1, 32, 0, scal.p, dRep, prm, 0, nc ? ncCounts.p : nullptr, total, nRanks);
+
+        // ---- report ----
+        CUDA_CHECK(cudaMemcpyAsync(hFinal, dRep, sizeof(DevReport), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
+        int hNc[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(hNc, ncCounts.p, sizeof(hNc), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (nRanks > 1) CUDA_CHECK(cudaEventElapsedTime(&arMs, evArA, evArB));
+        if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
+        const double *v = hFinal;
+        nParticlesHost = (int64_t)hScal->nSorted + hNc[0] - hNc[1];
+        nSlotsHost = total;
+        deltaTHost = hScal->deltaT;
+        stepHost = hScal->step;
+        sortedValid = true;
+        if (reports) {
+            pdfb200_step_report &r = reports[st];
+            std::memset(&r, 0, sizeof(r));
+            r.deltaT = dtUsed; r.deltaTNext = hScal->deltaT;
+            r.rhoRes = v[RP_CELLSUM] / nCells; r.rhoErrMin = -v[RP_CELLMAX]; r.rhoErrMax = v[RP_CELLMAX + 1];
+            r.totalMass = v[RP_CELLSUM + 1]; r.totalParticleMass = v[RP_CELLSUM + 2];
+            r.UMax = std::max(0.0, v[RP_K1MAX + ACC_UMAX]); r.UcorrMax = std::max(0.0, v[RP_K1MAX + ACC_UCORRMAX]);
+            r.etaMax = std::max(0.0, v[RP_K1MAX + ACC_ETAMAX]); r.etaMin = -v[RP_K1MAX + ACC_NEG_ETAMIN];
+            r.CoMax = std::max(0.0, v[RP_K1MAX + ACC_COMAX]);
+            for (int k = 0; k <= prm.nConserved; ++k) {
+                r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + v[RP_NCDELTA + k];
+                r.massInInst[k] = v[RP_K1SUM + ACC_MASS_IN + k] + v[RP_INJ + k];
+                r.massOutInst[k] = v[RP_K1SUM + ACC_MASS_OUT + k];
+            }
+            r.deltaMassInst[0] += v[RP_LOSTSUM];
+            r.nParticles = nParticlesHost;
+            r.nInjected = nInjected; r.nDeleted = (int64_t)v[RP_K1SUM + ACC_N_DELETED];
+            r.nCloned = hNc[0]; r.nEliminated = hNc[1]; r.nLost = (int64_t)v[RP_K1SUM + ACC_N_LOST];
+            r.momentsAllreduceMs = arMs;
+        }
+    }
+    CUDA_CHECK(cudaEventRecord(evStop, stream));
+    CUDA_CHECK(cudaEventSynchronize(evStop));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, evStart, evStop));
+    lastEvolveMs = ms;
+}

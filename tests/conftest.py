@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `pytest -m gpu` under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle.oracle import OracleLib
+    return OracleLib()
+
+
+@pytest.fixture(scope="session")
+def device_lib():
+    from pdffoam_b200.capi import DeviceLibrary
+    return DeviceLibrary()
