@@ -276,6 +276,12 @@ int pdfb200_download_geometry(pdfb200_cloud *cloud, double *faceCentres, double 
                               double *courantCoeffs, double *hNum);
 /* number of kernels of this library launched since the handle was created  */
 int64_t pdfb200_kernel_launches(pdfb200_cloud *cloud);
+/* accumulated device time (ms, CUDA events on the library's stream) of the regions
+ * of evolve(): out[0] field preparation + injection, [1] the fused particle kernel,
+ * [2] radix sort, [3] segment bounds + moment reduction, [4] moment all-reduce,
+ * [5] time-averaging + number control + step end; out[6] = steps, out[7] =
+ * particle-steps processed. reset != 0 clears the accumulators.              */
+int pdfb200_profile(pdfb200_cloud *cloud, double out[8], int reset);
 /* device time (ms) of the last evolve() call, CUDA events on the library's stream */
 double pdfb200_last_evolve_ms(pdfb200_cloud *cloud);
 

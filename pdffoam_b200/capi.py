@@ -171,7 +171,7 @@ API_SYMBOLS = [
     "upload_cloud_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
-    "kernel_launches", "last_evolve_ms",
+    "kernel_launches", "last_evolve_ms", "profile",
 ]
 
 
@@ -220,6 +220,7 @@ class Library:
         if self.has("kernel_launches"):
             f("kernel_launches").argtypes = [vp]; f("kernel_launches").restype = C.c_int64
             f("last_evolve_ms").argtypes = [vp]; f("last_evolve_ms").restype = C.c_double
+            f("profile").argtypes = [vp, c_double_p, C.c_int]
 
     def check(self, status: int, what: str):
         if status != 0:
@@ -452,6 +453,12 @@ class CloudHandle:
 
     def last_evolve_ms(self) -> float:
         return float(self.lib.fn("last_evolve_ms")(self.h))
+
+    def profile(self, reset: bool = False) -> Dict[str, float]:
+        out = np.zeros(8)
+        self.lib.check(self.lib.fn("profile")(self.h, _dp(out), int(reset)), "profile")
+        names = ("prep_ms", "evolve_kernel_ms", "sort_ms", "moments_ms", "allreduce_ms", "finalise_ms", "steps", "particle_steps")
+        return dict(zip(names, out.tolist()))
 
     def comm_init(self, n_ranks: int, rank: int, uid: bytes):
         self.lib.check(self.lib.fn("comm_init")(self.h, n_ranks, rank, uid), "comm_init")

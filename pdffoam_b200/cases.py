@@ -191,7 +191,8 @@ def synthetic_box(nx=20, ny=10, nz=10, ppc=50, variant="stochastic", closed=Fals
     rho0 = 1.0
     U = Ufun(cc); k = kfun(cc)
     eps = 0.09 ** 0.75 * k ** 1.5 / 0.1
-    p = np.zeros(mesh.n_cells) if det else -rho0 * U0 ** 2 * (cc[:, 0] / 2)
+    # deterministic variant: p = 2/3 rho k makes p* = p - 2/3 rho k exactly zero
+    p = (2. / 3. * rho0) * k if det else -rho0 * U0 ** 2 * (cc[:, 0] / 2)
     R = np.zeros((mesh.n_cells, 6)); R[:, 0] = R[:, 3] = R[:, 5] = 2.0 / 3.0 * k
 
     fixed_in = [] if closed else [inlet]

@@ -35,6 +35,7 @@ Cloud::~Cloud() {
     if (evStop) cudaEventDestroy(evStop);
     if (evArA) cudaEventDestroy(evArA);
     if (evArB) cudaEventDestroy(evArB);
+    for (auto &e : evMark) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -89,6 +90,7 @@ void Cloud::create(const pdfb200_mesh &m, const pdfb200_params &p, int dev, int6
     CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreate(&evStart)); CUDA_CHECK(cudaEventCreate(&evStop));
     CUDA_CHECK(cudaEventCreate(&evArA)); CUDA_CHECK(cudaEventCreate(&evArB));
+    for (auto &e : evMark) CUDA_CHECK(cudaEventCreate(&e));
     setParams(p);
     CUDA_CHECK(cudaMallocHost((void **)&hScal, sizeof(StepScalars)));
     CUDA_CHECK(cudaMallocHost((void **)&hFinal, 64 * sizeof(double)));
@@ -219,6 +221,14 @@ int pdfb200_download_geometry(pdfb200_cloud *c, double *fc, double *fa, double *
 }
 
 int64_t pdfb200_kernel_launches(pdfb200_cloud *c) { return c->c.launches; }
+
+int pdfb200_profile(pdfb200_cloud *c, double out[8], int reset) {
+    Cloud &C = c->c;
+    for (int r = 0; r < 6; ++r) out[r] = C.profMs[r];
+    out[6] = (double)C.profSteps; out[7] = C.profParticleSteps;
+    if (reset) { for (double &v : C.profMs) v = 0; C.profSteps = 0; C.profParticleSteps = 0; }
+    return PDFB200_OK;
+}
 double pdfb200_last_evolve_ms(pdfb200_cloud *c) { return c->c.lastEvolveMs; }
 
 }  // extern "C"

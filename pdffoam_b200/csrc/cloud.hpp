@@ -66,6 +66,11 @@ struct Cloud {
     int nMom = 0, nCov = 0, cellAuxStride = 0;
     long long launches = 0;
     double lastEvolveMs = 0;
+    // per-region device time of evolve(), accumulated from CUDA events on `stream`
+    cudaEvent_t evMark[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double profMs[6] = {0, 0, 0, 0, 0, 0};
+    double profParticleSteps = 0;
+    long long profSteps = 0;
     int numSMs = 148;
 
     // ---- host copies of the small mesh tables ----

@@ -783,9 +783,11 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     int k1Blocks = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k_evolve, K1_THREADS, (ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double)));
     k1Blocks = std::max(1, std::min(k1Blocks, 16));
+    auto mark = [&](int r) { CUDA_CHECK(cudaEventRecord(evMark[r], stream)); };
 
     for (int st = 0; st < nSteps; ++st) {
         // ---- cell-side preparation (all updateInternals) ----
+        mark(0);
         prepareFields();
         int nInjected = 0;
         if (hasOpen) LAUNCH(this, k_open_un, gridFor(nBnd, 128), 128, 0, dm, Ufv_b.p, Un.p);
@@ -827,7 +829,9 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
         const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
         CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
+        mark(1);
         LAUNCH(this, k_evolve, gridK1, K1_THREADS, (ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double), A);
+        mark(2);
         LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
         LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
         cur ^= 1;
@@ -836,6 +840,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         size_t tempBytes = cubTemp.n;
         if (total > 0)
             CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
+        mark(3);
         CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
         CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
         if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellStart.p, cellEnd.p, scal.p);
@@ -849,9 +854,11 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         case 5: launchMoments<5>(*this, S[cur], valsB.p); break;
         default: launchMoments<6>(*this, S[cur], valsB.p); break;
         }
+        mark(4);
         // ---- cross-GPU sum of the moment block ----
         float arMs = 0;
         if (nRanks > 1) commAllreduceMoments(*this, &arMs);
+        mark(5);
 
         // ---- time-averaging, mean fields, boundary conditions ----
         const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
@@ -891,8 +898,17 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
         int hNc[2] = {0, 0};
         CUDA_CHECK(cudaMemcpyAsync(hNc, ncCounts.p, sizeof(hNc), cudaMemcpyDeviceToHost, stream));
+        mark(6);
         CUDA_CHECK(cudaStreamSynchronize(stream));
         if (nRanks > 1) CUDA_CHECK(cudaEventElapsedTime(&arMs, evArA, evArB));
+        // per-region device times: prep+inject, evolve kernel, sort, bounds+moments, allreduce, finalise+control
+        for (int r = 0; r < 6; ++r) {
+            float t = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&t, evMark[r], evMark[r + 1]));
+            profMs[r] += t;
+        }
+        profParticleSteps += (double)total;
+        ++profSteps;
         if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
         const double *v = hFinal;
         nParticlesHost = (int64_t)hScal->nSorted + hNc[0] - hNc[1];
