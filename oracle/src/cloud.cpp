@@ -430,6 +430,7 @@ void Cloud::injectPatch(int patchI) {
     for (int j = 0; j < pp.size; ++j) {
         const int bf = pp.start + j - nI, f = nI + bf;
         const int cellI = mesh.owner[f];
+        if ((bf % nRanks) != rank) continue;   // particle-sharded runs: inflow faces are dealt round-robin to the ranks
         if (Un[bf] > 0) continue;   // outlet face
         InletRandom inrnd;
         inrnd.updateCoeffs(inletU[bf].x, std::sqrt(inletR[bf].xx));

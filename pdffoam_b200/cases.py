@@ -239,3 +239,116 @@ def synthetic_box(nx=20, ny=10, nz=10, ppc=50, variant="stochastic", closed=Fals
     info = _hex_info(mesh)
     info.update(inlet=inlet, outlet=outlet, U0=U0)
     return Case(name=f"syntheticBox{nx}x{ny}x{nz}", mesh=mesh, params=prm, fv=fv, cf=cf, tables=tables, info=info)
+
+
+def with_scalars(case: Case, names: Sequence[str], reaction: str, tables: Optional[Dict] = None, **kw) -> Case:
+    """Re-dress a case with the scalar set of a reacting tutorial:
+    ("z","chi","T") + SteadyFlamelet (SandiaD, SydneyBluffBodyFlame:
+    constant/thermophysicalProperties:11-20) or ("z","T") + BurkeSchumann
+    (SandiaPropaneJet: constant/thermophysicalProperties:18-31)."""
+    n_phi = len(names)
+    nc, nb = case.mesh.n_cells, case.mesh.n_boundary_faces
+    z, zb, zf = case.cf["Phi"][0], case.cf["Phib"][0], case.cf["PhibFixed"][0]
+    Phi, Phib, PhibFixed = [z], [zb], [zf]
+    for _ in names[1:]:
+        Phi.append(np.zeros(nc)); Phib.append(np.zeros(nb)); PhibFixed.append(np.zeros(nb, np.uint8))
+    case.cf.update(Phi=Phi, Phib=Phib, PhibFixed=PhibFixed)
+    n_cov = n_phi * (n_phi + 1) // 2
+    cov = [np.zeros(nc) for _ in range(n_cov)]
+    cov[0] = 0.05 * z * (1 - z)                      # zzCov: some variance so that chi = Cchi*Omega*zVar varies
+    case.cf.update(Cov=cov, Covb=[c[_bnd_owner(case.mesh)].copy() for c in cov], CovbFixed=[np.zeros(nb, np.uint8)] * n_cov)
+    p = case.params
+    base = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] not in ("mixed", "conserved", "addedIdx", "reserved", "nPhi", "nMixed", "nConserved", "nAdded")}
+    base.update(reactionModel=reaction, zIdx=0)
+    if reaction == "SteadyFlamelet":
+        base.update(chiIdx=names.index("chi"), addedIdx=[names.index("T")], Cchi=2.0)
+        case.tables = tables
+    elif reaction == "BurkeSchumann":
+        # tutorials/SandiaPropaneJet/constant/thermophysicalProperties:22-31 (stoichiometric T raised so that rho varies)
+        base.update(TIdx=names.index("T"), bsRox=287.007, bsRfuel=188.554, bsRstoi=237.780, bsTox=294.0, bsTfuel=294.0,
+                    bsTstoi=2000.0, bsZstoi=0.5)
+        case.fv["p"] = case.fv["p"] + 1.0e5          # absolute pressure for rho = p/(R T)
+        case.fv["pb"] = case.fv["pb"] + 1.0e5
+    base.update(kw)
+    case.params = default_params(n_phi, mixed=[0], conserved=[0], **base)
+    return case
+
+
+def load_flamelet_tables(path: str) -> Dict:
+    """tests/golden/flamelet_*.npz -> {"chi","z","fields":[rho, T]} (rows = chi, columns = z,
+    mcSteadyFlamelet.C:261-286)"""
+    t = np.load(path)
+    return dict(chi=t["chi"], z=t["z"], fields=[t["rho"], t["T"]])
+
+
+def _rotation_tensor(n1, n2):
+    """OpenFOAM rotationTensor(n1, n2) (transform.H)"""
+    n1, n2 = np.asarray(n1, float), np.asarray(n2, float)
+    s = n1 @ n2
+    n3 = np.cross(n1, n2)
+    return s * np.eye(3) + (1 - s) * np.outer(n3, n3) / (n3 @ n3 + 1e-300) + (np.outer(n2, n1) - np.outer(n1, n2))
+
+
+def wedge_jet(nx=24, nr_jet=4, nr_co=10, length=0.3, r_min=2e-4, r_jet=3.6e-3, r_max=0.05, half_angle_deg=5.0, ppc=30,
+              U_jet=50.0, U_co=1.0, number_control=True, lts="cell", poscorr="limitedSimple", seed=0x5EED) -> Case:
+    """An axisymmetric jet in a coflow on a one-cell-thick wedge — the shape of all
+    four tutorial configs: patches jet / coflow / outflow ->
+    inletOutlet, axis / outerWall -> slip, front / back -> wedge (empty handler)."""
+    xs = meshgen.graded(nx, 0.0, length, 4.0)
+    rs = np.concatenate([meshgen.graded(nr_jet, r_min, r_jet, 1.0), meshgen.graded(nr_co, r_jet, r_max, 6.0)[1:]])
+    mesh = meshgen.wedge_mesh(xs, rs, half_angle_deg, inlet_split=[("jet", r_jet), ("coflow", 1e30)])
+    th = np.deg2rad(half_angle_deg)
+    cc = mesh.cell_centres_simple()
+    fcb = mesh.face_centres_simple()[mesh.n_internal_faces:]
+    own = _bnd_owner(mesh)
+    nc, nb = mesh.n_cells, mesh.n_boundary_faces
+
+    def radius(x):
+        return np.hypot(x[:, 1], x[:, 2])
+
+    def Ufun(x):
+        r = radius(x)
+        spread = r_jet * (1 + 6.0 * x[:, 0] / length)
+        ux = U_co + (U_jet - U_co) * (r_jet / spread) * np.exp(-(r / spread) ** 2)
+        ur = 0.02 * ux * r / spread
+        return np.stack([ux, ur, np.zeros_like(ux)], axis=1)
+
+    def kfun(x):
+        return 0.01 * Ufun(x)[:, 0] ** 2 + 0.05
+
+    def zfun(x):
+        r = radius(x)
+        spread = r_jet * (1 + 6.0 * x[:, 0] / length)
+        return np.clip((r_jet / spread) * np.exp(-(r / spread) ** 2), 0.0, 1.0)
+
+    U = Ufun(cc); k = kfun(cc); eps = 0.09 ** 0.75 * k ** 1.5 / (0.5 * r_jet * 10)
+    p = np.zeros(nc)
+    R = np.zeros((nc, 6)); R[:, 0] = R[:, 3] = R[:, 5] = 2.0 / 3.0 * k
+    Ub = U[own].copy(); kb = k[own].copy(); epsb = eps[own].copy(); pb = p[own].copy(); Rb = R[own].copy()
+    fixed = ["jet", "coflow"]
+    for name in fixed:
+        s = mesh.boundary_slice(name)
+        Ub[s] = Ufun(fcb[s]); Ub[s, 1] = 0.0
+        kb[s] = kfun(fcb[s]); epsb[s] = 0.09 ** 0.75 * kb[s] ** 1.5 / (0.5 * r_jet * 10)
+        Rb[s] = 0; Rb[s, 0] = Rb[s, 3] = Rb[s, 5] = 2.0 / 3.0 * kb[s]
+    for name in ("axis", "outerWall"):
+        Ub[mesh.boundary_slice(name), 1] = 0.0
+    # wedge patches: wedgeFvPatchField::evaluate rotates the cell vector onto the patch
+    for name, sign in (("back", -1.0), ("front", 1.0)):
+        s = mesh.boundary_slice(name)
+        n = np.array([0.0, -np.sin(th), np.cos(th)]) if sign > 0 else np.array([0.0, -np.sin(th), -np.cos(th)])   # outward patch normal
+        cn = np.array([0.0, 0.0, 1.0]) if sign > 0 else np.array([0.0, 0.0, -1.0])
+        T = _rotation_tensor(cn, n)
+        Ub[s] = U[own][s] @ T.T
+    fv = dict(U=U, Ub=Ub, UbFixed=_flags(mesh, fixed), p=p, pb=pb, k=k, kb=kb, kbFixed=_flags(mesh, fixed),
+              epsilon=eps, epsilonb=epsb, R=R, Rb=Rb)
+    rho = np.ones(nc)
+    z = zfun(cc); zb = z[own].copy()
+    zb[mesh.boundary_slice("jet")] = 1.0; zb[mesh.boundary_slice("coflow")] = 0.0
+    cf = dict(rho=rho, rhob=rho[own].copy(), rhobFixed=_flags(mesh, fixed), Phi=[z], Phib=[zb], PhibFixed=[_flags(mesh, fixed)])
+    prm = default_params(1, particlesPerCell=ppc, mixed=[0], conserved=[0], CFL=0.3, averagingCoeff=50.0, DNum=0.05,
+                         localTimeStepping=lts, ltsUpperBound=20.0, positionCorrection=poscorr, pcC=5e-2,
+                         particleNumberControl=int(number_control), kMin=1e-8, Omega0=1e5, seed=seed,
+                         relaxTimeU=1e-5, relaxTimek=1e-5)
+    # cell volumes of the wedge hexes: (r2^2 - r1^2)/2 * 2*theta ... computed by the library; keep the case light
+    return Case(name=f"wedgeJet{nx}x{nr_jet + nr_co}", mesh=mesh, params=prm, fv=fv, cf=cf, info=dict(theta=th))

@@ -4,7 +4,7 @@ from pdffoam_b200 import cases
 from pdffoam_b200.capi import DeviceLibrary
 from oracle.oracle import OracleLib
 from parity_util import sort_by_id
-case = cases.synthetic_box(6, 4, 4, ppc=20, closed=True, number_control=True)
+case = cases.synthetic_box(6, 4, 4, ppc=20, closed=True, number_control=True); case.params.deltaT0 = 2e-3
 P = case.random_particles(20, seed=9)
 keep = np.ones(P["m"].shape[0], bool)
 rng = np.random.default_rng(0)
@@ -25,7 +25,7 @@ a = sort_by_id(dev.download_particles()); b = sort_by_id(ora.download_particles(
 bad = np.nonzero(a["tet"] != b["tet"])[0]
 for i in bad:
     print(a["id"][i], a["cell"][i], b["cell"][i], a["tet"][i], b["tet"][i], a["pos"][i], b["pos"][i], a["pos"][i]-b["pos"][i], a["m"][i], b["m"][i])
-for c in (0,):
+for c in sorted(set(a["cell"][bad].tolist())):
     for name, p in (("dev", a), ("ora", b)):
         sel = np.nonzero(p["cell"] == c)[0]
         order = np.argsort(-(p["eta"][sel]*p["m"][sel]))

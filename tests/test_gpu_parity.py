@@ -70,12 +70,14 @@ def test_open_box_injection_and_outflow(device_lib, oracle_lib):
 def test_particle_number_control(device_lib, oracle_lib):
     """clone / eliminate with id-keyed draws: identical populations.
 
-    Cloning ranks a cell's particles by eta*m. With cell local time stepping the
-    first step (deltaT = 1e-13) rescales eta to 1 + O(1e-13) for every particle,
-    so eta*m values of different particles differ only in their last bits and the
-    ranking then depends on 1-ulp differences between CPU and GPU interpolation
-    arithmetic. The test therefore starts from a realistic deltaT, where eta*m
-    values are well separated (exact ties, e.g. eta == 1, are broken by id)."""
+    Cloning ranks a cell's particles by eta*m. Wherever the interpolated eta
+    field is locally constant (e.g. the first step, deltaT = 1e-13, rescales eta
+    to 1 + O(1e-13) everywhere) particles of equal mass have eta*m values that
+    differ only in their last bits, and the ranking then depends on 1-ulp
+    differences between CPU and GPU interpolation arithmetic — an inherent
+    sensitivity of the reference algorithm (std::sort on near-ties), not a
+    defect. The test gives the particles distinct masses so that eta*m values
+    are separated far beyond round-off (exact ties are broken by id)."""
     case = cases.synthetic_box(6, 4, 4, ppc=20, closed=True, number_control=True)
     case.params.deltaT0 = 2e-3
     P = case.random_particles(20, seed=9)
@@ -91,6 +93,7 @@ def test_particle_number_control(device_lib, oracle_lib):
     R["id"] = np.arange(R["m"].shape[0], dtype=np.uint32)
     R["pos"] = R["pos"].copy()
     R["pos"][-dup.size:] += 1e-4 * (rng.random((dup.size, 3)) - 0.5)
+    R["m"] = R["m"] * rng.uniform(0.5, 1.5, size=R["m"].shape[0])
     dev, ora, reps = run_both(case, device_lib, oracle_lib, R, n_steps=5, rtol=1e-9, atol=1e-11)
     assert sum(r[0].nCloned for r in reps) > 0
     assert sum(r[0].nEliminated for r in reps) > 0
