@@ -65,7 +65,9 @@ def test_flamelet_lookup_matches_golden_vectors(device_lib):
 def test_burke_schumann(device_lib, oracle_lib):
     case = cases.with_scalars(cases.synthetic_box(6, 4, 4, ppc=18, closed=False), ["z", "T"], "BurkeSchumann")
     case.params.deltaT0 = 1e-3
-    run_both(case, device_lib, oracle_lib, None, n_steps=4, seed_on_device=True, rtol=RTOL, atol=ATOL)
+    # grad p* is formed from absolute pressures (1e5) times shape gradients (~1e2) that sum to zero:
+    # round-off of that cancellation is ~1e-9 in the gradient, ~1e-11 in U after one step
+    run_both(case, device_lib, oracle_lib, None, n_steps=4, seed_on_device=True, rtol=1e-8, atol=1e-9)
 
 
 def test_particle_local_time_stepping_and_cell_scheme(device_lib, oracle_lib):
@@ -85,7 +87,11 @@ def test_two_dimensional_slab_with_empty_patches(device_lib, oracle_lib):
     mesh = meshgen.slab_mesh(11, 5, lo=(0.0, 0.0), hi=(6.0, 2.0), thickness=2.0)
     nc, nb = mesh.n_cells, mesh.n_boundary_faces
     own = mesh.owner[mesh.n_internal_faces:]
-    U = np.tile([1.0, 0.2, 0.0], (nc, 1)); k = np.full(nc, 0.3)
+    # a non-uniform velocity field: with a uniform one every cell has the same Courant time scale and the
+    # reference's rescaling of eta, (etaMax-1)/max(eta-min(eta)) * (eta-min(eta)) + 1, degenerates to 0/0
+    ccx = mesh.cell_centres_simple()
+    U = np.stack([1.0 + 0.3 * np.sin(np.pi * ccx[:, 0] / 3.0), 0.2 * np.cos(np.pi * ccx[:, 1] / 2.0), np.zeros(nc)], axis=1)
+    k = np.full(nc, 0.3)
     R = np.zeros((nc, 6)); R[:, 0] = R[:, 3] = R[:, 5] = 0.2
     Ub = U[own].copy(); Ub[:, 2] = 0
     for name, comp in (("xmin", 0), ("xmax", 0), ("ymin", 1), ("ymax", 1)):
@@ -111,7 +117,7 @@ def test_two_dimensional_slab_with_empty_patches(device_lib, oracle_lib):
         rd = dev.evolve(1)[0]; ro = ora.evolve(1)[0]
         compare_particles(dev.download_particles(), ora.download_particles(), RTOL, ATOL, True, f"slab step {s}")
         compare_cell_fields(dev.download_cell_fields(), ora.download_cell_fields(), RTOL, ATOL, f"slab step {s}")
-        assert rd.UcorrMax > 0                                    # the density bump drives a correction velocity
+    assert rd.UcorrMax > 0                                        # the density bump drives a correction velocity
     Q = dev.download_particles()
     assert np.all(Q["pos"][:, 2] == 0.0)
 

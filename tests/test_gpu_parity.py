@@ -76,9 +76,10 @@ def test_particle_number_control(device_lib, oracle_lib):
     differ only in their last bits, and the ranking then depends on 1-ulp
     differences between CPU and GPU interpolation arithmetic — an inherent
     sensitivity of the reference algorithm (std::sort on near-ties), not a
-    defect. The test gives the particles distinct masses so that eta*m values
-    are separated far beyond round-off (exact ties are broken by id)."""
-    case = cases.synthetic_box(6, 4, 4, ppc=20, closed=True, number_control=True)
+    defect. The test gives the particles distinct masses and switches local time
+    stepping off (eta == 1), so that eta*m values are either separated far beyond
+    round-off or tie exactly (a clone and its source), which is broken by id."""
+    case = cases.synthetic_box(6, 4, 4, ppc=20, closed=True, number_control=True, lts="none")
     case.params.deltaT0 = 2e-3
     P = case.random_particles(20, seed=9)
     # unbalance the population: drop most particles of some cells, triple others
