@@ -232,7 +232,8 @@ _DEVICE_LIB: Optional[Library] = None
 
 
 def device_library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpdfb200.so")
+    # PDFB200_LIB selects another build of the same library (kernel tuning experiments)
+    return os.environ.get("PDFB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpdfb200.so")
 
 
 def DeviceLibrary() -> Library:

@@ -37,7 +37,7 @@ struct __align__(16) TetRec {
     int ptB, ptC;     // global point labels of b and c
     int cell;
     double g[9];      // gradN of vertices a (face centre), b, c; g_d = -(g_a+g_b+g_c)
-    double pad[3];
+    double centre[3]; // centre of `cell` (vertex d): saves the dependent cell-centre load in the walk
 };
 static_assert(sizeof(TetRec) == 128, "TetRec must be one 128-byte line");
 

@@ -41,39 +41,73 @@ struct K1Args {
     int hasOpen;
 };
 
-struct TetL {   // a tet record in registers
-    int nbr[4];
+// a tet record in registers (no arrays: nothing here may be indexed dynamically,
+// or the compiler would move it to local memory)
+struct TetL {
+    int n0, n1, n2, n3;          // neighbours across the faces opposite a, b, c, d
     int face, ptB, ptC, cell;
-    double g[9];
+    double g0, g1, g2, g3, g4, g5, g6, g7, g8;   // gradN of a, b, c
+    double cx, cy, cz;           // centre of the cell (vertex d)
 };
 
-__device__ inline void loadTet(const TetRec *tets, int t, TetL &T) {
-    const int4 *pi = reinterpret_cast<const int4 *>(tets + t);
-    const int4 a = __ldg(pi), b = __ldg(pi + 1);
-    T.nbr[0] = a.x; T.nbr[1] = a.y; T.nbr[2] = a.z; T.nbr[3] = a.w;
+// Per-warp staging of tet records in shared memory ("cell geometry staged in
+// shared memory"): at the start of an iteration each warp copies the records
+// of the cells its 32 particles start in (coalesced 128-bit loads) into its own
+// shared-memory window; the walk then reads a record from the window when the
+// tet is inside it and from global memory otherwise, through one generic load
+// path (no divergence). Records sit at a 144-byte stride to spread the banks.
+#define STAGE_RECORDS 32
+#define STAGE_STRIDE_B 144
+struct TetStage {
+    const char *base;   // this warp's window (generic address of shared memory)
+    int lo, n;          // first staged tet, number of staged records
+};
+
+__device__ __forceinline__ void loadTet(const TetRec *tets, const TetStage &S, int t, TetL &T) {
+    const unsigned off = (unsigned)(t - S.lo);
+    const char *rec = (off < (unsigned)S.n) ? S.base + (size_t)off * STAGE_STRIDE_B : reinterpret_cast<const char *>(tets + t);
+    const int4 *pi = reinterpret_cast<const int4 *>(rec);
+    const int4 a = pi[0], b = pi[1];
+    T.n0 = a.x; T.n1 = a.y; T.n2 = a.z; T.n3 = a.w;
     T.face = b.x; T.ptB = b.y; T.ptC = b.z; T.cell = b.w;
-    const double2 *pd = reinterpret_cast<const double2 *>(tets + t) + 2;
-    const double2 g0 = __ldg(pd), g1 = __ldg(pd + 1), g2 = __ldg(pd + 2), g3 = __ldg(pd + 3), g4 = __ldg(pd + 4);
-    T.g[0] = g0.x; T.g[1] = g0.y; T.g[2] = g1.x; T.g[3] = g1.y; T.g[4] = g2.x; T.g[5] = g2.y;
-    T.g[6] = g3.x; T.g[7] = g3.y; T.g[8] = g4.x;
+    const double2 *pd = reinterpret_cast<const double2 *>(rec) + 2;
+    const double2 g0 = pd[0], g1 = pd[1], g2 = pd[2], g3 = pd[3], g4 = pd[4], g5 = pd[5];
+    T.g0 = g0.x; T.g1 = g0.y; T.g2 = g1.x; T.g3 = g1.y; T.g4 = g2.x; T.g5 = g2.y;
+    T.g6 = g3.x; T.g7 = g3.y; T.g8 = g4.x;
+    T.cx = g4.y; T.cy = g5.x; T.cz = g5.y;
+}
+// plain global path (kernels without staging)
+__device__ __forceinline__ void loadTet(const TetRec *tets, int t, TetL &T) {
+    TetStage S;
+    S.base = nullptr; S.lo = 0; S.n = 0;
+    loadTet(tets, S, t, T);
 }
 
-__device__ inline V3 cellCentre(const DMesh &M, int c) {
+__device__ __forceinline__ V3 cellCentre(const DMesh &M, int c) {
     const double2 *p = reinterpret_cast<const double2 *>(M.cellCentre4 + c);
-    const double2 a = __ldg(p), b = __ldg(p + 1);
-    return mk(a.x, a.y, b.x);
+    const double2 a = __ldg(p);
+    const double z = __ldg(reinterpret_cast<const double *>(p + 1));
+    return mk(a.x, a.y, z);
 }
 
-__device__ inline void baryAt(const TetL &T, V3 r, double w[4]) {
-    w[0] = dotf(T.g[0], T.g[1], T.g[2], r);
-    w[1] = dotf(T.g[3], T.g[4], T.g[5], r);
-    w[2] = dotf(T.g[6], T.g[7], T.g[8], r);
-    w[3] = 1.0 - ((w[0] + w[1]) + w[2]);
+__device__ __forceinline__ void baryAt(const TetL &T, V3 r, double &w0, double &w1, double &w2, double &w3) {
+    w0 = dotf(T.g0, T.g1, T.g2, r);
+    w1 = dotf(T.g3, T.g4, T.g5, r);
+    w2 = dotf(T.g6, T.g7, T.g8, r);
+    w3 = 1.0 - ((w0 + w1) + w2);
 }
 
-__device__ inline double clamp01(double x) { return fmax(0.0, fmin(1.0, x)); }
+__device__ __forceinline__ double clamp01(double x) { return fmax(0.0, fmin(1.0, x)); }
 
-__device__ inline double massPerDepth(const DMesh &M, V3 pos, double m) {
+// phi[idx] without dynamic indexing
+__device__ __forceinline__ double pickPhi(const double (&phi)[PDFB200_MAX_PHI], int idx) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == idx) v = phi[k];
+    return v;
+}
+
+__device__ __forceinline__ double massPerDepth(const DMesh &M, V3 pos, double m) {
     if (M.axisym) {
         const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
         const double r = mag3(pos - dot3(pos, ax) * ax);
@@ -82,133 +116,34 @@ __device__ inline double massPerDepth(const DMesh &M, V3 pos, double m) {
     return m;
 }
 
-__device__ inline V3 reflectVec(V3 v, V3 n) {
+__device__ __forceinline__ V3 reflectVec(V3 v, V3 n) {
     const double d = dot3(v, n);
     return v - (2.0 * d) * n;
 }
 
-__device__ inline void constrainDir(const int d[3], V3 &v) {
+__device__ __forceinline__ void constrainDir(const int d[3], V3 &v) {
     if (d[0] < 0) v.x = 0;
     if (d[1] < 0) v.y = 0;
     if (d[2] < 0) v.z = 0;
 }
 
-// constrainParticle (mcParticleCloud.C:76-101)
-__device__ inline void constrainParticle(const DMesh &M, double dt, V3 pos, V3 &U, V3 &Ucorr, V3 &Utrack) {
-    constrainDir(M.solD, Utrack);
-    if (M.axisym) {
-        V3 dest = pos + dt * Utrack;
-        const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
-        V3 n = cross3(ax, dest);
-        n = n / mag3(n);
-        double T[9];
-        rotationTensor(n, mk(M.centreNormal[0], M.centreNormal[1], M.centreNormal[2]), T);
-        U = xform(T, U); Ucorr = xform(T, Ucorr);
-        dest = xform(T, dest);
-        constrainDir(M.geoD, dest);
-        Utrack = (dest - pos) / dt;
-    }
+// constrainParticle (mcParticleCloud.C:76-101); the axisymmetric rotation is kept out of
+// line so that 3-D cases do not carry its code in the instruction cache
+__device__ __forceinline__ void constrainAxisym(const DMesh &M, double dt, V3 pos, V3 &U, V3 &Ucorr, V3 &Utrack) {
+    V3 dest = pos + dt * Utrack;
+    const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
+    V3 n = cross3(ax, dest);
+    n = n / mag3(n);
+    double T[9];
+    rotationTensor(n, mk(M.centreNormal[0], M.centreNormal[1], M.centreNormal[2]), T);
+    U = xform(T, U); Ucorr = xform(T, Ucorr);
+    dest = xform(T, dest);
+    constrainDir(M.geoD, dest);
+    Utrack = (dest - pos) / dt;
 }
-
-struct PartFlags {
-    bool reflected, reflOpen;
-    V3 reflBV;
-    int nSteps;
-};
-
-// status: 0 alive, 1 deleted at an open boundary, 2 lost
-// mcParticle::move on the tet walk (see oracle/src/cloud.cpp Cloud::move for the
-// algorithm statement; both evaluate identical expressions).
-__device__ inline int trackParticle(const K1Args &A, double trackTime, double stepFraction, V3 &pos, int &tet, TetL &T,
-                                    V3 &Utrack, V3 &U, V3 &Ucorr, PartFlags &fl, double w[4], double m,
-                                    const double *phi, double *acc) {
-    const DMesh &M = A.M;
-    double tEnd = (1.0 - stepFraction) * trackTime;
-    const double dtMax = tEnd;
-    int entry = -1;
-    bool haveW = false;
-    while (tEnd > 0) {
-        double dt = fmin(dtMax, tEnd);
-        V3 dest = pos + dt * Utrack;
-        constrainDir(M.geoD, dest);
-        const V3 x0 = pos;
-        const V3 dx = dest - x0;
-        double tf = 1.0;
-        int status = 0;
-        bool hit = false;
-        for (;;) {
-            const V3 r = x0 - cellCentre(M, T.cell);
-            double p[4], q[4];
-            baryAt(T, r, p);
-            q[0] = dotf(T.g[0], T.g[1], T.g[2], dx);
-            q[1] = dotf(T.g[3], T.g[4], T.g[5], dx);
-            q[2] = dotf(T.g[6], T.g[7], T.g[8], dx);
-            q[3] = -((q[0] + q[1]) + q[2]);
-            int best = -1;
-            double pb = 0, qb = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool cand = (i != entry) && (q[i] < 0) && (p[i] + q[i] < 0);
-                if (cand && (best < 0 || p[i] * qb > pb * q[i])) { best = i; pb = p[i]; qb = q[i]; }
-            }
-            if (best < 0) {
-                pos = dest;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) w[i] = p[i] + q[i];
-                haveW = true;
-                tf = 1.0;
-                break;
-            }
-            ++fl.nSteps;
-            if (fl.nSteps > 1000) { status = 2; break; }
-            if (best != 3 || T.face < M.nInternalFaces) {
-                tet = T.nbr[best];
-                loadTet(M.tets, tet, T);
-                entry = (best == 1) ? 2 : (best == 2 ? 1 : best);
-                continue;
-            }
-            // boundary face
-            double s = p[3] / (-q[3]);
-            s = fmin(1.0, fmax(0.0, s));
-            pos = x0 + s * dx;
-            tf = s;
-            hit = true;
-            const int bf = T.face - M.nInternalFaces;
-            const int info = __ldg(M.bfInfo + bf);
-            const int handler = BF_HANDLER(info);
-            if (BF_GEOM(info) != PDFB200_PATCH_GENERIC || handler == PDFB200_BC_EMPTY) { status = 2; break; }
-            const double4 n4 = M.bfNormal[bf];
-            const V3 nw = mk(n4.x, n4.y, n4.z);
-            if (handler == PDFB200_BC_SLIP) {
-                U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
-                fl.reflected = true;
-            } else {
-                const double Un = A.Un[bf];
-                if (Un < 0 || !BF_REFLECTING(info)) {
-                    const double mpd = massPerDepth(M, pos, m);
-                    const int base = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
-                    acc[(base)*K1_THREADS] -= mpd;
-                    for (int cs = 0; cs < A.P.nConserved; ++cs) acc[(base + 1 + cs) * K1_THREADS] -= mpd * phi[A.P.conserved[cs]];
-                    status = 1;
-                    break;
-                }
-                U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
-                fl.reflected = true; fl.reflOpen = true;
-                fl.reflBV = nw * Un;
-            }
-            entry = 3;
-            break;
-        }
-        if (status != 0) return status;
-        (void)hit;
-        dt *= tf;
-        tEnd -= dt;
-    }
-    if (!haveW) {   // zero-length track (or it ended on a boundary): weights at the current position
-        const V3 r = pos - cellCentre(M, T.cell);
-        baryAt(T, r, w);
-    }
-    return 0;
+__device__ __forceinline__ void constrainParticle(const DMesh &M, double dt, V3 pos, V3 &U, V3 &Ucorr, V3 &Utrack) {
+    constrainDir(M.solD, Utrack);
+    if (M.axisym) constrainAxisym(M, dt, pos, U, Ucorr, Utrack);
 }
 
 // mcSteadyFlamelet helpers (mcSteadyFlamelet.C:44-93)
@@ -230,19 +165,22 @@ __device__ inline double binterpDev(const double *v, int nRows, int nCols, int i
     return v00 * wxm * wym + v10 * wx * wym + v01 * wxm * wy + v11 * wx * wy;
 }
 
-__device__ inline double stabilise(double x, double y) { return x < 0 ? x - y : x + y; }
+__device__ __forceinline__ double stabilise(double x, double y) { return x < 0 ? x - y : x + y; }
 
 // Reaction models on one particle: mcColdReactionModel.C:62-65,
 // mcBurkeSchumannReactionModel.C:77-91, mcSteadyFlamelet.C:304-329.
 struct FlameletTables { const double *chi, *z, *fields; int nChi, nZ; };
-__device__ inline void reactionCorrect(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
-                                       double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho) {
-    if (P.reactionModel == PDFB200_REACTION_COLD) {
-        rho = P.coldDensity;
-    } else if (P.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN) {
-        double z = 0;
-#pragma unroll
-        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.zIdx) z = phi[k];
+__device__ __forceinline__ void reactionCorrectTable(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
+                                                     double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho);
+__device__ __forceinline__ void reactionCorrect(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
+                                                double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho) {
+    if (P.reactionModel == PDFB200_REACTION_COLD) rho = P.coldDensity;
+    else if (P.reactionModel != PDFB200_REACTION_NONE) reactionCorrectTable(P, F, Omega, zVar, pCell, phi, rho);
+}
+__device__ __forceinline__ void reactionCorrectTable(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
+                                                  double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho) {
+    if (P.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN) {
+        const double z = pickPhi(phi, P.zIdx);
         const double RTox = P.bsRox * P.bsTox, RTfuel = P.bsRfuel * P.bsTfuel, RTstoi = P.bsRstoi * P.bsTstoi;
         const double RT = z < P.bsZstoi ? (RTstoi - RTox) / P.bsZstoi * z + RTox
                                         : (RTfuel - RTstoi) / (1 - P.bsZstoi) * (z - P.bsZstoi) + RTstoi;
@@ -252,9 +190,7 @@ __device__ inline void reactionCorrect(const pdfb200_params &P, const FlameletTa
 #pragma unroll
         for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.TIdx) phi[k] = Tt;
     } else if (P.reactionModel == PDFB200_REACTION_STEADY_FLAMELET) {
-        double z = 0;
-#pragma unroll
-        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.zIdx) z = phi[k];
+        const double z = pickPhi(phi, P.zIdx);
         const double chi = fmax(P.Cchi * Omega * zVar, PDF_SMALL);
         int iz, ichi; double wz, wchi;
         findCoeffsDev(F.z, F.nZ, z, iz, wz);
@@ -272,32 +208,38 @@ __device__ inline void reactionCorrect(const pdfb200_params &P, const FlameletTa
 
 // interpolationCellPointFace of every mid-point field at once: the four node
 // records of the tet (points b and c, face centre, cell centre) blended with
-// the clamped barycentric weights; pst receives the four p* node values for
-// gradInterpolationConstantTet (order a, b, c, d).
-__device__ inline void interpMid(const DMesh &M, const pdfb200_params &P, const double *nodeMid, const TetL &T,
-                                 const double w[4], double (&val)[NODE_MID_STRIDE], double (&pst)[4]) {
+// the clamped barycentric weights (order a, b, c, d); pst receives the four p*
+// node values for gradInterpolationConstantTet (order a, b, c, d).
+__device__ __forceinline__ void interpMid(const DMesh &M, const pdfb200_params &P, const double *nodeMid, const TetL &T,
+                                          double w0, double w1, double w2, double w3, double (&val)[NODE_MID_STRIDE],
+                                          double (&pst)[4]) {
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
     const double2 *nb = reinterpret_cast<const double2 *>(nodeMid + (nodeP + T.ptB) * NODE_MID_STRIDE);
     const double2 *nc = reinterpret_cast<const double2 *>(nodeMid + (nodeP + T.ptC) * NODE_MID_STRIDE);
     const double2 *na = reinterpret_cast<const double2 *>(nodeMid + (nodeF + T.face) * NODE_MID_STRIDE);
     const double2 *nd = reinterpret_cast<const double2 *>(nodeMid + (size_t)T.cell * NODE_MID_STRIDE);
-    const double fb = clamp01(w[1]), fc = clamp01(w[2]), fa = clamp01(w[0]), fd = clamp01(w[3]);
+    const double fb = clamp01(w1), fc = clamp01(w2), fa = clamp01(w0), fd = clamp01(w3);
+    const bool anyCell = (P.interpU == PDFB200_INTERP_CELL) | (P.interpk == PDFB200_INTERP_CELL) |
+                         (P.interpDiffU == PDFB200_INTERP_CELL) | (P.interpOmega == PDFB200_INTERP_CELL) |
+                         (P.interpEta == PDFB200_INTERP_CELL) | (P.interpZVar == PDFB200_INTERP_CELL);
     double cv[NODE_MID_STRIDE];
 #pragma unroll
-    for (int k = 0; k < NODE_MID_STRIDE / 2; ++k) {
+    for (int k = 0; k < (NODE_MID_STRIDE - 1) / 2 + 1; ++k) {
+        if (2 * k >= NM_ZVAR + 1) break;
         const double2 vb = __ldg(nb + k), vc = __ldg(nc + k), va = __ldg(na + k), vd = __ldg(nd + k);
         val[2 * k] = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
         val[2 * k + 1] = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
         cv[2 * k] = vd.x; cv[2 * k + 1] = vd.y;
         if (2 * k == NM_PSTAR) { pst[0] = va.x; pst[1] = vb.x; pst[2] = vc.x; pst[3] = vd.x; }
     }
-    // interpolation scheme "cell": the cell value
-    if (P.interpU == PDFB200_INTERP_CELL) { val[NM_U] = cv[NM_U]; val[NM_U + 1] = cv[NM_U + 1]; val[NM_U + 2] = cv[NM_U + 2]; }
-    if (P.interpk == PDFB200_INTERP_CELL) val[NM_K] = cv[NM_K];
-    if (P.interpDiffU == PDFB200_INTERP_CELL) { val[NM_DU] = cv[NM_DU]; val[NM_DU + 1] = cv[NM_DU + 1]; val[NM_DU + 2] = cv[NM_DU + 2]; }
-    if (P.interpOmega == PDFB200_INTERP_CELL) val[NM_OMEGA] = cv[NM_OMEGA];
-    if (P.interpEta == PDFB200_INTERP_CELL) val[NM_ETA] = cv[NM_ETA];
-    if (P.interpZVar == PDFB200_INTERP_CELL) val[NM_ZVAR] = cv[NM_ZVAR];
+    if (anyCell) {   // interpolation scheme "cell": the cell value
+        if (P.interpU == PDFB200_INTERP_CELL) { val[NM_U] = cv[NM_U]; val[NM_U + 1] = cv[NM_U + 1]; val[NM_U + 2] = cv[NM_U + 2]; }
+        if (P.interpk == PDFB200_INTERP_CELL) val[NM_K] = cv[NM_K];
+        if (P.interpDiffU == PDFB200_INTERP_CELL) { val[NM_DU] = cv[NM_DU]; val[NM_DU + 1] = cv[NM_DU + 1]; val[NM_DU + 2] = cv[NM_DU + 2]; }
+        if (P.interpOmega == PDFB200_INTERP_CELL) val[NM_OMEGA] = cv[NM_OMEGA];
+        if (P.interpEta == PDFB200_INTERP_CELL) val[NM_ETA] = cv[NM_ETA];
+        if (P.interpZVar == PDFB200_INTERP_CELL) val[NM_ZVAR] = cv[NM_ZVAR];
+    }
 }
 
 // shared locate rule (oracle Mesh::locate): the tet of `cell` with the largest
@@ -350,14 +292,20 @@ __device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uin
 }
 
 // computeCourantNo (mcParticleCloud.C:2120-2148)
-__device__ inline double courantNo(const DMesh &M, int cell, V3 Utrack) {
+__device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack) {
     double Co = 0.;
     const int js = __ldg(M.cellFaceStart + cell), je = __ldg(M.cellFaceStart + cell + 1);
     for (int j = js; j < je; ++j) Co = fmax(Co, fabs(dot3(ld3(M.cellCo, j), Utrack)));
     return Co;
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 4
+#endif
+// dynamic shared memory: thread-private accumulators + one staging window per warp
+#define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double) + (K1_THREADS / 32) * STAGE_RECORDS * STAGE_STRIDE_B)
+
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Args A) {
     extern __shared__ double smem[];
     double *accS = smem + threadIdx.x;                         // sums: accS[k*K1_THREADS]
     double *accM = smem + ACC_NSUM * K1_THREADS + threadIdx.x;  // maxima
@@ -368,15 +316,38 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
 
     const DMesh &M = A.M;
     const pdfb200_params &P = A.P;
-    const StepScalars sc = *A.sc;
-    const int nSorted = sc.nSorted, total = sc.nSorted + sc.nTail;
-    const double deltaT = sc.deltaT;
+    const int nSorted = A.sc->nSorted, total = nSorted + A.sc->nTail, nSlotsIn = A.sc->nSlots, nInjStart = A.sc->nInjStart;
+    const int anyLost = A.sc->anyLost;
+    const uint32_t step = A.sc->step;
+    const double deltaT = A.sc->deltaT;
     const int nPhi = P.nPhi;
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
 
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int slot = (i < nSorted) ? (int)A.perm[i] : sc.nSlots + (i - nSorted);
-        int cell = A.in.cell[slot];
+    const int lane = threadIdx.x & 31;
+    char *const stageWin = reinterpret_cast<char *>(smem + (ACC_NSUM + ACC_NMAX) * K1_THREADS) +
+                           (size_t)(threadIdx.x >> 5) * STAGE_RECORDS * STAGE_STRIDE_B;
+
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool active = i < total;
+        const int slot = !active ? 0 : (i < nSorted) ? (int)A.perm[i] : nSlotsIn + (i - nSorted);
+        int cell = active ? A.in.cell[slot] : -1;
+
+        // ---- stage the tet records of the warp's start cells in shared memory ----
+        TetStage stage;
+        {
+            const int myLo = (cell >= 0) ? __ldg(M.cellTetStart + cell) : 0x7fffffff;
+            const int lo = __reduce_min_sync(0xffffffffu, myLo);
+            const long long room = M.nTets - lo;
+            const int n = (lo == 0x7fffffff) ? 0 : (int)(room < STAGE_RECORDS ? room : STAGE_RECORDS);
+            __syncwarp();   // every lane has finished reading the previous window
+            const int4 *src = reinterpret_cast<const int4 *>(M.tets + lo);
+            for (int j = lane; j < n * 8; j += 32)
+                *reinterpret_cast<int4 *>(stageWin + (j >> 3) * STAGE_STRIDE_B + (j & 7) * 16) = __ldg(src + j);
+            __syncwarp();
+            stage.base = stageWin; stage.lo = lo; stage.n = n;
+        }
+        if (!active) continue;
         if (cell < 0) { A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
         V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
         V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
@@ -386,11 +357,11 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
         for (int k = 0; k < PDFB200_MAX_PHI; ++k) phi[k] = (k < nPhi) ? A.in.phi[k][slot] : 0.0;
         int tet = A.in.tet[slot];
         const uint32_t id = A.in.id[slot];
-        if (sc.anyLost) m += A.lostShare[cell];
-        const bool injected = (i >= nSorted + sc.nInjStart);
+        if (anyLost) m += A.lostShare[cell];
+        const bool injected = (i >= nSorted + nInjStart);
         const int injPatch = injected ? A.injPatchTail[i - nSorted] : -1;
 
-        int status = 0;
+        int status = 0;   // 0 alive, 1 deleted at an open boundary, 2 lost
         // ---- E1: mcOpenBoundary::correct(false), cull behind the moving outflow plane ----
         if (A.hasOpen) {
             const int ks = __ldg(M.openCellStart + cell), ke = __ldg(M.openCellStart + cell + 1);
@@ -406,7 +377,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
                     if (xp < eta * (Un * deltaT)) {
                         const double mpd = massPerDepth(M, pos, m);
                         accS[ACC_MASS_OUT * K1_THREADS] -= mpd;
-                        for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * phi[P.conserved[cs]];
+                        for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, P.conserved[cs]);
                         status = 1;
                     }
                 }
@@ -418,58 +389,135 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
         {
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_MINUS * K1_THREADS] -= mpd;
-            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * phi[P.conserved[cs]];
+            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, P.conserved[cs]);
         }
         // ---- E3: position correction gather ----
         TetL T;
-        loadTet(M.tets, tet, T);
+        loadTet(M.tets, stage, tet, T);
         V3 Ucorr = mk(0, 0, 0);
         if (P.positionCorrection != PDFB200_POSCORR_NONE) {
             if (P.interpUPosCorr == PDFB200_INTERP_CELL) {
                 const double *q = A.nodePC + (size_t)T.cell * 4;
                 Ucorr = mk(q[0], q[1], q[2]);
             } else {
-                double w0[4];
-                baryAt(T, pos - cellCentre(M, T.cell), w0);
-                const double fb = clamp01(w0[1]), fc = clamp01(w0[2]), fa = clamp01(w0[0]), fd = clamp01(w0[3]);
+                double a0, a1, a2, a3;
+                baryAt(T, pos - mk(T.cx, T.cy, T.cz), a0, a1, a2, a3);
+                const double fb = clamp01(a1), fc = clamp01(a2), fa = clamp01(a0), fd = clamp01(a3);
                 const double2 *qb = reinterpret_cast<const double2 *>(A.nodePC + (nodeP + T.ptB) * 4);
                 const double2 *qc = reinterpret_cast<const double2 *>(A.nodePC + (nodeP + T.ptC) * 4);
                 const double2 *qa = reinterpret_cast<const double2 *>(A.nodePC + (nodeF + T.face) * 4);
                 const double2 *qd = reinterpret_cast<const double2 *>(A.nodePC + (size_t)T.cell * 4);
-                const double2 b0 = __ldg(qb), b1 = __ldg(qb + 1), c0 = __ldg(qc), c1 = __ldg(qc + 1);
-                const double2 a0 = __ldg(qa), a1 = __ldg(qa + 1), d0 = __ldg(qd), d1 = __ldg(qd + 1);
-                Ucorr.x = fma(fd, d0.x, fma(fa, a0.x, fma(fc, c0.x, fb * b0.x)));
-                Ucorr.y = fma(fd, d0.y, fma(fa, a0.y, fma(fc, c0.y, fb * b0.y)));
-                Ucorr.z = fma(fd, d1.x, fma(fa, a1.x, fma(fc, c1.x, fb * b1.x)));
+                const double2 b0 = __ldg(qb), c0 = __ldg(qc), a0v = __ldg(qa), d0 = __ldg(qd);
+                const double b1 = __ldg(reinterpret_cast<const double *>(qb + 1)), c1 = __ldg(reinterpret_cast<const double *>(qc + 1));
+                const double a1v = __ldg(reinterpret_cast<const double *>(qa + 1)), d1 = __ldg(reinterpret_cast<const double *>(qd + 1));
+                Ucorr.x = fma(fd, d0.x, fma(fa, a0v.x, fma(fc, c0.x, fb * b0.x)));
+                Ucorr.y = fma(fd, d0.y, fma(fa, a0v.y, fma(fc, c0.y, fb * b0.y)));
+                Ucorr.z = fma(fd, d1, fma(fa, a1v, fma(fc, c1, fb * b1)));
             }
         }
         // ---- E4 ----
         V3 Utrack = U + Ucorr;
         constrainParticle(M, deltaT / 2, pos, U, Ucorr, Utrack);
-        PartFlags fl;
-        fl.reflected = false; fl.reflOpen = false; fl.reflBV = mk(0, 0, 0); fl.nSteps = 0;
+        bool reflected = false, reflOpen = false;
+        V3 reflBV = mk(0, 0, 0);
         const V3 Uold = U, posOld = pos;
         const int tetOld = tet;
-        // ---- E5: first tracking pass over eta*deltaT/2 ----
-        double w[4];
-        double stepFraction = 0.0;
-        if (injected) { double u0, u1; rngUniform2(A.key, id, sc.step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
-        status = trackParticle(A, eta * (deltaT / 2.), stepFraction, pos, tet, T, Utrack, U, Ucorr, fl, w, m, phi, accS);
-        if (status != 0) {
-            if (status == 2) { atomicAdd(A.lostMass + T.cell, m); accS[ACC_N_LOST * K1_THREADS] += 1; }
-            else accS[ACC_N_DELETED * K1_THREADS] += 1;
-            A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1;
-            continue;
-        }
-        cell = T.cell;
-        // ---- E6: Courant number ----
-        fl.nSteps = 0;
-        double Co = courantNo(M, cell, Utrack);
-        // ---- E7: models at the mid-point ----
-        {
+        double w0 = 0, w1 = 0, w2 = 0, w3 = 0, CoKeep = 0;
+
+        // ---- E5 (phase 0: eta*deltaT/2) and E10 (phase 1: eta*deltaT): mcParticle::move on the
+        //      tet walk (see oracle/src/cloud.cpp Cloud::move; identical expressions) ----
+#pragma unroll 1
+#ifdef K1_EXP_ONEPHASE   // timing experiment only: skips the full-step walk
+        for (int phase = 0; phase < 1; ++phase) {
+#else
+        for (int phase = 0; phase < 2; ++phase) {
+#endif
+            double stepFraction = 0.0;
+            if (phase == 0 && injected) { double u0, u1; rngUniform2(A.key, id, step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
+            const double trackTime = (phase == 0) ? eta * (deltaT / 2.) : eta * deltaT;
+            double tEnd = (1.0 - stepFraction) * trackTime;
+#ifdef K1_EXP_NOWALK   // timing experiment only
+            tEnd = 0;
+#endif
+            const double dtMax = tEnd;
+            int entry = -1, nSteps = 0;
+            bool haveW = false;
+            while (tEnd > 0 && status == 0) {
+                double dt = fmin(dtMax, tEnd);
+                V3 dest = pos + dt * Utrack;
+                constrainDir(M.geoD, dest);
+                const V3 x0 = pos;
+                const V3 dx = dest - x0;
+                double tf = 1.0;
+                for (;;) {
+                    const V3 r = x0 - mk(T.cx, T.cy, T.cz);
+                    double p0, p1, p2, p3;
+                    baryAt(T, r, p0, p1, p2, p3);
+                    const double q0 = dotf(T.g0, T.g1, T.g2, dx), q1 = dotf(T.g3, T.g4, T.g5, dx), q2 = dotf(T.g6, T.g7, T.g8, dx);
+                    const double q3 = -((q0 + q1) + q2);
+                    int best = -1;
+                    double pb = 0, qb = 0;
+                    if (entry != 0 && q0 < 0 && p0 + q0 < 0) { best = 0; pb = p0; qb = q0; }
+                    if (entry != 1 && q1 < 0 && p1 + q1 < 0 && (best < 0 || p1 * qb > pb * q1)) { best = 1; pb = p1; qb = q1; }
+                    if (entry != 2 && q2 < 0 && p2 + q2 < 0 && (best < 0 || p2 * qb > pb * q2)) { best = 2; pb = p2; qb = q2; }
+                    if (entry != 3 && q3 < 0 && p3 + q3 < 0 && (best < 0 || p3 * qb > pb * q3)) { best = 3; pb = p3; qb = q3; }
+                    if (best < 0) {
+                        pos = dest;
+                        w0 = p0 + q0; w1 = p1 + q1; w2 = p2 + q2; w3 = p3 + q3;
+                        haveW = true;
+                        tf = 1.0;
+                        break;
+                    }
+                    ++nSteps;
+                    if (nSteps > 1000) { status = 2; break; }
+                    if (best != 3 || T.face < M.nInternalFaces) {
+                        tet = (best == 0) ? T.n0 : (best == 1) ? T.n1 : (best == 2) ? T.n2 : T.n3;
+                        loadTet(M.tets, stage, tet, T);
+                        entry = (best == 1) ? 2 : (best == 2 ? 1 : best);
+                        continue;
+                    }
+                    // boundary face
+                    double s = p3 / (-q3);
+                    s = fmin(1.0, fmax(0.0, s));
+                    pos = x0 + s * dx;
+                    tf = s;
+                    const int bf = T.face - M.nInternalFaces;
+                    const int info = __ldg(M.bfInfo + bf);
+                    const int handler = BF_HANDLER(info);
+                    if (BF_GEOM(info) != PDFB200_PATCH_GENERIC || handler == PDFB200_BC_EMPTY) { status = 2; break; }
+                    const double4 n4 = M.bfNormal[bf];
+                    const V3 nw = mk(n4.x, n4.y, n4.z);
+                    if (handler != PDFB200_BC_SLIP) {
+                        const double Un = A.Un[bf];
+                        if (Un < 0 || !BF_REFLECTING(info)) {
+                            const double mpd = massPerDepth(M, pos, m);
+                            const int base = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
+                            accS[base * K1_THREADS] -= mpd;
+                            for (int cs = 0; cs < P.nConserved; ++cs) accS[(base + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, P.conserved[cs]);
+                            status = 1;
+                            break;
+                        }
+                        reflOpen = true;
+                        reflBV = nw * Un;
+                    }
+                    U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
+                    reflected = true;
+                    entry = 3;
+                    break;
+                }
+                dt *= tf;
+                tEnd -= dt;
+            }
+            if (status != 0) break;
+            if (!haveW) baryAt(T, pos - mk(T.cx, T.cy, T.cz), w0, w1, w2, w3);   // zero-length track or ended on a boundary
+            if (phase == 1) break;
+
+            // ================= mid-point: E6, E7, E9 =================
+            cell = T.cell;
+            double Co = courantNo(M, cell, Utrack);
             double val[NODE_MID_STRIDE];
             double pst[4];
-            interpMid(M, P, A.nodeMid, T, w, val, pst);
+            interpMid(M, P, A.nodeMid, T, w0, w1, w2, w3, val, pst);
             const double *aux = A.cellAux + (size_t)cell * A.auxStride;
             // mcRASOmegaModel::correct
             if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
@@ -479,9 +527,10 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
                 const double fac = 1.0 - exp(-Cmix2 * Omega * eta * deltaT);
                 for (int mI = 0; mI < P.nMixed; ++mI) {
                     const int s = P.mixed[mI];
+                    const double mean = __ldg(aux + 2 + s);
 #pragma unroll
                     for (int k = 0; k < PDFB200_MAX_PHI; ++k)
-                        if (k == s) phi[k] -= fac * (phi[k] - aux[2 + k]);
+                        if (k == s) phi[k] -= fac * (phi[k] - mean);
                 }
             }
             // reaction model
@@ -492,28 +541,41 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
             }
             // the six normals of the step
             double xi0, xi1, xi2, gd0, gd1, gd2;
-            rngNormal2(A.key, id, sc.step, RNG_STEP_NORMALS, 0, xi0, xi1);
-            rngNormal2(A.key, id, sc.step, RNG_STEP_NORMALS, 1, xi2, gd0);
-            rngNormal2(A.key, id, sc.step, RNG_STEP_NORMALS, 2, gd1, gd2);
+            {
+                // one copy of the Philox + Box-Muller code (instruction-cache footprint)
+                double na = 0, nb2 = 0, nc2 = 0, nd2 = 0, ne = 0, nf = 0;
+#pragma unroll 1
+                for (uint32_t sub = 0; sub < 3; ++sub) {
+                    double a, b;
+#ifdef K1_EXP_NORNG   // timing experiment only: results are wrong
+                    a = 0.1 * sub; b = -0.1 * sub;
+#else
+                    rngNormal2(A.key, id, step, RNG_STEP_NORMALS, sub, a, b);
+#endif
+                    if (sub == 0) { na = a; nb2 = b; } else if (sub == 1) { nc2 = a; nd2 = b; } else { ne = a; nf = b; }
+                }
+                xi0 = na; xi1 = nb2; xi2 = nc2; gd0 = nd2; gd1 = ne; gd2 = nf;
+            }
             // mcSLMFullVelocityModel::correct
             if (P.velocityModel != PDFB200_VELOCITY_NONE) {
                 const double dTp = eta * deltaT;
                 const V3 UFap = mk(val[NM_U], val[NM_U + 1], val[NM_U + 2]);
                 // gradInterpolationConstantTet: g_d*cell + g_b*ptB + g_c*ptC + g_a*face
-                const V3 ga = mk(T.g[0], T.g[1], T.g[2]), gb = mk(T.g[3], T.g[4], T.g[5]), gc = mk(T.g[6], T.g[7], T.g[8]);
+                const V3 ga = mk(T.g0, T.g1, T.g2), gb = mk(T.g3, T.g4, T.g5), gc = mk(T.g6, T.g7, T.g8);
                 const V3 gdv = -((ga + gb) + gc);
                 V3 gradP = (gdv * pst[3] + gb * pst[1]) + gc * pst[2];
                 gradP = gradP + ga * pst[0];
                 const double kFap = fmax(val[NM_K], P.kMin);
                 const V3 diffUap = mk(val[NM_DU], val[NM_DU + 1], val[NM_DU + 2]);
                 const double Acoef = -(0.5 * P.C1 + 0.75 * P.C0) * Omega;
-                const V3 B = -(gradP / rho + Acoef * UFap);
+                const V3 B = -(gradP * (1.0 / rho) + Acoef * UFap);   // one reciprocal instead of three divisions
                 const double sq = sqrt(P.C0 * kFap * Omega * dTp);
                 const V3 deltaU = (B + Acoef * U) * dTp + sq * mk(xi0, xi1, xi2);
                 const V3 Ubefore = U;
                 U = U + (((deltaU + 0.5 * Acoef * deltaU * dTp) + diffUap * deltaT) + (Ubefore - UFap) * aux[0] * deltaT);
                 Co = fmax(Co, Omega);
             }
+            CoKeep = Co;
             // local time stepping
             if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
             else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) eta = fmin(P.CFL / stabilise(deltaT * Co, PDF_VSMALL), P.ltsUpperBound);
@@ -521,16 +583,14 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
 
             // ---- E9: mid-point rule from the old position ----
             pos = posOld;
-            if (tet != tetOld) { tet = tetOld; loadTet(M.tets, tet, T); }
-            if (fl.reflected) Utrack = Uold; else Utrack = 0.5 * (Uold + U);
+            if (tet != tetOld) { tet = tetOld; loadTet(M.tets, stage, tet, T); }
+            if (reflected) Utrack = Uold; else Utrack = 0.5 * (Uold + U);
             const double hNum = __ldg(reinterpret_cast<const double *>(M.cellCentre4 + T.cell) + 3);
             const double C = P.DNum * sqrt(hNum * deltaT * mag3(Utrack)) / deltaT;
             Utrack = Utrack + mk(C * gd0, C * gd1, C * gd2);
             Utrack = Utrack + Ucorr;
             constrainParticle(M, deltaT, pos, U, Ucorr, Utrack);
         }
-        // ---- E10: second tracking pass over eta*deltaT ----
-        status = trackParticle(A, eta * deltaT, 0.0, pos, tet, T, Utrack, U, Ucorr, fl, w, m, phi, accS);
         if (status != 0) {
             if (status == 2) { atomicAdd(A.lostMass + T.cell, m); accS[ACC_N_LOST * K1_THREADS] += 1; }
             else accS[ACC_N_DELETED * K1_THREADS] += 1;
@@ -539,7 +599,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
         }
         cell = T.cell;
         // ---- E11: mcOpenBoundary::correct(true) ----
-        if (fl.reflOpen) U = U + 2 * fl.reflBV;
+        if (reflOpen) U = U + 2 * reflBV;
 
         // ---- write back in sorted order ----
         A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
@@ -554,13 +614,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_evolve(const K1Args A) {
         {
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_PLUS * K1_THREADS] += mpd;
-            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * phi[P.conserved[cs]];
+            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * pickPhi(phi, P.conserved[cs]);
             accS[ACC_N_ALIVE * K1_THREADS] += 1;
             accM[ACC_UMAX * K1_THREADS] = fmax(accM[ACC_UMAX * K1_THREADS], mag3(U));
             accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
             accM[ACC_ETAMAX * K1_THREADS] = fmax(accM[ACC_ETAMAX * K1_THREADS], eta);
             accM[ACC_NEG_ETAMIN * K1_THREADS] = fmax(accM[ACC_NEG_ETAMIN * K1_THREADS], -eta);
-            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], Co);
+            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], CoKeep);
         }
     }
 

@@ -133,7 +133,7 @@ __global__ void k_build_tets(int nCells, int nInternalFaces, const int *cellFace
             if (f < nInternalFaces) T.nbr[3] = (own ? faceTetStartNei[f] : faceTetStartOwn[f]) + i;
             else T.nbr[3] = -1;
             T.face = f; T.ptB = ptBI; T.ptC = ptCI; T.cell = c;
-            T.pad[0] = T.pad[1] = T.pad[2] = 0;
+            T.centre[0] = d.x; T.centre[1] = d.y; T.centre[2] = d.z;
             tets[t] = T;
         }
     }

@@ -185,10 +185,10 @@ __global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const 
     const V3 pos = mk(S.px[i], S.py[i], S.pz[i]);
     TetL T;
     loadTet(M.tets, S.tet[i], T);
-    double w[4];
-    baryAt(T, pos - cellCentre(M, T.cell), w);
+    double w0, w1, w2, w3;
+    baryAt(T, pos - cellCentre(M, T.cell), w0, w1, w2, w3);
     double val[NODE_MID_STRIDE], pst[4];
-    interpMid(M, P, nodeMid, T, w, val, pst);
+    interpMid(M, P, nodeMid, T, w0, w1, w2, w3, val, pst);
     double eta = 1.0;
     if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
     else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
@@ -359,9 +359,9 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
             if (P.localTimeStepping == PDFB200_LTS_CELL) {
                 TetL TL;
                 loadTet(M.tets, tet, TL);
-                double w[4], val[NODE_MID_STRIDE], pst[4];
-                baryAt(TL, pos - cellCentre(M, cellI), w);
-                interpMid(M, P, nodeMid, TL, w, val, pst);
+                double w0, w1, w2, w3, val[NODE_MID_STRIDE], pst[4];
+                baryAt(TL, pos - cellCentre(M, cellI), w0, w1, w2, w3);
+                interpMid(M, P, nodeMid, TL, w0, w1, w2, w3, val, pst);
                 eta = val[NM_ETA];
             } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
                 V3 Ut = Up;
@@ -781,7 +781,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     DBuf<int> ncCounts; ncCounts.alloc(2);
     CUDA_CHECK(cudaEventRecord(evStart, stream));
     int k1Blocks = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k_evolve, K1_THREADS, (ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double)));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k_evolve, K1_THREADS, K1_SMEM_BYTES));
     k1Blocks = std::max(1, std::min(k1Blocks, 16));
     auto mark = [&](int r) { CUDA_CHECK(cudaEventRecord(evMark[r], stream)); };
 
@@ -830,7 +830,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
         CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
         mark(1);
-        LAUNCH(this, k_evolve, gridK1, K1_THREADS, (ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double), A);
+        LAUNCH(this, k_evolve, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
         mark(2);
         LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
         LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
