@@ -37,7 +37,9 @@ struct HostPatch { int start, size, geom, handler, reflecting; };
 
 // layout of the particle kernel's per-thread accumulators
 #define K1_THREADS 128
+#ifndef K1_MAXCONS
 #define K1_MAXCONS 3
+#endif
 #define K1_NC1 (1 + K1_MAXCONS)
 // thread-private shared-memory accumulators
 #define ACC_DM_MINUS 0

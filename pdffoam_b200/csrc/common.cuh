@@ -132,6 +132,16 @@ __device__ inline void st3(double *p, long long i, V3 v) { p[3 * i] = v.x; p[3 *
 // fused dot product of the tet walk: the same fma chain as oracle dotf()
 __device__ inline double dotf(double gx, double gy, double gz, V3 r) { return fma(gx, r.x, fma(gy, r.y, gz * r.z)); }
 
+// 256-bit read-only global load (SASS: LDG.E.ENL2.256.CONSTANT, new on sm_100). One
+// instruction per 32-byte chunk instead of two: half the L1 wavefronts for the
+// record gathers of the particle kernel. The address must be 32-byte aligned.
+struct __align__(32) D4 { double x, y, z, w; };
+__device__ __forceinline__ D4 ld256(const void *p) {
+    D4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
 // rotationTensor(n1,n2) (OpenFOAM transform.H), row-major
 __host__ __device__ inline void rotationTensor(V3 n1, V3 n2, double T[9]) {
     const double s = dot3(n1, n2);

@@ -50,6 +50,7 @@ struct TetL {
     double cx, cy, cz;           // centre of the cell (vertex d)
 };
 
+// OPTIONAL (-DK1_STAGE, off by default: measured no gain on B200, see profiles/README.md).
 // Per-warp staging of tet records in shared memory ("cell geometry staged in
 // shared memory"): at the start of an iteration each warp copies the records
 // of the cells its 32 particles start in (coalesced 128-bit loads) into its own
@@ -64,17 +65,32 @@ struct TetStage {
 };
 
 __device__ __forceinline__ void loadTet(const TetRec *tets, const TetStage &S, int t, TetL &T) {
+#ifndef K1_STAGE
+    const char *rec = reinterpret_cast<const char *>(tets + t);
+#else
     const unsigned off = (unsigned)(t - S.lo);
     const char *rec = (off < (unsigned)S.n) ? S.base + (size_t)off * STAGE_STRIDE_B : reinterpret_cast<const char *>(tets + t);
+#endif
+#ifndef K1_STAGE
+    // four 256-bit loads (LDG.E.256, sm_100): half the L1 wavefronts of 128-bit loads for a
+    // record gather in which most lanes touch different 128-byte lines
+    const D4 r0 = ld256(rec), r1 = ld256(rec + 32), r2 = ld256(rec + 64), r3 = ld256(rec + 96);
+    T.n0 = __double2loint(r0.x); T.n1 = __double2hiint(r0.x); T.n2 = __double2loint(r0.y); T.n3 = __double2hiint(r0.y);
+    T.face = __double2loint(r0.z); T.ptB = __double2hiint(r0.z); T.ptC = __double2loint(r0.w); T.cell = __double2hiint(r0.w);
+    T.g0 = r1.x; T.g1 = r1.y; T.g2 = r1.z; T.g3 = r1.w; T.g4 = r2.x; T.g5 = r2.y; T.g6 = r2.z; T.g7 = r2.w;
+    T.g8 = r3.x; T.cx = r3.y; T.cy = r3.z; T.cz = r3.w;
+    return;
+#else
     const int4 *pi = reinterpret_cast<const int4 *>(rec);
+    const double2 *pd = reinterpret_cast<const double2 *>(rec) + 2;
     const int4 a = pi[0], b = pi[1];
+    const double2 g0 = pd[0], g1 = pd[1], g2 = pd[2], g3 = pd[3], g4 = pd[4], g5 = pd[5];
     T.n0 = a.x; T.n1 = a.y; T.n2 = a.z; T.n3 = a.w;
     T.face = b.x; T.ptB = b.y; T.ptC = b.z; T.cell = b.w;
-    const double2 *pd = reinterpret_cast<const double2 *>(rec) + 2;
-    const double2 g0 = pd[0], g1 = pd[1], g2 = pd[2], g3 = pd[3], g4 = pd[4], g5 = pd[5];
     T.g0 = g0.x; T.g1 = g0.y; T.g2 = g1.x; T.g3 = g1.y; T.g4 = g2.x; T.g5 = g2.y;
     T.g6 = g3.x; T.g7 = g3.y; T.g8 = g4.x;
     T.cx = g4.y; T.cy = g5.x; T.cz = g5.y;
+#endif
 }
 // plain global path (kernels without staging)
 __device__ __forceinline__ void loadTet(const TetRec *tets, int t, TetL &T) {
@@ -100,10 +116,11 @@ __device__ __forceinline__ void baryAt(const TetL &T, V3 r, double &w0, double &
 __device__ __forceinline__ double clamp01(double x) { return fmax(0.0, fmin(1.0, x)); }
 
 // phi[idx] without dynamic indexing
-__device__ __forceinline__ double pickPhi(const double (&phi)[PDFB200_MAX_PHI], int idx) {
+template <int NPHI>
+__device__ __forceinline__ double pickPhi(const double (&phi)[NPHI], int idx) {
     double v = 0.0;
 #pragma unroll
-    for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == idx) v = phi[k];
+    for (int k = 0; k < NPHI; ++k) if (k == idx) v = phi[k];
     return v;
 }
 
@@ -170,16 +187,12 @@ __device__ __forceinline__ double stabilise(double x, double y) { return x < 0 ?
 // Reaction models on one particle: mcColdReactionModel.C:62-65,
 // mcBurkeSchumannReactionModel.C:77-91, mcSteadyFlamelet.C:304-329.
 struct FlameletTables { const double *chi, *z, *fields; int nChi, nZ; };
-__device__ __forceinline__ void reactionCorrectTable(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
-                                                     double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho);
+template <int NPHI>
 __device__ __forceinline__ void reactionCorrect(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
-                                                double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho) {
-    if (P.reactionModel == PDFB200_REACTION_COLD) rho = P.coldDensity;
-    else if (P.reactionModel != PDFB200_REACTION_NONE) reactionCorrectTable(P, F, Omega, zVar, pCell, phi, rho);
-}
-__device__ __forceinline__ void reactionCorrectTable(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
-                                                  double pCell, double (&phi)[PDFB200_MAX_PHI], double &rho) {
-    if (P.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN) {
+                                                double pCell, double (&phi)[NPHI], double &rho) {
+    if (P.reactionModel == PDFB200_REACTION_COLD) {
+        rho = P.coldDensity;
+    } else if (P.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN) {
         const double z = pickPhi(phi, P.zIdx);
         const double RTox = P.bsRox * P.bsTox, RTfuel = P.bsRfuel * P.bsTfuel, RTstoi = P.bsRstoi * P.bsTstoi;
         const double RT = z < P.bsZstoi ? (RTstoi - RTox) / P.bsZstoi * z + RTox
@@ -188,7 +201,7 @@ __device__ __forceinline__ void reactionCorrectTable(const pdfb200_params &P, co
                                         : (P.bsTfuel - P.bsTstoi) / (1 - P.bsZstoi) * (z - P.bsZstoi) + P.bsTstoi;
         rho = pCell / RT;
 #pragma unroll
-        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.TIdx) phi[k] = Tt;
+        for (int k = 0; k < NPHI; ++k) if (k == P.TIdx) phi[k] = Tt;
     } else if (P.reactionModel == PDFB200_REACTION_STEADY_FLAMELET) {
         const double z = pickPhi(phi, P.zIdx);
         const double chi = fmax(P.Cchi * Omega * zVar, PDF_SMALL);
@@ -197,11 +210,11 @@ __device__ __forceinline__ void reactionCorrectTable(const pdfb200_params &P, co
         findCoeffsDev(F.chi, F.nChi, chi, ichi, wchi);
         rho = binterpDev(F.fields, F.nChi, F.nZ, ichi, wchi, iz, wz);
 #pragma unroll
-        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.chiIdx) phi[k] = chi;
+        for (int k = 0; k < NPHI; ++k) if (k == P.chiIdx) phi[k] = chi;
         for (int a = 0; a < P.nAdded; ++a) {
             const double v = binterpDev(F.fields + (size_t)(1 + a) * F.nChi * F.nZ, F.nChi, F.nZ, ichi, wchi, iz, wz);
 #pragma unroll
-            for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k == P.addedIdx[a]) phi[k] = v;
+            for (int k = 0; k < NPHI; ++k) if (k == P.addedIdx[a]) phi[k] = v;
         }
     }
 }
@@ -214,23 +227,25 @@ __device__ __forceinline__ void interpMid(const DMesh &M, const pdfb200_params &
                                           double w0, double w1, double w2, double w3, double (&val)[NODE_MID_STRIDE],
                                           double (&pst)[4]) {
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
-    const double2 *nb = reinterpret_cast<const double2 *>(nodeMid + (nodeP + T.ptB) * NODE_MID_STRIDE);
-    const double2 *nc = reinterpret_cast<const double2 *>(nodeMid + (nodeP + T.ptC) * NODE_MID_STRIDE);
-    const double2 *na = reinterpret_cast<const double2 *>(nodeMid + (nodeF + T.face) * NODE_MID_STRIDE);
-    const double2 *nd = reinterpret_cast<const double2 *>(nodeMid + (size_t)T.cell * NODE_MID_STRIDE);
+    const double *nb = nodeMid + (nodeP + T.ptB) * NODE_MID_STRIDE;
+    const double *nc = nodeMid + (nodeP + T.ptC) * NODE_MID_STRIDE;
+    const double *na = nodeMid + (nodeF + T.face) * NODE_MID_STRIDE;
+    const double *nd = nodeMid + (size_t)T.cell * NODE_MID_STRIDE;
     const double fb = clamp01(w1), fc = clamp01(w2), fa = clamp01(w0), fd = clamp01(w3);
     const bool anyCell = (P.interpU == PDFB200_INTERP_CELL) | (P.interpk == PDFB200_INTERP_CELL) |
                          (P.interpDiffU == PDFB200_INTERP_CELL) | (P.interpOmega == PDFB200_INTERP_CELL) |
                          (P.interpEta == PDFB200_INTERP_CELL) | (P.interpZVar == PDFB200_INTERP_CELL);
     double cv[NODE_MID_STRIDE];
+    // 96-byte node records: three 256-bit loads per node
 #pragma unroll
-    for (int k = 0; k < (NODE_MID_STRIDE - 1) / 2 + 1; ++k) {
-        if (2 * k >= NM_ZVAR + 1) break;
-        const double2 vb = __ldg(nb + k), vc = __ldg(nc + k), va = __ldg(na + k), vd = __ldg(nd + k);
-        val[2 * k] = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
-        val[2 * k + 1] = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
-        cv[2 * k] = vd.x; cv[2 * k + 1] = vd.y;
-        if (2 * k == NM_PSTAR) { pst[0] = va.x; pst[1] = vb.x; pst[2] = vc.x; pst[3] = vd.x; }
+    for (int k = 0; k < NODE_MID_STRIDE / 4; ++k) {
+        const D4 vb = ld256(nb + 4 * k), vc = ld256(nc + 4 * k), va = ld256(na + 4 * k), vd = ld256(nd + 4 * k);
+        val[4 * k] = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
+        val[4 * k + 1] = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
+        val[4 * k + 2] = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
+        val[4 * k + 3] = fma(fd, vd.w, fma(fa, va.w, fma(fc, vc.w, fb * vb.w)));
+        cv[4 * k] = vd.x; cv[4 * k + 1] = vd.y; cv[4 * k + 2] = vd.z; cv[4 * k + 3] = vd.w;
+        if (4 * k == NM_PSTAR) { pst[0] = va.x; pst[1] = vb.x; pst[2] = vc.x; pst[3] = vd.x; }
     }
     if (anyCell) {   // interpolation scheme "cell": the cell value
         if (P.interpU == PDFB200_INTERP_CELL) { val[NM_U] = cv[NM_U]; val[NM_U + 1] = cv[NM_U + 1]; val[NM_U + 2] = cv[NM_U + 2]; }
@@ -303,8 +318,14 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #define K1_MIN_BLOCKS 4
 #endif
 // dynamic shared memory: thread-private accumulators + one staging window per warp
+#ifdef K1_STAGE
 #define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double) + (K1_THREADS / 32) * STAGE_RECORDS * STAGE_STRIDE_B)
+#else
+#define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double))
+#endif
 
+// NPHI = compile-time bound on the particle scalars held in registers (nPhi <= NPHI)
+template <int NPHI>
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Args A) {
     extern __shared__ double smem[];
     double *accS = smem + threadIdx.x;                         // sums: accS[k*K1_THREADS]
@@ -335,6 +356,9 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
 
         // ---- stage the tet records of the warp's start cells in shared memory ----
         TetStage stage;
+#ifndef K1_STAGE
+        stage.base = nullptr; stage.lo = 0; stage.n = 0;
+#else
         {
             const int myLo = (cell >= 0) ? __ldg(M.cellTetStart + cell) : 0x7fffffff;
             const int lo = __reduce_min_sync(0xffffffffu, myLo);
@@ -347,14 +371,15 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
             __syncwarp();
             stage.base = stageWin; stage.lo = lo; stage.n = n;
         }
+#endif
         if (!active) continue;
         if (cell < 0) { A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
         V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
         V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
         double m = A.in.m[slot], Omega = A.in.omega[slot], rho = A.in.rho[slot], eta = A.in.eta[slot];
-        double phi[PDFB200_MAX_PHI];
+        double phi[NPHI];
 #pragma unroll
-        for (int k = 0; k < PDFB200_MAX_PHI; ++k) phi[k] = (k < nPhi) ? A.in.phi[k][slot] : 0.0;
+        for (int k = 0; k < NPHI; ++k) phi[k] = (k < nPhi) ? A.in.phi[k][slot] : 0.0;
         int tet = A.in.tet[slot];
         const uint32_t id = A.in.id[slot];
         if (anyLost) m += A.lostShare[cell];
@@ -403,23 +428,19 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                 double a0, a1, a2, a3;
                 baryAt(T, pos - mk(T.cx, T.cy, T.cz), a0, a1, a2, a3);
                 const double fb = clamp01(a1), fc = clamp01(a2), fa = clamp01(a0), fd = clamp01(a3);
-                const double2 *qb = reinterpret_cast<const double2 *>(A.nodePC + (nodeP + T.ptB) * 4);
-                const double2 *qc = reinterpret_cast<const double2 *>(A.nodePC + (nodeP + T.ptC) * 4);
-                const double2 *qa = reinterpret_cast<const double2 *>(A.nodePC + (nodeF + T.face) * 4);
-                const double2 *qd = reinterpret_cast<const double2 *>(A.nodePC + (size_t)T.cell * 4);
-                const double2 b0 = __ldg(qb), c0 = __ldg(qc), a0v = __ldg(qa), d0 = __ldg(qd);
-                const double b1 = __ldg(reinterpret_cast<const double *>(qb + 1)), c1 = __ldg(reinterpret_cast<const double *>(qc + 1));
-                const double a1v = __ldg(reinterpret_cast<const double *>(qa + 1)), d1 = __ldg(reinterpret_cast<const double *>(qd + 1));
-                Ucorr.x = fma(fd, d0.x, fma(fa, a0v.x, fma(fc, c0.x, fb * b0.x)));
-                Ucorr.y = fma(fd, d0.y, fma(fa, a0v.y, fma(fc, c0.y, fb * b0.y)));
-                Ucorr.z = fma(fd, d1, fma(fa, a1v, fma(fc, c1, fb * b1)));
+                // 32-byte node records: one 256-bit load per node
+                const D4 vb = ld256(A.nodePC + (nodeP + T.ptB) * 4), vc = ld256(A.nodePC + (nodeP + T.ptC) * 4);
+                const D4 va = ld256(A.nodePC + (nodeF + T.face) * 4), vd = ld256(A.nodePC + (size_t)T.cell * 4);
+                Ucorr.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
+                Ucorr.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
+                Ucorr.z = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
             }
         }
         // ---- E4 ----
         V3 Utrack = U + Ucorr;
         constrainParticle(M, deltaT / 2, pos, U, Ucorr, Utrack);
-        bool reflected = false, reflOpen = false;
-        V3 reflBV = mk(0, 0, 0);
+        bool reflected = false;
+        int reflBf = -1;   // boundary face of the last open-boundary reflection (mcOpenBoundary.C:201-204)
         const V3 Uold = U, posOld = pos;
         const int tetOld = tet;
         double w0 = 0, w1 = 0, w2 = 0, w3 = 0, CoKeep = 0;
@@ -455,12 +476,20 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                     baryAt(T, r, p0, p1, p2, p3);
                     const double q0 = dotf(T.g0, T.g1, T.g2, dx), q1 = dotf(T.g3, T.g4, T.g5, dx), q2 = dotf(T.g6, T.g7, T.g8, dx);
                     const double q3 = -((q0 + q1) + q2);
-                    int best = -1;
-                    double pb = 0, qb = 0;
-                    if (entry != 0 && q0 < 0 && p0 + q0 < 0) { best = 0; pb = p0; qb = q0; }
-                    if (entry != 1 && q1 < 0 && p1 + q1 < 0 && (best < 0 || p1 * qb > pb * q1)) { best = 1; pb = p1; qb = q1; }
-                    if (entry != 2 && q2 < 0 && p2 + q2 < 0 && (best < 0 || p2 * qb > pb * q2)) { best = 2; pb = p2; qb = q2; }
-                    if (entry != 3 && q3 < 0 && p3 + q3 < 0 && (best < 0 || p3 * qb > pb * q3)) { best = 3; pb = p3; qb = q3; }
+                    // exit face: sequential scan a,b,c,d written with selects (no branches);
+                    // candidate i: not the entry face, moving towards it, and its plane lies before dest
+                    const bool c0 = (entry != 0) & (q0 < 0) & (p0 + q0 < 0);
+                    const bool c1 = (entry != 1) & (q1 < 0) & (p1 + q1 < 0);
+                    const bool c2 = (entry != 2) & (q2 < 0) & (p2 + q2 < 0);
+                    const bool c3 = (entry != 3) & (q3 < 0) & (p3 + q3 < 0);
+                    int best = c0 ? 0 : -1;
+                    double pb = c0 ? p0 : 0.0, qb = c0 ? q0 : 0.0;
+                    const bool t1 = c1 & ((best < 0) | (p1 * qb > pb * q1));
+                    best = t1 ? 1 : best; pb = t1 ? p1 : pb; qb = t1 ? q1 : qb;
+                    const bool t2 = c2 & ((best < 0) | (p2 * qb > pb * q2));
+                    best = t2 ? 2 : best; pb = t2 ? p2 : pb; qb = t2 ? q2 : qb;
+                    const bool t3 = c3 & ((best < 0) | (p3 * qb > pb * q3));
+                    best = t3 ? 3 : best;
                     if (best < 0) {
                         pos = dest;
                         w0 = p0 + q0; w1 = p1 + q1; w2 = p2 + q2; w3 = p3 + q3;
@@ -470,10 +499,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                     }
                     ++nSteps;
                     if (nSteps > 1000) { status = 2; break; }
-                    if (best != 3 || T.face < M.nInternalFaces) {
-                        tet = (best == 0) ? T.n0 : (best == 1) ? T.n1 : (best == 2) ? T.n2 : T.n3;
+                    if (best != 3 || T.n3 >= 0) {   // n3 < 0 marks a boundary face
+                        int nb = (best == 0) ? T.n0 : T.n1;
+                        nb = (best == 2) ? T.n2 : nb;
+                        tet = (best == 3) ? T.n3 : nb;
                         loadTet(M.tets, stage, tet, T);
-                        entry = (best == 1) ? 2 : (best == 2 ? 1 : best);
+                        entry = best ^ (((best == 1) | (best == 2)) ? 3 : 0);   // the shared face is opposite c (b) in the tet across b (c)
                         continue;
                     }
                     // boundary face
@@ -497,8 +528,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                             status = 1;
                             break;
                         }
-                        reflOpen = true;
-                        reflBV = nw * Un;
+                        reflBf = bf;
                     }
                     U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
                     reflected = true;
@@ -529,7 +559,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                     const int s = P.mixed[mI];
                     const double mean = __ldg(aux + 2 + s);
 #pragma unroll
-                    for (int k = 0; k < PDFB200_MAX_PHI; ++k)
+                    for (int k = 0; k < NPHI; ++k)
                         if (k == s) phi[k] -= fac * (phi[k] - mean);
                 }
             }
@@ -599,16 +629,24 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
         }
         cell = T.cell;
         // ---- E11: mcOpenBoundary::correct(true) ----
-        if (reflOpen) U = U + 2 * reflBV;
+        if (reflBf >= 0) {
+            const double4 n4 = M.bfNormal[reflBf];
+            const V3 reflBV = mk(n4.x, n4.y, n4.z) * A.Un[reflBf];
+            U = U + 2 * reflBV;
+        }
 
         // ---- write back in sorted order ----
         A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
         A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
         A.out.m[i] = m; A.out.omega[i] = Omega; A.out.rho[i] = rho; A.out.eta[i] = eta;
 #pragma unroll
-        for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
+        for (int k = 0; k < NPHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
         A.out.cell[i] = cell; A.out.tet[i] = tet; A.out.id[i] = id;
+#ifdef K1_KEY_CELL_ONLY   // experiment: sort by cell only (stable sort keeps the previous order inside a cell)
+        A.keyOut[i] = ((uint32_t)cell << M.tetBits);
+#else
         A.keyOut[i] = ((uint32_t)cell << M.tetBits) | (uint32_t)(tet - __ldg(M.cellTetStart + cell));
+#endif
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {

@@ -781,7 +781,9 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     DBuf<int> ncCounts; ncCounts.alloc(2);
     CUDA_CHECK(cudaEventRecord(evStart, stream));
     int k1Blocks = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k_evolve, K1_THREADS, K1_SMEM_BYTES));
+    // the scalars live in registers: instantiate the kernel for nPhi <= 1, 2, 3 and the general bound
+    void (*k1)(const K1Args) = prm.nPhi <= 1 ? k_evolve<1> : prm.nPhi == 2 ? k_evolve<2> : prm.nPhi == 3 ? k_evolve<3> : k_evolve<PDFB200_MAX_PHI>;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k1, K1_THREADS, K1_SMEM_BYTES));
     k1Blocks = std::max(1, std::min(k1Blocks, 16));
     auto mark = [&](int r) { CUDA_CHECK(cudaEventRecord(evMark[r], stream)); };
 
@@ -830,7 +832,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
         CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
         mark(1);
-        LAUNCH(this, k_evolve, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
+        LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
         mark(2);
         LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
         LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
