@@ -401,6 +401,16 @@ class CloudHandle:
     def set_delta_t(self, dt: float):
         self.lib.check(self.lib.fn("set_delta_t")(self.h, dt), "set_delta_t")
 
+    def download_rho(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Only the mean density, the one field fed back to the FV equations
+        (pdfSimpleFoam/createFields.H:18); `out` may be a pinned host buffer."""
+        if out is None:
+            out = np.zeros(self.mesh.n_cells)
+        s = CellFieldsStruct()
+        s.rho = _dp(out)
+        self.lib.check(self.lib.fn("download_cell_fields")(self.h, C.byref(s)), "download_cell_fields")
+        return out
+
     def download_cell_fields(self, moments: bool = True) -> Dict[str, np.ndarray]:
         nc = self.mesh.n_cells
         out = dict(rho=np.zeros(nc), rhoInst=np.zeros(nc), pnd=np.zeros(nc), pndInst=np.zeros(nc), U=np.zeros((nc, 3)),

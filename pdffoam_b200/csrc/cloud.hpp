@@ -122,7 +122,7 @@ struct Cloud {
     DBuf<uint32_t> keysA, keysB, valsA, valsB, iota;
     DBuf<int> injPatchTail;
     DBuf<unsigned char> cubTemp;
-    DBuf<int> cellStart, cellEnd, ncFlag, ncCount, ncOffset, scanTmp;
+    DBuf<int> cellStart, cellEnd, ncFlag, ncCount, ncOffset, scanTmp, scanTileSums, scanTileOffs;
     DBuf<int> injCount, injOffset;
     DBuf<double> injSums;
     DBuf<double> k1PartSum, k1PartMax, cellPartSum, finalSums;   // deterministic reductions

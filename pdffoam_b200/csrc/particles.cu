@@ -32,15 +32,67 @@ __global__ void k_locate(DMesh M, int n, PState S) {
 }
 
 // fold per-CTA partial rows in index order (one thread per column)
+// launched with (32, 8) threads: warp w folds rows w, w+8, ... of column threadIdx.x, then
+// the eight partials are combined in warp order (fixed order -> deterministic)
 __global__ void k_fold_rows(int nRows, int nCols, const double *rows, double *out, int isMax) {
-    const int k = threadIdx.x;
-    if (k >= nCols) return;
+    __shared__ double part[8][33];
+    const int k = threadIdx.x, w = threadIdx.y;
     double x = isMax ? -PDF_VGREAT : 0.0;
-    for (int r = 0; r < nRows; ++r) { const double y = rows[(size_t)r * nCols + k]; x = isMax ? fmax(x, y) : x + y; }
-    out[k] = x;
+    if (k < nCols)
+        for (int r = w; r < nRows; r += 8) { const double y = rows[(size_t)r * nCols + k]; x = isMax ? fmax(x, y) : x + y; }
+    part[w][k] = x;
+    __syncthreads();
+    if (w == 0 && k < nCols) {
+        double t = part[0][k];
+        for (int j = 1; j < 8; ++j) t = isMax ? fmax(t, part[j][k]) : t + part[j][k];
+        out[k] = t;
+    }
 }
 
-// exclusive scan of an int array in a single CTA (n up to a few million)
+// multi-block exclusive scan, phase 1: sum of each tile of SCAN_TILE elements
+#define SCAN_TILE 4096
+__global__ void k_scan_tile_sums(int n, const int *in, int *tileSums) {
+    __shared__ int warpSums[32];
+    const int base = blockIdx.x * SCAN_TILE;
+    int s = 0;
+    for (int j = threadIdx.x; j < SCAN_TILE; j += blockDim.x) { const int i = base + j; s += i < n ? in[i] : 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = threadIdx.x < (blockDim.x >> 5) ? warpSums[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) tileSums[blockIdx.x] = t;
+    }
+}
+// phase 3: rescan every tile starting from its scanned tile offset (blockDim = 1024, 4 per thread)
+__global__ void k_scan_tiles(int n, const int *in, const int *tileOffsets, int *out) {
+    __shared__ int warpSums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    int v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k) < n ? in[i0 + k] : 0; t += v[k]; }
+    int x = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warpSums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int s = warpSums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        warpSums[lane] = s;
+    }
+    __syncthreads();
+    int run = tileOffsets[blockIdx.x] + (warp > 0 ? warpSums[warp - 1] : 0) + (x - t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
+}
+
+// exclusive scan of an int array in a single CTA (small n, or the tile sums of the multi-block scan)
 __global__ void k_scan_single(int n, const int *in, int *out, int *total) {
     __shared__ int warpSums[32];
     __shared__ int carry;
@@ -293,113 +345,138 @@ struct InletRnd {
     }
 };
 
-// mcInletOutletBoundary::correct(false) (.C:232-354): one thread per boundary
-// face runs the sequential `while (mGen < mIn)` loop; pass 0 counts, pass 1
-// regenerates the same particles (counter-based RNG) and writes them at the
-// offsets of an exclusive scan, so slots and ids are deterministic.
+// mcInletOutletBoundary::correct(false) (.C:232-354): one WARP per boundary face. The
+// reference's loop `while (mGen < mIn)` is sequential only in the accumulated mass: the
+// candidates themselves (inflow velocity by Newton inversion, point on the face, tet,
+// local time step) are keyed by (face, k) and independent, so the 32 lanes generate
+// candidates k = kBase + lane in parallel and then replay the accept/stop logic in k
+// order through shuffles, with the same floating-point sequence as the serial loop.
+// pass 0 counts; pass 1 regenerates the same particles (counter-based RNG) and writes
+// them at the offsets of an exclusive scan, so slots and ids are deterministic.
 __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey key, StepScalars *sc, const double *Un,
                          const double *rho_b, const double *Phi_b, const double *inletU, const double *inletR,
                          const double *fwdTrans, const double *probVec, const double *nodeMid, int *count,
                          const int *offset, int *injPatchTail, double *injSums, int nRanks, int rank, long long capacity) {
-    const int bf = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bf >= M.nBnd) return;
-    const int info = M.bfInfo[bf];
-    if (pass == 0) count[bf] = 0;
-    if (pass == 1) for (int k = 0; k < K1_NC1; ++k) injSums[(size_t)bf * K1_NC1 + k] = 0;
-    if (BF_HANDLER(info) != PDFB200_BC_INLET_OUTLET) return;
-    if ((bf % nRanks) != rank) return;          // inflow faces are dealt round-robin to the ranks
-    if (Un[bf] > 0) return;                     // outlet face
-    if (pass == 1 && count[bf] == 0) return;
-    const int f = M.nInternalFaces + bf, cellI = M.owner[f];
-    const double deltaT = sc->deltaT;
-    const uint32_t step = sc->step;
-    InletRnd inrnd;
-    const V3 Uloc = ld3(inletU, bf);
-    const double *R = inletR + 6 * (size_t)bf;
-    inrnd.updateCoeffs(Uloc.x, sqrt(R[0]));
-    const double mp = rho_b[bf] * M.cellVolumes[cellI] / P.particlesPerCell;
-    const double mIn = rho_b[bf] * inrnd.Q * M.magSf[f] * deltaT;
-    const double *T = fwdTrans + 9 * (size_t)bf;
-    const int s = M.faceStart[f], n = M.faceStart[f + 1] - s, s0 = M.faceStart[M.nInternalFaces];
-    const double *wv = probVec + (s - s0);
-    const V3 C = ld3(M.faceCentres, f), Sf = ld3(M.faceAreas, f);
-    const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
-    const int nGen = pass == 1 ? count[bf] : 0;
-    // pass 1 needs sum(r) of the batch first (adjustAxiSymmetricMass)
-    double sumR = 0.;
-    const int loops = (pass == 1 && M.axisym) ? 2 : 1;
-    for (int loop = 0; loop < loops; ++loop) {
-        const bool writing = pass == 1 && loop == loops - 1;
-        double mGen = 0;
-        uint32_t kDraw = 0;
-        int made = 0;
-        while (mGen < mIn) {
-            double uVal, uTri, n1, n2, a1, a2, uAcc, dummy;
-            rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 0, uVal, uTri);
-            rngNormal2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 1, n1, n2);
-            rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 2, a1, a2);
-            rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 3, uAcc, dummy);
-            ++kDraw;
-            // randomVelocity (.C:215-229): U_global = revTrans & Up = fwdTrans^T & Up
-            const V3 UpL = mk(inrnd.value(uVal), Uloc.y + sqrt(R[3]) * n1, Uloc.z + sqrt(R[5]) * n2);
-            const V3 Up = mk(T[0] * UpL.x + T[3] * UpL.y + T[6] * UpL.z, T[1] * UpL.x + T[4] * UpL.y + T[7] * UpL.z,
-                             T[2] * UpL.x + T[5] * UpL.y + T[8] * UpL.z);
-            // randomPoint (.C:179-212)
-            int idx1 = 0;
-            while (idx1 < n && wv[idx1] < uTri) ++idx1;   // lower_bound
-            int idx2 = idx1 + 1;
-            if (idx2 == n) idx2 = 0;
-            if (idx1 == n) idx1 = n - 1;                  // uTri beyond the last entry (== 1 up to round-off)
-            if (a1 + a2 > 1.0) { a1 = 1.0 - a1; a2 = 1.0 - a2; }
-            V3 pos = ((a1 * ld3(M.points, M.facePoints[s + idx1]) + a2 * ld3(M.points, M.facePoints[s + idx2])) + (1.0 - a1 - a2) * C) - PDF_SMALL * Sf;
-            if (M.nGeoD <= 2) constrainDir(M.geoD, pos);
-            // local time stepping of the new particle
-            const int tet = locateTet(M, pos, cellI);
-            double eta = 1.0;
-            if (P.localTimeStepping == PDFB200_LTS_CELL) {
-                TetL TL;
-                loadTet(M.tets, tet, TL);
-                double w0, w1, w2, w3, val[NODE_MID_STRIDE], pst[4];
-                baryAt(TL, pos - cellCentre(M, cellI), w0, w1, w2, w3);
-                interpMid(M, P, nodeMid, TL, w0, w1, w2, w3, val, pst);
-                eta = val[NM_ETA];
-            } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
-                V3 Ut = Up;
-                constrainDir(M.geoD, Ut);
-                eta = fmin(P.CFL / stabilise(deltaT * courantNo(M, cellI, Ut), PDF_VSMALL), P.ltsUpperBound);
-            }
-            const double m = mp / eta;
-            if (mGen + m > mIn) {
-                if (uAcc > (mIn - mGen) / m) break;
-            }
-            if (pass == 1 && loop == 0 && M.axisym) sumR += mag3(pos - dot3(pos, ax) * ax);
-            if (writing) {
-                const long long tailIdx = (long long)sc->nInjStart + offset[bf] + made;
-                const long long slot = (long long)sc->nSlots + tailIdx;
-                if (slot < capacity) {
-                    double mm = m;
-                    if (M.axisym) mm *= (nGen / sumR) * mag3(pos - dot3(pos, ax) * ax);
-                    S.px[slot] = pos.x; S.py[slot] = pos.y; S.pz[slot] = pos.z;
-                    S.ux[slot] = Up.x; S.uy[slot] = Up.y; S.uz[slot] = Up.z;
-                    S.m[slot] = mm; S.omega[slot] = 0; S.rho[slot] = 0; S.eta[slot] = eta;
-                    const double mpd = massPerDepth(M, pos, mm);
-                    injSums[(size_t)bf * K1_NC1] += mpd;
-                    for (int k = 0; k < P.nPhi; ++k) {
-                        const double ph = Phi_b[(size_t)k * M.nBnd + bf];
-                        S.phi[k][slot] = ph;
-                    }
-                    for (int cs = 0; cs < P.nConserved; ++cs) injSums[(size_t)bf * K1_NC1 + 1 + cs] += mpd * Phi_b[(size_t)P.conserved[cs] * M.nBnd + bf];
-                    S.cell[slot] = cellI; S.tet[slot] = tet;
-                    S.id[slot] = sc->nextId + (uint32_t)(offset[bf] + made) * (uint32_t)nRanks;
-                    injPatchTail[tailIdx] = BF_PATCH(info);
+    const int lane = threadIdx.x & 31;
+    const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int bf = warpGlobal; bf < M.nBnd; bf += nWarps) {
+        const int info = M.bfInfo[bf];
+        if (pass == 0 && lane == 0) count[bf] = 0;
+        if (pass == 1 && lane < K1_NC1) injSums[(size_t)bf * K1_NC1 + lane] = 0;
+        if (BF_HANDLER(info) != PDFB200_BC_INLET_OUTLET) continue;
+        if ((bf % nRanks) != rank) continue;        // inflow faces are dealt round-robin to the ranks
+        if (Un[bf] > 0) continue;                   // outlet face
+        const int nGen = pass == 1 ? count[bf] : 0;
+        if (pass == 1 && nGen == 0) continue;
+        const int f = M.nInternalFaces + bf, cellI = M.owner[f];
+        const double deltaT = sc->deltaT;
+        const uint32_t step = sc->step;
+        InletRnd inrnd;
+        const V3 Uloc = ld3(inletU, bf);
+        const double *R = inletR + 6 * (size_t)bf;
+        inrnd.updateCoeffs(Uloc.x, sqrt(R[0]));
+        const double mp = rho_b[bf] * M.cellVolumes[cellI] / P.particlesPerCell;
+        const double mIn = rho_b[bf] * inrnd.Q * M.magSf[f] * deltaT;
+        const double *T = fwdTrans + 9 * (size_t)bf;
+        const int s = M.faceStart[f], n = M.faceStart[f + 1] - s, s0 = M.faceStart[M.nInternalFaces];
+        const double *wv = probVec + (s - s0);
+        const V3 C = ld3(M.faceCentres, f), Sf = ld3(M.faceAreas, f);
+        const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
+        const double sqRyy = sqrt(R[3]), sqRzz = sqrt(R[5]);
+        double sumR = 0.;
+        const int loops = (pass == 1 && M.axisym) ? 2 : 1;
+        for (int loop = 0; loop < loops; ++loop) {
+            const bool writing = pass == 1 && loop == loops - 1;
+            double mGen = 0;
+            int made = 0;
+            double sums[K1_NC1];
+#pragma unroll
+            for (int k = 0; k < K1_NC1; ++k) sums[k] = 0;
+            bool done = false;
+            for (uint32_t kBase = 0; !done; kBase += 32) {
+                const uint32_t kDraw = kBase + lane;
+                double uVal, uTri, n1, n2, a1, a2, uAcc, dummy;
+                rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 0, uVal, uTri);
+                rngNormal2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 1, n1, n2);
+                rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 2, a1, a2);
+                rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 3, uAcc, dummy);
+                // randomVelocity (.C:215-229): U_global = revTrans & Up = fwdTrans^T & Up
+                const V3 UpL = mk(inrnd.value(uVal), Uloc.y + sqRyy * n1, Uloc.z + sqRzz * n2);
+                const V3 Up = mk(T[0] * UpL.x + T[3] * UpL.y + T[6] * UpL.z, T[1] * UpL.x + T[4] * UpL.y + T[7] * UpL.z,
+                                 T[2] * UpL.x + T[5] * UpL.y + T[8] * UpL.z);
+                // randomPoint (.C:179-212)
+                int idx1 = 0;
+                while (idx1 < n && wv[idx1] < uTri) ++idx1;   // lower_bound
+                int idx2 = idx1 + 1;
+                if (idx2 == n) idx2 = 0;
+                if (idx1 == n) idx1 = n - 1;                  // uTri beyond the last entry (== 1 up to round-off)
+                if (a1 + a2 > 1.0) { a1 = 1.0 - a1; a2 = 1.0 - a2; }
+                V3 pos = ((a1 * ld3(M.points, M.facePoints[s + idx1]) + a2 * ld3(M.points, M.facePoints[s + idx2])) + (1.0 - a1 - a2) * C) - PDF_SMALL * Sf;
+                if (M.nGeoD <= 2) constrainDir(M.geoD, pos);
+                // local time stepping of the new particle
+                const int tet = locateTet(M, pos, cellI);
+                double eta = 1.0;
+                if (P.localTimeStepping == PDFB200_LTS_CELL) {
+                    TetL TL;
+                    loadTet(M.tets, tet, TL);
+                    double w0, w1, w2, w3, val[NODE_MID_STRIDE], pst[4];
+                    baryAt(TL, pos - cellCentre(M, cellI), w0, w1, w2, w3);
+                    interpMid(M, P, nodeMid, TL, w0, w1, w2, w3, val, pst);
+                    eta = val[NM_ETA];
+                } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
+                    V3 Ut = Up;
+                    constrainDir(M.geoD, Ut);
+                    eta = fmin(P.CFL / stabilise(deltaT * courantNo(M, cellI, Ut), PDF_VSMALL), P.ltsUpperBound);
                 }
+                const double m = mp / eta;
+                const double rAx = M.axisym ? mag3(pos - dot3(pos, ax) * ax) : 0.0;
+                // replay of the serial accept/stop logic in k order (all lanes compute the same scalars)
+                int nAcc = 0;
+                for (int j = 0; j < 32; ++j) {
+                    const double mj = __shfl_sync(0xffffffffu, m, j), uj = __shfl_sync(0xffffffffu, uAcc, j);
+                    if (!(mGen < mIn)) { done = true; break; }
+                    if (mGen + mj > mIn) {
+                        if (uj > (mIn - mGen) / mj) { done = true; break; }
+                    }
+                    if (pass == 1 && loop == 0 && M.axisym) sumR += __shfl_sync(0xffffffffu, rAx, j);
+                    mGen += mj;
+                    ++nAcc;
+                }
+                double mm = m, mpd = 0.0;
+                const bool mine = lane < nAcc;
+                if (writing) {
+                    if (M.axisym) mm *= (nGen / sumR) * rAx;
+                    mpd = massPerDepth(M, pos, mm);
+                    if (mine) {
+                        const long long tailIdx = (long long)sc->nInjStart + offset[bf] + made + lane;
+                        const long long slot = (long long)sc->nSlots + tailIdx;
+                        if (slot < capacity) {
+                            S.px[slot] = pos.x; S.py[slot] = pos.y; S.pz[slot] = pos.z;
+                            S.ux[slot] = Up.x; S.uy[slot] = Up.y; S.uz[slot] = Up.z;
+                            S.m[slot] = mm; S.omega[slot] = 0; S.rho[slot] = 0; S.eta[slot] = eta;
+                            for (int k = 0; k < P.nPhi; ++k) S.phi[k][slot] = Phi_b[(size_t)k * M.nBnd + bf];
+                            S.cell[slot] = cellI; S.tet[slot] = tet;
+                            S.id[slot] = sc->nextId + (uint32_t)(offset[bf] + made + lane) * (uint32_t)nRanks;
+                            injPatchTail[tailIdx] = BF_PATCH(info);
+                        }
+                    }
+                    // mass-in sums in k order
+                    for (int j = 0; j < nAcc; ++j) {
+                        const double mj = __shfl_sync(0xffffffffu, mpd, j);
+                        sums[0] += mj;
+                        for (int cs = 0; cs < P.nConserved; ++cs) sums[1 + cs] += mj * Phi_b[(size_t)P.conserved[cs] * M.nBnd + bf];
+                    }
+                }
+                made += nAcc;
+                if (nAcc < 32) done = true;
             }
-            mGen += m;
-            ++made;
+            if (pass == 0 && lane == 0) count[bf] = made;
+            if (writing && lane == 0)
+                for (int k = 0; k < K1_NC1; ++k) injSums[(size_t)bf * K1_NC1 + k] = sums[k];
         }
-        if (pass == 0) count[bf] = made;
     }
 }
+
 
 __global__ void k_inject_finish(int nBnd, const int *total, StepScalars *sc, long long capacity, int nRanks) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -614,6 +691,19 @@ __global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int
 // ===========================================================================
 // host side
 // ===========================================================================
+// exclusive scan of n ints (+ total): one CTA for small n, three kernels otherwise
+static void scanInts(Cloud &c, int n, const int *in, int *out, int *total) {
+    if (n <= 2 * SCAN_TILE) {
+        LAUNCH(&c, k_scan_single, 1, 1024, 0, n, in, out, total);
+        return;
+    }
+    const int nTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if ((int)c.scanTileSums.n < nTiles) { c.scanTileSums.alloc(nTiles); c.scanTileOffs.alloc(nTiles); }
+    LAUNCH(&c, k_scan_tile_sums, nTiles, 256, 0, n, in, c.scanTileSums.p);
+    LAUNCH(&c, k_scan_single, 1, 1024, 0, nTiles, c.scanTileSums.p, c.scanTileOffs.p, total);
+    LAUNCH(&c, k_scan_tiles, nTiles, 1024, 0, n, in, c.scanTileOffs.p, out);
+}
+
 static RngKey makeKey(uint64_t seed) {
     RngKey k;
     k.k0 = (uint32_t)(seed & 0xffffffffu);
@@ -799,15 +889,15 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
                 inletCached = true;
             }
             for (int pass = 0; pass < 2; ++pass) {
-                LAUNCH(this, k_inject, gridFor(nBnd, 64), 64, 0, dm, prm, pass, S[cur], key, scal.p, Un.p, rho_b.p, Phi_b.p, inletU.p,
+                LAUNCH(this, k_inject, std::min(gridFor((long long)nBnd * 32, 128), numSMs * 16), 128, 0, dm, prm, pass, S[cur], key, scal.p, Un.p, rho_b.p, Phi_b.p, inletU.p,
                        inletR.p, fwdTrans.p, probVec.p, nodeMid.p, injCount.p, injOffset.p, injPatchTail.p, injSums.p, nRanks, rank,
                        (long long)capacity);
-                if (pass == 0) LAUNCH(this, k_scan_single, 1, 1024, 0, nBnd, injCount.p, injOffset.p, scanTmp.p);
+                if (pass == 0) scanInts(*this, nBnd, injCount.p, injOffset.p, scanTmp.p);
             }
             LAUNCH(this, k_inject_finish, 1, 32, 0, nBnd, scanTmp.p, scal.p, (long long)capacity, nRanks);
             const int gI = std::min(gridFor(nBnd, 256), numSMs * 2);
             LAUNCH(this, k_colsum_nc1, gI, 256, 0, nBnd, injSums.p, k1PartSum.p);
-            LAUNCH(this, k_fold_rows, 1, 32, 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
         } else {
             CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_INJ, 0, K1_NC1 * sizeof(double), stream));
         }
@@ -834,8 +924,8 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         mark(1);
         LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
         mark(2);
-        LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
-        LAUNCH(this, k_fold_rows, 1, 32, 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
         cur ^= 1;
 
         // ---- radix sort by (cell, tet) + segment bounds + moments ----
@@ -865,15 +955,15 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         // ---- time-averaging, mean fields, boundary conditions ----
         const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
         fieldsFinalise(*this, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, gF);
-        LAUNCH(this, k_fold_rows, 1, 32, 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
-        LAUNCH(this, k_fold_rows, 1, 32, 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
 
         // ---- particle-number control ----
         CUDA_CHECK(cudaMemsetAsync(ncCounts.p, 0, 2 * sizeof(int), stream));
         const bool nc = prm.particleNumberControl != 0;
         if (nc) {
             LAUNCH(this, k_nc_classify, gridFor(nCells, 256), 256, 0, dm, prm, PaNIC.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, nRanks);
-            LAUNCH(this, k_scan_single, 1, 1024, 0, nCells, ncCount.p, ncOffset.p, scanTmp.p + 1);
+            scanInts(*this, nCells, ncCount.p, ncOffset.p, scanTmp.p + 1);
             CUDA_CHECK(cudaMemsetAsync(ncDelta.p, 0, (size_t)nCells * K1_NC1 * sizeof(double), stream));
             // nSlots for the clones = this step's entry count
             LAUNCH(this, k_set_slots, 1, 32, 0, scal.p, total);
@@ -883,7 +973,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             // fold ncDelta over cells deterministically: per-CTA partials, then rows
             const int gR = std::min(gridFor(nCells, 256), numSMs * 4);
             LAUNCH(this, k_colsum_nc1, gR, 256, 0, nCells, ncDelta.p, k1PartSum.p);
-            LAUNCH(this, k_fold_rows, 1, 32, 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
         } else {
             CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_NCDELTA, 0, K1_NC1 * sizeof(double), stream));
         }
@@ -891,7 +981,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         {
             const int gL = std::min(gridFor(nCells, 256), numSMs * 4);
             LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, nc ? ncCount.p : nullptr, lostShare.p, k1PartMax.p);
-            LAUNCH(this, k_fold_rows, 1, 32, 0, gL, 1, k1PartMax.p, dRep->v + RP_LOSTSUM, 0);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gL, 1, k1PartMax.p, dRep->v + RP_LOSTSUM, 0);
         }
         LAUNCH(this, k_step_end, 1, 32, 0, scal.p, dRep, prm, 0, nc ? ncCounts.p : nullptr, total, nRanks);
 
