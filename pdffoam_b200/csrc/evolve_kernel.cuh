@@ -642,11 +642,9 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
 #pragma unroll
         for (int k = 0; k < NPHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
         A.out.cell[i] = cell; A.out.tet[i] = tet; A.out.id[i] = id;
-#ifdef K1_KEY_CELL_ONLY   // experiment: sort by cell only (stable sort keeps the previous order inside a cell)
-        A.keyOut[i] = ((uint32_t)cell << M.tetBits);
-#else
-        A.keyOut[i] = ((uint32_t)cell << M.tetBits) | (uint32_t)(tet - __ldg(M.cellTetStart + cell));
-#endif
+        // tetBits == 0: sort by cell only (the stable sort keeps the previous order inside a cell)
+        A.keyOut[i] = (M.tetBits == 0) ? (uint32_t)cell
+                                       : (((uint32_t)cell << M.tetBits) | (uint32_t)(tet - __ldg(M.cellTetStart + cell)));
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {

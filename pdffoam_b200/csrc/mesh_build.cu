@@ -258,8 +258,12 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     }
     hCTS[nCells] = (int)nT;
     nTets = nT;
-    tetBits = ilog2ceil(maxTetsPerCell);
+    // Sort key: cell only (one radix pass fewer; the stable sort keeps the previous order inside a
+    // cell) unless a cell holds so many particles that whole warps share a tet, where ordering by
+    // (cell, local tet) makes the lanes of a warp read the same tet records.
+    tetBits = (prm.particlesPerCell >= 256) ? ilog2ceil(maxTetsPerCell) : 0;
     keyBits = ilog2ceil(nCells) + tetBits;
+    if (keyBits > 31) { tetBits = 0; keyBits = ilog2ceil(nCells); }
     if (keyBits > 31) throw std::runtime_error("mesh: sort key does not fit 31 bits");
 
     // point -> cells (ascending cells)

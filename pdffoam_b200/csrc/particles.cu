@@ -523,50 +523,89 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
         double dsum[K1_NC1];
 #pragma unroll
         for (int k = 0; k < K1_NC1; ++k) dsum[k] = 0;
+        const int cnt = e - s;
+        // cells of up to 128 local particles (4 per lane) are handled from registers; larger ones
+        // re-read global memory
+        const bool inRegs = cnt <= 128;
         if (fl == 1) {
             // cloneParticles (:1107-1139): the n heaviest by eta*m (ties by id) are split
             const int n = nClone[c];
-            unsigned long long split[2] = {0ull, 0ull};   // which of this lane's entries get halved (<= 128 per lane)
-            int it = 0;
-            for (int j = s + lane; j < e; j += 32, ++it) {
-                const int slot = (int)perm[j];
-                const double key_i = S.eta[slot] * S.m[slot];
-                const uint32_t id_i = S.id[slot];
-                int rk = 0;
-                for (int q = s; q < e; ++q) {
-                    const int sq = (int)perm[q];
-                    const double kq = S.eta[sq] * S.m[sq];
-                    if (kq > key_i || (kq == key_i && S.id[sq] < id_i)) ++rk;
+            auto makeClone = [&](int slot, int rk, uint32_t id_i) {
+                const long long tailIdx = cloneOffset[c] + rk;
+                const long long dst = (long long)sc->nSlots + tailIdx;
+                if (dst >= capacity) { sc->overflow = 1; return; }
+                const V3 posOld = mk(S.px[slot], S.py[slot], S.pz[slot]);
+                const V3 pos = randomPointInCell(M, key, c, id_i, RNG_CLONE_POS, step);
+                const double mOld = S.m[slot];
+                const double mHalf = mOld / 2.0;
+                S.px[dst] = pos.x; S.py[dst] = pos.y; S.pz[dst] = pos.z;
+                S.ux[dst] = S.ux[slot]; S.uy[dst] = S.uy[slot]; S.uz[dst] = S.uz[slot];
+                S.m[dst] = mHalf; S.omega[dst] = S.omega[slot]; S.rho[dst] = S.rho[slot]; S.eta[dst] = S.eta[slot];
+                for (int k = 0; k < P.nPhi; ++k) S.phi[k][dst] = S.phi[k][slot];
+                S.cell[dst] = c; S.tet[dst] = locateTet(M, pos, c);
+                S.id[dst] = sc->nextId + (uint32_t)tailIdx * (uint32_t)nRanks;
+                if (M.axisym) {
+                    const double d = massPerDepth(M, pos, mHalf) + massPerDepth(M, posOld, mHalf) - massPerDepth(M, posOld, mOld);
+                    dsum[0] += d;
+                    for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
                 }
-                if (rk < n && it < 128) {
-                    split[it >> 6] |= 1ull << (it & 63);
-                    const long long tailIdx = cloneOffset[c] + rk;
-                    const long long dst = (long long)sc->nSlots + tailIdx;
-                    if (dst >= capacity) { sc->overflow = 1; continue; }
-                    const V3 posOld = mk(S.px[slot], S.py[slot], S.pz[slot]);
-                    const V3 pos = randomPointInCell(M, key, c, id_i, RNG_CLONE_POS, step);
-                    const double mOld = S.m[slot];
-                    const double mHalf = mOld / 2.0;
-                    S.px[dst] = pos.x; S.py[dst] = pos.y; S.pz[dst] = pos.z;
-                    S.ux[dst] = S.ux[slot]; S.uy[dst] = S.uy[slot]; S.uz[dst] = S.uz[slot];
-                    S.m[dst] = mHalf; S.omega[dst] = S.omega[slot]; S.rho[dst] = S.rho[slot]; S.eta[dst] = S.eta[slot];
-                    for (int k = 0; k < P.nPhi; ++k) S.phi[k][dst] = S.phi[k][slot];
-                    S.cell[dst] = c; S.tet[dst] = locateTet(M, pos, c);
-                    S.id[dst] = sc->nextId + (uint32_t)tailIdx * (uint32_t)nRanks;
-                    if (M.axisym) {
-                        const double d = massPerDepth(M, pos, mHalf) + massPerDepth(M, posOld, mHalf) - massPerDepth(M, posOld, mOld);
-                        dsum[0] += d;
-                        for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
+            };
+            if (inRegs) {
+                double keyv[4]; uint32_t idv[4]; int slotv[4], rkv[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int j = s + lane + 32 * it;
+                    const bool valid = j < e;
+                    const int slot = valid ? (int)perm[j] : 0;
+                    slotv[it] = slot;
+                    keyv[it] = valid ? S.eta[slot] * S.m[slot] : -PDF_VGREAT;
+                    idv[it] = valid ? S.id[slot] : 0xffffffffu;
+                    rkv[it] = 0;
+                }
+                // rank every entry against all others through warp shuffles
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int nr = min(32, cnt - 32 * r);   // warp-uniform
+                    for (int l = 0; l < nr; ++l) {
+                        const double kq = __shfl_sync(0xffffffffu, keyv[r], l);
+                        const uint32_t iq = __shfl_sync(0xffffffffu, idv[r], l);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) rkv[it] += (kq > keyv[it] || (kq == keyv[it] && iq < idv[it])) ? 1 : 0;
                     }
                 }
-            }
-            __syncwarp();
-            // halve the sources only after every lane has ranked against the old masses
-            it = 0;
-            for (int j = s + lane; j < e; j += 32, ++it) {
-                if (it < 128 && ((split[it >> 6] >> (it & 63)) & 1ull)) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    if (s + lane + 32 * it < e && rkv[it] < n) {
+                        makeClone(slotv[it], rkv[it], idv[it]);
+                        S.m[slotv[it]] = S.m[slotv[it]] / 2.0;   // ranks came from registers: safe to halve now
+                    }
+                }
+            } else {
+                unsigned long long split[4] = {0ull, 0ull, 0ull, 0ull};   // this lane's entries that get halved (first 256)
+                int it = 0;
+                for (int j = s + lane; j < e; j += 32, ++it) {
                     const int slot = (int)perm[j];
-                    S.m[slot] = S.m[slot] / 2.0;
+                    const double key_i = S.eta[slot] * S.m[slot];
+                    const uint32_t id_i = S.id[slot];
+                    int rk = 0;
+                    for (int q = s; q < e; ++q) {
+                        const int sq = (int)perm[q];
+                        const double kq = S.eta[sq] * S.m[sq];
+                        if (kq > key_i || (kq == key_i && S.id[sq] < id_i)) ++rk;
+                    }
+                    if (rk < n && it < 256) {
+                        split[it >> 6] |= 1ull << (it & 63);
+                        makeClone(slot, rk, id_i);
+                    }
+                }
+                __syncwarp();
+                // halve the sources only after every lane has ranked against the old masses
+                it = 0;
+                for (int j = s + lane; j < e; j += 32, ++it) {
+                    if (it < 256 && ((split[it >> 6] >> (it & 63)) & 1ull)) {
+                        const int slot = (int)perm[j];
+                        S.m[slot] = S.m[slot] / 2.0;
+                    }
                 }
             }
             if (lane == 0) { PaNIC[c] += n; atomicAdd(ncCounts, n); }
@@ -576,7 +615,24 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
             const int nx = ncur - P.particlesPerCell;
             const double Psel = (2. * nx) / ncur;
             double mA = 0., mB = 0.;
-            for (int j = s + lane; j < e; j += 32) {
+            // selection state of this lane's first four entries (all of them when inRegs)
+            int slotv[4]; double u2v[4]; bool selv[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int j = s + lane + 32 * it;
+                selv[it] = false; slotv[it] = 0; u2v[it] = 0;
+                if (j < e) {
+                    const int slot = (int)perm[j];
+                    double u1, u2;
+                    rngUniform2(key, S.id[slot], step, RNG_NC_PARTICLE, 0, u1, u2);
+                    slotv[it] = slot; u2v[it] = u2; selv[it] = u1 < Psel;
+                    if (selv[it]) {
+                        const double meta = S.eta[slot] * S.m[slot];
+                        if (u2 < 0.5) mA += meta; else mB += meta;
+                    }
+                }
+            }
+            for (int j = s + lane + 128; j < e; j += 32) {
                 const int slot = (int)perm[j];
                 double u1, u2;
                 rngUniform2(key, S.id[slot], step, RNG_NC_PARTICLE, 0, u1, u2);
@@ -594,20 +650,23 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
                 const bool delA = u < Pd;
                 const double sfac = delA ? 1. / Pd : (mA + mB) / mA;
                 int nKilled = 0;
-                for (int j = s + lane; j < e; j += 32) {
+                auto settle = [&](int slot, bool inA) {
+                    const V3 pos = mk(S.px[slot], S.py[slot], S.pz[slot]);
+                    const double mOld = S.m[slot];
+                    double d;
+                    if (inA == delA) { S.cell[slot] = -1; ++nKilled; d = -massPerDepth(M, pos, mOld); }
+                    else { const double mNew = mOld * sfac; S.m[slot] = mNew; d = massPerDepth(M, pos, mNew) - massPerDepth(M, pos, mOld); }
+                    dsum[0] += d;
+                    for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
+                };
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    if (selv[it]) settle(slotv[it], u2v[it] < 0.5);
+                for (int j = s + lane + 128; j < e; j += 32) {
                     const int slot = (int)perm[j];
                     double u1, u2;
                     rngUniform2(key, S.id[slot], step, RNG_NC_PARTICLE, 0, u1, u2);
-                    if (u1 < Psel) {
-                        const bool inA = u2 < 0.5;
-                        const V3 pos = mk(S.px[slot], S.py[slot], S.pz[slot]);
-                        const double mOld = S.m[slot];
-                        double d;
-                        if (inA == delA) { S.cell[slot] = -1; ++nKilled; d = -massPerDepth(M, pos, mOld); }
-                        else { const double mNew = mOld * sfac; S.m[slot] = mNew; d = massPerDepth(M, pos, mNew) - massPerDepth(M, pos, mOld); }
-                        dsum[0] += d;
-                        for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
-                    }
+                    if (u1 < Psel) settle(slot, u2 < 0.5);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) nKilled += __shfl_xor_sync(0xffffffffu, nKilled, o);
