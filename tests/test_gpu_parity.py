@@ -100,6 +100,18 @@ def test_particle_number_control(device_lib, oracle_lib):
     assert sum(r[0].nEliminated for r in reps) > 0
 
 
+def test_dense_cells_sorted_by_cell_and_tet(device_lib, oracle_lib):
+    """>= 256 particles/cell switches the device sort key from cell to (cell, local tet);
+    open box with number control so that every consumer of the sorted order runs."""
+    case = cases.synthetic_box(4, 2, 2, ppc=256, closed=False, number_control=True, lts="none")
+    case.params.deltaT0 = 2e-3
+    P = case.random_particles(256, seed=21)
+    rng = np.random.default_rng(4)
+    P["m"] = P["m"] * rng.uniform(0.5, 1.5, size=P["m"].shape[0])
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=4, rtol=1e-9, atol=1e-11)
+    assert sum(r[0].nInjected for r in reps) > 0
+
+
 def test_seed_on_device_matches_oracle(device_lib, oracle_lib):
     case = cases.synthetic_box(6, 4, 3, ppc=16, closed=True)
     run_both(case, device_lib, oracle_lib, None, n_steps=3, seed_on_device=True, rtol=1e-9, atol=1e-11)
