@@ -55,7 +55,12 @@ enum {
 
 /* model selectors; the words are the reference's run-time selection names */
 enum { PDFB200_VELOCITY_NONE = 0, PDFB200_VELOCITY_SLMFULL = 1 };      /* "SLMFull" */
-enum { PDFB200_MIXING_NONE = 0, PDFB200_MIXING_IEM = 1 };              /* "IEM"     */
+/* "IEM" (mcIEMMixingModel.C:68-83); "modifiedCurl" is new (BASELINE north_star, SURVEY
+ * Appendix C; not in the reference): after the step's sort the particles of a cell are matched
+ * in disjoint random pairs, a pair (p,q) mixes with probability
+ * 3*Cmix*Omega_pq*eta_pq*deltaT*(w_p+w_q)/(2*wbar) (w = eta*m; several rounds when > 1) and
+ * both move a fraction a ~ U(0,1) towards the pair's weighted mean. */
+enum { PDFB200_MIXING_NONE = 0, PDFB200_MIXING_IEM = 1, PDFB200_MIXING_MODCURL = 2 };
 enum { PDFB200_OMEGA_NONE = 0, PDFB200_OMEGA_RAS = 1 };                /* "RAS"     */
 enum {
     PDFB200_REACTION_NONE = 0,

@@ -306,12 +306,70 @@ void Cloud::omegaCorrect(Particle &p) const {
 }
 
 void Cloud::mixingCorrect(Particle &p) const {
-    if (prm.mixingModel == PDFB200_MIXING_NONE) return;
+    if (prm.mixingModel != PDFB200_MIXING_IEM) return;
     const double Cmix2 = 0.5 * prm.Cmix;
     for (int mI = 0; mI < prm.nMixed; ++mI) {
         double &phi = p.Phi[prm.mixed[mI]];
         const double phiap = PhicPdf[prm.mixed[mI]].c[p.cell];
         phi -= (1.0 - std::exp(-Cmix2 * p.Omega * p.eta * deltaT)) * (phi - phiap);
+    }
+}
+
+// "modifiedCurl" pair mixing (no reference; definition in include/pdfb200.h and DESIGN.md).
+// Runs on the particles of every cell after tracking, before the moments are taken.
+// Per cell and round: order the particles by (hash(id, step, round), id), pair consecutive
+// ones, mix pair (p,q) with probability Ppq/R and a ~ U(0,1) towards the weighted pair mean.
+void Cloud::curlMixing() {
+    if (prm.mixingModel != PDFB200_MIXING_MODCURL || prm.nMixed == 0) return;
+    const int RMAX = 8;
+    std::vector<std::vector<size_t>> addr(mesh.nCells);
+    for (size_t i = 0; i < particles.size(); ++i) addr[particles[i].cell].push_back(i);
+    struct Ent { uint32_t h, id; size_t i; };
+    std::vector<Ent> ord;
+    for (int c = 0; c < mesh.nCells; ++c) {
+        const std::vector<size_t> &L = addr[c];
+        const int n = (int)L.size();
+        if (n < 2) continue;
+        double wSum = 0, wMax = 0, oeMax = 0;
+        for (size_t i : L) {
+            const Particle &p = particles[i];
+            const double w = p.eta * p.m;
+            wSum += w; wMax = std::max(wMax, w); oeMax = std::max(oeMax, p.Omega * p.eta);
+        }
+        const double wBar = wSum / n;
+        const double pc = 3.0 * prm.Cmix * deltaT * oeMax * (wMax / wBar);
+        const int R = std::min(RMAX, std::max(1, (int)std::ceil(pc)));
+        for (int r = 0; r < R; ++r) {
+            ord.clear();
+            for (size_t i : L) {
+                uint32_t h;
+                if (prm.rngMode == 1) h = (uint32_t)(srng.scalar01() * 4294967296.0);
+                else {
+                    const uint32_t ctr[4] = {particles[i].id, step, RNG_MIX_HASH, (uint32_t)r};
+                    uint32_t o[4];
+                    philox4x32_10(ctr, krng.key, o);
+                    h = o[0];
+                }
+                ord.push_back({h, particles[i].id, i});
+            }
+            std::sort(ord.begin(), ord.end(), [](const Ent &a, const Ent &b) { return a.h < b.h || (a.h == b.h && a.id < b.id); });
+            for (int j = 0; j + 1 < n; j += 2) {
+                Particle &p = particles[ord[j].i], &q = particles[ord[j + 1].i];
+                double u, a;
+                if (prm.rngMode == 1) { u = srng.scalar01(); a = srng.scalar01(); }
+                else krng.uniform2(p.id, step, RNG_MIX_PAIR, (uint32_t)r, u, a);
+                const double wp = p.eta * p.m, wq = q.eta * q.m;
+                const double Om = 0.5 * (p.Omega + q.Omega), et = 0.5 * (p.eta + q.eta);
+                const double Ppq = 3.0 * prm.Cmix * Om * et * deltaT * ((wp + wq) / (2.0 * wBar)) / R;
+                if (!(u < Ppq)) continue;
+                for (int mI = 0; mI < prm.nMixed; ++mI) {
+                    const int s = prm.mixed[mI];
+                    const double mean = (wp * p.Phi[s] + wq * q.Phi[s]) / (wp + wq);
+                    p.Phi[s] += a * (mean - p.Phi[s]);
+                    q.Phi[s] += a * (mean - q.Phi[s]);
+                }
+            }
+        }
     }
 }
 
@@ -855,6 +913,8 @@ void Cloud::evolveBegin(pdfb200_step_report *rep, std::vector<double> &block) {
     std::array<double, 1 + PDFB200_MAX_PHI> massInInst{}, massOutInst{};
     for (size_t pI = 0; pI < mesh.patches.size(); ++pI)
         for (int k = 0; k <= prm.nConserved; ++k) { massInInst[k] += patchMassIn[pI][k]; massOutInst[k] += patchMassOut[pI][k]; }
+    // pair mixing of the modifiedCurl model (new; IEM already acted at the mid-point)
+    curlMixing();
     // E12 first half (:929-956)
     accumulateInstantMoments(block);
 

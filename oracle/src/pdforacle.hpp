@@ -189,7 +189,9 @@ enum RngPurpose : uint32_t {
     RNG_NC_CELL = 4,        // entity = cell (eliminate: which population dies)
     RNG_CLONE_POS = 5,      // entity = particle id; sub = 2*attempt(+1)
     RNG_SEED = 6,           // entity = initial particle index
-    RNG_INJECT = 7          // entity = boundary face; sub = 4*k + {0..3}
+    RNG_INJECT = 7,         // entity = boundary face; sub = 4*k + {0..3}
+    RNG_MIX_HASH = 8,       // entity = particle id; sub = round (modifiedCurl: matching order)
+    RNG_MIX_PAIR = 9        // entity = id of the pair's first particle; sub = round (mix?, a)
 };
 
 struct KeyedRng {
@@ -363,6 +365,7 @@ struct Cloud {
     // models on one particle (mcModel::correct(mcParticle&))
     void omegaCorrect(Particle &p) const;               // mcRASOmegaModel.C:125-147
     void mixingCorrect(Particle &p) const;              // mcIEMMixingModel.C:68-83
+    void curlMixing();                                  // "modifiedCurl" (new; see include/pdfb200.h)
     void reactionCorrect(Particle &p) const;            // cold / BurkeSchumann / SteadyFlamelet
     void velocityCorrect(Particle &p, const double xi[3]) const;  // mcSLMFullVelocityModel.C:146-185
     void ltsCorrect(Particle &p) const;                 // mcCellLocalTimeStepping.C:164-174 etc.

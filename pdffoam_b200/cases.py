@@ -19,7 +19,7 @@ from .meshgen import PolyMesh
 
 # run-time selection names of the reference -> enum values of include/pdfb200.h
 VELOCITY_MODELS = {"none": 0, "SLMFull": 1}                 # mcSLMFullVelocityModel.C:39-45
-MIXING_MODELS = {"none": 0, "IEM": 1}                       # mcIEMMixingModel.C:37-43
+MIXING_MODELS = {"none": 0, "IEM": 1, "modifiedCurl": 2}     # mcIEMMixingModel.C:37-43; modifiedCurl is new
 OMEGA_MODELS = {"none": 0, "RAS": 1}                        # mcRASOmegaModel.C:63-69
 REACTION_MODELS = {"none": 0, "cold": 1, "BurkeSchumann": 2, "SteadyFlamelet": 3}
 POSITION_CORRECTIONS = {"none": 0, "limitedSimple": 1}

@@ -48,7 +48,7 @@ static void validateParams(const pdfb200_params &p) {
     if (!(p.eliminateAt > 1)) throw std::invalid_argument("eliminateAt must be > 1");                                   // mcSolution.C:155-161
     if (p.particlesPerCell <= 0) throw std::invalid_argument("particlesPerCell must be positive");
     if (p.velocityModel < 0 || p.velocityModel > PDFB200_VELOCITY_SLMFULL) throw std::invalid_argument("Unknown mcVelocityModel type");
-    if (p.mixingModel < 0 || p.mixingModel > PDFB200_MIXING_IEM) throw std::invalid_argument("Unknown mcMixingModel type");
+    if (p.mixingModel < 0 || p.mixingModel > PDFB200_MIXING_MODCURL) throw std::invalid_argument("Unknown mcMixingModel type");
     if (p.omegaModel < 0 || p.omegaModel > PDFB200_OMEGA_RAS) throw std::invalid_argument("Unknown mcOmegaModel type");
     if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_STEADY_FLAMELET) throw std::invalid_argument("Unknown mcReactionModel type");
     if (p.positionCorrection < 0 || p.positionCorrection > PDFB200_POSCORR_LIMITED_SIMPLE) throw std::invalid_argument("Unknown mcPositionCorrection type");

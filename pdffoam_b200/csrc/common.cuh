@@ -30,6 +30,8 @@
 #define RNG_CLONE_POS 5u
 #define RNG_SEED 6u
 #define RNG_INJECT 7u
+#define RNG_MIX_HASH 8u   // entity = particle id; sub = round (modifiedCurl matching order)
+#define RNG_MIX_PAIR 9u   // entity = id of the pair's first particle; sub = round
 
 struct __align__(16) TetRec {
     int nbr[4];       // tet across the face opposite a, b, c, d (-1: boundary)

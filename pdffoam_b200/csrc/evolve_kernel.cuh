@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
             // mcRASOmegaModel::correct
             if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
             // mcIEMMixingModel::correct
-            if (P.mixingModel != PDFB200_MIXING_NONE) {
+            if (P.mixingModel == PDFB200_MIXING_IEM) {
                 const double Cmix2 = 0.5 * P.Cmix;
                 const double fac = 1.0 - exp(-Cmix2 * Omega * eta * deltaT);
                 for (int mI = 0; mI < P.nMixed; ++mI) {

@@ -191,6 +191,115 @@ __global__ void k_moments(DMesh M, PState S, const uint32_t *perm, const int *ce
 }
 
 // ---------------------------------------------------------------------------
+// "modifiedCurl" pair mixing (new, not in the reference; definition in
+// include/pdfb200.h, CPU restatement oracle/src/cloud.cpp Cloud::curlMixing).
+// One warp per cell on the freshly sorted order. Per round the cell's particles
+// are ranked by (Philox hash of the id, id) and consecutive ranks form disjoint
+// pairs, so the pairs of a round are independent and one lane mixes one pair.
+// Cells of up to 128 local particles are ranked through warp shuffles from
+// registers; larger ones go through the two scratch arrays.
+// ---------------------------------------------------------------------------
+#define MIX_RMAX 8
+#define MIX_WARPS 8
+__global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
+                                                              const int *cellEnd, const StepScalars *sc, RngKey key, uint32_t *hashScratch,
+                                                              uint32_t *rankSlot) {
+    __shared__ int slotByRank[MIX_WARPS][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t step = sc->step;
+    const double deltaT = sc->deltaT;
+    for (int c = blockIdx.x * MIX_WARPS + warp; c < M.nCells; c += gridDim.x * MIX_WARPS) {
+        const int s = cellStart[c], e = cellEnd[c];
+        const int n = e - s;
+        if (n < 2) continue;
+        double wSum = 0, wMax = 0, oeMax = 0;
+        for (int j = s + lane; j < e; j += 32) {
+            const int slot = (int)perm[j];
+            const double eta = S.eta[slot], w = eta * S.m[slot];
+            wSum += w; wMax = fmax(wMax, w); oeMax = fmax(oeMax, S.omega[slot] * eta);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wSum += __shfl_xor_sync(0xffffffffu, wSum, o);
+            wMax = fmax(wMax, __shfl_xor_sync(0xffffffffu, wMax, o));
+            oeMax = fmax(oeMax, __shfl_xor_sync(0xffffffffu, oeMax, o));
+        }
+        const double wBar = wSum / n;
+        const double pc = 3.0 * P.Cmix * deltaT * oeMax * (wMax / wBar);
+        const int R = min(MIX_RMAX, max(1, (int)ceil(pc)));
+        auto mixPair = [&](int p, int q, int r) {
+            double u, a;
+            rngUniform2(key, S.id[p], step, RNG_MIX_PAIR, (uint32_t)r, u, a);
+            const double etap = S.eta[p], etaq = S.eta[q];
+            const double wp = etap * S.m[p], wq = etaq * S.m[q];
+            const double Om = 0.5 * (S.omega[p] + S.omega[q]), et = 0.5 * (etap + etaq);
+            const double Ppq = 3.0 * P.Cmix * Om * et * deltaT * ((wp + wq) / (2.0 * wBar)) / R;
+            if (!(u < Ppq)) return;
+            for (int mI = 0; mI < P.nMixed; ++mI) {
+                double *col = S.phi[P.mixed[mI]];
+                const double fp = col[p], fq = col[q];
+                const double mean = (wp * fp + wq * fq) / (wp + wq);
+                col[p] = fp + a * (mean - fp);
+                col[q] = fq + a * (mean - fq);
+            }
+        };
+        auto hashOf = [&](uint32_t id, int r) {
+            uint32_t o[4];
+            philox4x32_10(id, step, RNG_MIX_HASH, (uint32_t)r, key.k0, key.k1, o);
+            return o[0];
+        };
+        for (int r = 0; r < R; ++r) {
+            if (n <= 128) {
+                uint32_t hv[4], idv[4];
+                int slotv[4], rkv[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int j = s + lane + 32 * it;
+                    const bool valid = j < e;
+                    const int slot = valid ? (int)perm[j] : 0;
+                    slotv[it] = slot;
+                    idv[it] = valid ? S.id[slot] : 0xffffffffu;
+                    hv[it] = valid ? hashOf(idv[it], r) : 0xffffffffu;
+                    rkv[it] = 0;
+                }
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int nr = min(32, n - 32 * rr);   // warp-uniform
+                    for (int l = 0; l < nr; ++l) {
+                        const uint32_t hq = __shfl_sync(0xffffffffu, hv[rr], l);
+                        const uint32_t iq = __shfl_sync(0xffffffffu, idv[rr], l);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) rkv[it] += (hq < hv[it] || (hq == hv[it] && iq < idv[it])) ? 1 : 0;
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    if (s + lane + 32 * it < e) slotByRank[warp][rkv[it]] = slotv[it];
+                __syncwarp();
+                for (int j = lane; 2 * j + 1 < n; j += 32) mixPair(slotByRank[warp][2 * j], slotByRank[warp][2 * j + 1], r);
+                __syncwarp();
+            } else {
+                for (int j = s + lane; j < e; j += 32) hashScratch[j] = hashOf(S.id[perm[j]], r);
+                __syncwarp();
+                for (int j = s + lane; j < e; j += 32) {
+                    const int slot = (int)perm[j];
+                    const uint32_t h = hashScratch[j], id = S.id[slot];
+                    int rk = 0;
+                    for (int q = s; q < e; ++q) {
+                        const uint32_t hq = hashScratch[q];
+                        if (hq < h || (hq == h && S.id[perm[q]] < id)) ++rk;
+                    }
+                    rankSlot[s + rk] = (uint32_t)slot;
+                }
+                __syncwarp();
+                for (int j = lane; 2 * j + 1 < n; j += 32) mixPair((int)rankSlot[s + 2 * j], (int)rankSlot[s + 2 * j + 1], r);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // initReleaseParticles (mcParticleCloud.C:1534-1629): one thread per cell
 // ---------------------------------------------------------------------------
 __global__ void k_seed(DMesh M, pdfb200_params P, PState S, RngKey key, int rank, int nRanks, const double *rho_c,
@@ -996,6 +1105,12 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
         if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellStart.p, cellEnd.p, scal.p);
         else { hScal->nSorted = 0; }
+        // "modifiedCurl" pair mixing on the sorted order, before the moments are taken
+        if (prm.mixingModel == PDFB200_MIXING_MODCURL && prm.nMixed > 0 && total > 0) {
+            if (valsA.n < (size_t)capacity) valsA.alloc(capacity);
+            LAUNCH(this, k_mix_curl, std::min(gridFor(nCells, MIX_WARPS), numSMs * 8), MIX_WARPS * 32, 0, dm, prm, S[cur], valsB.p,
+                   cellStart.p, cellEnd.p, scal.p, key, keysA.p, valsA.p);
+        }
         switch (prm.nPhi) {
         case 0: launchMoments<0>(*this, S[cur], valsB.p); break;
         case 1: launchMoments<1>(*this, S[cur], valsB.p); break;
