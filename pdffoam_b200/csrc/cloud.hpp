@@ -144,6 +144,7 @@ struct Cloud {
     ~Cloud();
     void create(const pdfb200_mesh &m, const pdfb200_params &p, int device, int64_t capacity);
     void buildMesh(const pdfb200_mesh &m);            // mesh_build.cu
+    void chooseSortKey();                             // mesh_build.cu
     void setParams(const pdfb200_params &p);
     void setTables(int nChi, int nZ, const double *chi, const double *z, int nFields, const double *const *fields);
     void uploadFv(const pdfb200_fv_fields &f);

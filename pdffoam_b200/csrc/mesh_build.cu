@@ -205,6 +205,17 @@ static int ilog2ceil(long long v) {
     return b;
 }
 
+// Sort key: cell only (one radix pass fewer; the stable sort keeps the previous order inside a
+// cell) unless this rank holds so many particles per cell that whole warps share a tet, where
+// ordering by (cell, local tet) makes the lanes of a warp read the same tet records.
+void Cloud::chooseSortKey() {
+    const int localPpc = prm.particlesPerCell / std::max(nRanks, 1);
+    tetBits = (localPpc >= 256) ? ilog2ceil(maxTetsPerCell) : 0;
+    keyBits = ilog2ceil(nCells) + tetBits;
+    if (keyBits > 31) { tetBits = 0; keyBits = ilog2ceil(nCells); }
+    dm.tetBits = tetBits;
+}
+
 void Cloud::buildMesh(const pdfb200_mesh &m) {
     nCells = m.nCells; nFaces = m.nFaces; nInternalFaces = m.nInternalFaces; nPoints = m.nPoints;
     nBnd = nFaces - nInternalFaces;
@@ -258,12 +269,7 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     }
     hCTS[nCells] = (int)nT;
     nTets = nT;
-    // Sort key: cell only (one radix pass fewer; the stable sort keeps the previous order inside a
-    // cell) unless a cell holds so many particles that whole warps share a tet, where ordering by
-    // (cell, local tet) makes the lanes of a warp read the same tet records.
-    tetBits = (prm.particlesPerCell >= 256) ? ilog2ceil(maxTetsPerCell) : 0;
-    keyBits = ilog2ceil(nCells) + tetBits;
-    if (keyBits > 31) { tetBits = 0; keyBits = ilog2ceil(nCells); }
+    chooseSortKey();
     if (keyBits > 31) throw std::runtime_error("mesh: sort key does not fit 31 bits");
 
     // point -> cells (ascending cells)
