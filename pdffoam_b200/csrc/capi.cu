@@ -28,6 +28,7 @@ void commDestroy(Cloud &c);   // comm.cu
 Cloud::~Cloud() {
     if (device >= 0) cudaSetDevice(device);
     commDestroy(*this);
+    dropSpecialisedKernel();
     for (void *p : stateAllocs) cudaFree(p);
     if (hScal) cudaFreeHost(hScal);
     if (hFinal) cudaFreeHost(hFinal);
@@ -67,6 +68,7 @@ void Cloud::setParams(const pdfb200_params &p) {
     validateParams(p);
     if (haveCloudFields && p.nPhi != prm.nPhi) throw std::invalid_argument("set_params: nPhi cannot change after the fields were uploaded");
     prm = p;
+    dropSpecialisedKernel();
     prm.C0 = fmax(0.0, prm.C0);                    // mcSLMFullVelocityModel.C:97-98
     prm.C1 = fmax(0.0, fmin(1.0, prm.C1));
     nCov = prm.nPhi * (prm.nPhi + 1) / 2;

@@ -136,6 +136,12 @@ struct Cloud {
     uint32_t stepHost = 0;
     double deltaTHost = 1e-13;
 
+    // ---- run-time specialised particle kernel (jit.cu) ----
+    int jitState = 0;                 // 0 not tried, 1 loaded, -1 not available
+    void *jitLibrary = nullptr, *jitKernel = nullptr;
+    void *specialisedKernel();        // nullptr -> use the ahead-of-time generic kernel
+    void dropSpecialisedKernel();     // parameters or mesh flags changed
+
     // ---- multi-GPU ----
     int nRanks = 1, rank = 0;
     NcclApi *nccl = nullptr;

@@ -59,6 +59,7 @@ void Cloud::commInit(int nRanks_, int rank_, const char id[128]) {
     if (nParticlesHost > 0) throw std::logic_error("comm_init: call before seeding/uploading particles");
     nRanks = nRanks_; rank = rank_;
     chooseSortKey();   // the particles per cell held by this rank decide the key
+    dropSpecialisedKernel();
     if (nRanks == 1) return;
     nccl = loadNccl();
     ncclUniqueId_t uid;

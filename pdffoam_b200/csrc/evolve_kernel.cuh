@@ -21,6 +21,33 @@
 
 #include "common.cuh"
 
+// Compile-time knowledge of the run. The kernel is built twice from this one source: ahead of
+// time with the mesh flags and model parameters read at run time (k_evolve<NPHI>, below), and at
+// run time by jit.cu for the cloud at hand with K1_JIT defined, where the generated prologue
+// turns the parameters (struct JitP) and the mesh flags (JIT_*) into constants, so that every
+// model the case does not select drops out of the code (instruction footprint, registers).
+#ifdef K1_JIT
+#define MESH_AXISYM(M) (JIT_AXISYM != 0)
+#define MESH_GEOD(M, k) (JIT_GEOD##k)
+#define MESH_SOLD(M, k) (JIT_SOLD##k)
+#define MESH_NGEOD(M) (JIT_NGEOD)
+#define MESH_TETBITS(M) (JIT_TETBITS)
+// JitP (generated): the parameters the kernel reads as static constexpr members, the index lists
+// as constexpr functions mixedAt(i) / conservedAt(i) / addedIdxAt(i)
+typedef JitP KParams;
+#define PRM_AT(P, field, i) ((P).field##At(i))
+#else
+typedef pdfb200_params KParams;
+#define PRM_AT(P, field, i) ((P).field[i])
+#define MESH_AXISYM(M) ((M).axisym != 0)
+#define MESH_GEOD(M, k) ((M).geoD[k])
+#define MESH_SOLD(M, k) ((M).solD[k])
+#define MESH_NGEOD(M) ((M).nGeoD)
+#define MESH_TETBITS(M) ((M).tetBits)
+#endif
+#define MESH_GEOD3(M) MESH_GEOD(M, 0), MESH_GEOD(M, 1), MESH_GEOD(M, 2)
+#define MESH_SOLD3(M) MESH_SOLD(M, 0), MESH_SOLD(M, 1), MESH_SOLD(M, 2)
+
 struct K1Args {
     DMesh M;
     pdfb200_params P;
@@ -125,7 +152,7 @@ __device__ __forceinline__ double pickPhi(const double (&phi)[NPHI], int idx) {
 }
 
 __device__ __forceinline__ double massPerDepth(const DMesh &M, V3 pos, double m) {
-    if (M.axisym) {
+    if (MESH_AXISYM(M)) {
         const V3 ax = mk(M.axis[0], M.axis[1], M.axis[2]);
         const double r = mag3(pos - dot3(pos, ax) * ax);
         return m / (fmax(r, PDF_SMALL) * M.openingAngle);
@@ -138,10 +165,10 @@ __device__ __forceinline__ V3 reflectVec(V3 v, V3 n) {
     return v - (2.0 * d) * n;
 }
 
-__device__ __forceinline__ void constrainDir(const int d[3], V3 &v) {
-    if (d[0] < 0) v.x = 0;
-    if (d[1] < 0) v.y = 0;
-    if (d[2] < 0) v.z = 0;
+__device__ __forceinline__ void constrainDir(int d0, int d1, int d2, V3 &v) {
+    if (d0 < 0) v.x = 0;
+    if (d1 < 0) v.y = 0;
+    if (d2 < 0) v.z = 0;
 }
 
 // constrainParticle (mcParticleCloud.C:76-101); the axisymmetric rotation is kept out of
@@ -155,12 +182,12 @@ __device__ __forceinline__ void constrainAxisym(const DMesh &M, double dt, V3 po
     rotationTensor(n, mk(M.centreNormal[0], M.centreNormal[1], M.centreNormal[2]), T);
     U = xform(T, U); Ucorr = xform(T, Ucorr);
     dest = xform(T, dest);
-    constrainDir(M.geoD, dest);
+    constrainDir(MESH_GEOD3(M), dest);
     Utrack = (dest - pos) / dt;
 }
 __device__ __forceinline__ void constrainParticle(const DMesh &M, double dt, V3 pos, V3 &U, V3 &Ucorr, V3 &Utrack) {
-    constrainDir(M.solD, Utrack);
-    if (M.axisym) constrainAxisym(M, dt, pos, U, Ucorr, Utrack);
+    constrainDir(MESH_SOLD3(M), Utrack);
+    if (MESH_AXISYM(M)) constrainAxisym(M, dt, pos, U, Ucorr, Utrack);
 }
 
 // mcSteadyFlamelet helpers (mcSteadyFlamelet.C:44-93)
@@ -188,7 +215,7 @@ __device__ __forceinline__ double stabilise(double x, double y) { return x < 0 ?
 // mcBurkeSchumannReactionModel.C:77-91, mcSteadyFlamelet.C:304-329.
 struct FlameletTables { const double *chi, *z, *fields; int nChi, nZ; };
 template <int NPHI>
-__device__ __forceinline__ void reactionCorrect(const pdfb200_params &P, const FlameletTables &F, double Omega, double zVar,
+__device__ __forceinline__ void reactionCorrect(const KParams &P, const FlameletTables &F, double Omega, double zVar,
                                                 double pCell, double (&phi)[NPHI], double &rho) {
     if (P.reactionModel == PDFB200_REACTION_COLD) {
         rho = P.coldDensity;
@@ -214,7 +241,7 @@ __device__ __forceinline__ void reactionCorrect(const pdfb200_params &P, const F
         for (int a = 0; a < P.nAdded; ++a) {
             const double v = binterpDev(F.fields + (size_t)(1 + a) * F.nChi * F.nZ, F.nChi, F.nZ, ichi, wchi, iz, wz);
 #pragma unroll
-            for (int k = 0; k < NPHI; ++k) if (k == P.addedIdx[a]) phi[k] = v;
+            for (int k = 0; k < NPHI; ++k) if (k == PRM_AT(P, addedIdx, a)) phi[k] = v;
         }
     }
 }
@@ -223,7 +250,7 @@ __device__ __forceinline__ void reactionCorrect(const pdfb200_params &P, const F
 // records of the tet (points b and c, face centre, cell centre) blended with
 // the clamped barycentric weights (order a, b, c, d); pst receives the four p*
 // node values for gradInterpolationConstantTet (order a, b, c, d).
-__device__ __forceinline__ void interpMid(const DMesh &M, const pdfb200_params &P, const double *nodeMid, const TetL &T,
+__device__ __forceinline__ void interpMid(const DMesh &M, const KParams &P, const double *nodeMid, const TetL &T,
                                           double w0, double w1, double w2, double w3, double (&val)[NODE_MID_STRIDE],
                                           double (&pst)[4]) {
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
@@ -300,7 +327,7 @@ __device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uin
         const double ry = fmin(fmax(10.0 * PDF_SMALL, uy), 1.0 - 10.0 * PDF_SMALL);
         const double rz = fmin(fmax(10.0 * PDF_SMALL, uz), 1.0 - 10.0 * PDF_SMALL);
         position = minb + mk(rx * dimb.x, ry * dimb.y, rz * dimb.z);
-        if (M.nGeoD <= 2) constrainDir(M.geoD, position);
+        if (MESH_NGEOD(M) <= 2) constrainDir(MESH_GEOD3(M), position);
         if (pointInCell(M, position, cell) || attempt > 10000) break;
     }
     return position;
@@ -326,7 +353,7 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 
 // NPHI = compile-time bound on the particle scalars held in registers (nPhi <= NPHI)
 template <int NPHI>
-__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Args A) {
+__device__ __forceinline__ void evolveBody(const K1Args &A) {
     extern __shared__ double smem[];
     double *accS = smem + threadIdx.x;                         // sums: accS[k*K1_THREADS]
     double *accM = smem + ACC_NSUM * K1_THREADS + threadIdx.x;  // maxima
@@ -336,7 +363,13 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
     for (int k = 0; k < ACC_NMAX; ++k) accM[k * K1_THREADS] = -PDF_VGREAT;
 
     const DMesh &M = A.M;
+#ifdef K1_JIT
+    const JitP P{};
+    constexpr bool hasOpen = JIT_HAS_OPEN != 0;
+#else
     const pdfb200_params &P = A.P;
+    const bool hasOpen = A.hasOpen != 0;
+#endif
     const int nSorted = A.sc->nSorted, total = nSorted + A.sc->nTail, nSlotsIn = A.sc->nSlots, nInjStart = A.sc->nInjStart;
     const int anyLost = A.sc->anyLost;
     const uint32_t step = A.sc->step;
@@ -388,7 +421,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
 
         int status = 0;   // 0 alive, 1 deleted at an open boundary, 2 lost
         // ---- E1: mcOpenBoundary::correct(false), cull behind the moving outflow plane ----
-        if (A.hasOpen) {
+        if (hasOpen) {
             const int ks = __ldg(M.openCellStart + cell), ke = __ldg(M.openCellStart + cell + 1);
             for (int k = ks; k < ke && status == 0; ++k) {
                 const int bf = M.openCellFaces[k];
@@ -402,7 +435,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                     if (xp < eta * (Un * deltaT)) {
                         const double mpd = massPerDepth(M, pos, m);
                         accS[ACC_MASS_OUT * K1_THREADS] -= mpd;
-                        for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, P.conserved[cs]);
+                        for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
                         status = 1;
                     }
                 }
@@ -414,7 +447,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
         {
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_MINUS * K1_THREADS] -= mpd;
-            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, P.conserved[cs]);
+            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
         }
         // ---- E3: position correction gather ----
         TetL T;
@@ -466,7 +499,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
             while (tEnd > 0 && status == 0) {
                 double dt = fmin(dtMax, tEnd);
                 V3 dest = pos + dt * Utrack;
-                constrainDir(M.geoD, dest);
+                constrainDir(MESH_GEOD3(M), dest);
                 const V3 x0 = pos;
                 const V3 dx = dest - x0;
                 double tf = 1.0;
@@ -524,7 +557,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                             const double mpd = massPerDepth(M, pos, m);
                             const int base = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
                             accS[base * K1_THREADS] -= mpd;
-                            for (int cs = 0; cs < P.nConserved; ++cs) accS[(base + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, P.conserved[cs]);
+                            for (int cs = 0; cs < P.nConserved; ++cs) accS[(base + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
                             status = 1;
                             break;
                         }
@@ -556,7 +589,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
                 const double Cmix2 = 0.5 * P.Cmix;
                 const double fac = 1.0 - exp(-Cmix2 * Omega * eta * deltaT);
                 for (int mI = 0; mI < P.nMixed; ++mI) {
-                    const int s = P.mixed[mI];
+                    const int s = PRM_AT(P, mixed, mI);
                     const double mean = __ldg(aux + 2 + s);
 #pragma unroll
                     for (int k = 0; k < NPHI; ++k)
@@ -643,14 +676,14 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
         for (int k = 0; k < NPHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
         A.out.cell[i] = cell; A.out.tet[i] = tet; A.out.id[i] = id;
         // tetBits == 0: sort by cell only (the stable sort keeps the previous order inside a cell)
-        A.keyOut[i] = (M.tetBits == 0) ? (uint32_t)cell
-                                       : (((uint32_t)cell << M.tetBits) | (uint32_t)(tet - __ldg(M.cellTetStart + cell)));
+        A.keyOut[i] = (MESH_TETBITS(M) == 0) ? (uint32_t)cell
+                                             : (((uint32_t)cell << MESH_TETBITS(M)) | (uint32_t)(tet - __ldg(M.cellTetStart + cell)));
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_PLUS * K1_THREADS] += mpd;
-            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * pickPhi(phi, P.conserved[cs]);
+            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
             accS[ACC_N_ALIVE * K1_THREADS] += 1;
             accM[ACC_UMAX * K1_THREADS] = fmax(accM[ACC_UMAX * K1_THREADS], mag3(U));
             accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
@@ -684,3 +717,11 @@ __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Ar
         }
     }
 }
+
+#ifndef K1_JIT
+template <int NPHI>
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve(const K1Args A) { evolveBody<NPHI>(A); }
+#else
+// the specialised kernel of this cloud (loaded by jit.cu through cudaLibraryLoadFromFile)
+extern "C" __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_evolve_jit(const K1Args A) { evolveBody<JIT_NPHI>(A); }
+#endif

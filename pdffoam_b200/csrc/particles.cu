@@ -354,7 +354,7 @@ __global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const 
     if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
     else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
         V3 Ut = mk(S.ux[i], S.uy[i], S.uz[i]);
-        constrainDir(M.geoD, Ut);
+        constrainDir(MESH_GEOD3(M), Ut);
         eta = fmin(P.CFL / stabilise(sc->deltaT * courantNo(M, T.cell, Ut), PDF_VSMALL), P.ltsUpperBound);
     }
     S.eta[i] = eta;
@@ -521,7 +521,7 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
                 if (idx1 == n) idx1 = n - 1;                  // uTri beyond the last entry (== 1 up to round-off)
                 if (a1 + a2 > 1.0) { a1 = 1.0 - a1; a2 = 1.0 - a2; }
                 V3 pos = ((a1 * ld3(M.points, M.facePoints[s + idx1]) + a2 * ld3(M.points, M.facePoints[s + idx2])) + (1.0 - a1 - a2) * C) - PDF_SMALL * Sf;
-                if (M.nGeoD <= 2) constrainDir(M.geoD, pos);
+                if (M.nGeoD <= 2) constrainDir(MESH_GEOD3(M), pos);
                 // local time stepping of the new particle
                 const int tet = locateTet(M, pos, cellI);
                 double eta = 1.0;
@@ -534,7 +534,7 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
                     eta = val[NM_ETA];
                 } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
                     V3 Ut = Up;
-                    constrainDir(M.geoD, Ut);
+                    constrainDir(MESH_GEOD3(M), Ut);
                     eta = fmin(P.CFL / stabilise(deltaT * courantNo(M, cellI, Ut), PDF_VSMALL), P.ltsUpperBound);
                 }
                 const double m = mp / eta;
@@ -1043,6 +1043,9 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     void (*k1)(const K1Args) = prm.nPhi <= 1 ? k_evolve<1> : prm.nPhi == 2 ? k_evolve<2> : prm.nPhi == 3 ? k_evolve<3> : k_evolve<PDFB200_MAX_PHI>;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1Blocks, k1, K1_THREADS, K1_SMEM_BYTES));
     k1Blocks = std::max(1, std::min(k1Blocks, 16));
+    // the kernel specialised for this cloud's parameters and mesh flags, when there is one (jit.cu)
+    void *k1Jit = specialisedKernel();
+    if (k1Jit) k1Blocks = K1_MIN_BLOCKS;
     auto mark = [&](int r) { CUDA_CHECK(cudaEventRecord(evMark[r], stream)); };
 
     for (int st = 0; st < nSteps; ++st) {
@@ -1090,7 +1093,13 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
         CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
         mark(1);
-        LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
+        if (k1Jit) {
+            void *kargs[] = {&A};
+            CUDA_CHECK(cudaLaunchKernel(k1Jit, dim3(gridK1), dim3(K1_THREADS), kargs, K1_SMEM_BYTES, stream));
+            ++launches;
+        } else {
+            LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
+        }
         mark(2);
         LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
         LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
