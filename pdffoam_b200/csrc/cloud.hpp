@@ -126,7 +126,7 @@ struct Cloud {
     DBuf<int> injCount, injOffset;
     DBuf<double> injSums;
     DBuf<double> k1PartSum, k1PartMax, cellPartSum, finalSums;   // deterministic reductions
-    DBuf<double> ncDelta;
+    DBuf<double> ncDelta, cloneDelta;   // cloneDelta: [capacity][K1_NC1], axisymmetric cases only
     DBuf<StepScalars> scal;
     StepScalars *hScal = nullptr;     // pinned mirror
     double *hFinal = nullptr;         // pinned reduction results

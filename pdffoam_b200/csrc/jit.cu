@@ -127,7 +127,8 @@ void *Cloud::specialisedKernel() {
         return nullptr;
     }
     const std::string pro = prologue(*this);
-    const std::string flags = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false";
+    std::string flags = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false";
+    if (const char *x = std::getenv("PDFB200_JIT_FLAGS")) flags += std::string(" ") + x;   // tuning experiments (-DK1_...)
     const uint64_t h = fnv1a(srcA, fnv1a(srcH, fnv1a(srcC, fnv1a(srcK, fnv1a(flags, fnv1a(pro))))));
     char name[64];
     std::snprintf(name, sizeof name, "k_evolve_%016llx", (unsigned long long)h);

@@ -621,7 +621,7 @@ __global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, co
 __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
                            const int *cellEnd, const int *flag, const int *nClone, const int *cloneOffset,
                            double *PaNIC, StepScalars *sc, RngKey key, int rank, int nRanks, long long capacity,
-                           double *ncDelta, int *ncCounts /* [2]: cloned, eliminated */) {
+                           double *ncDelta, int *ncCounts /* [2]: cloned, eliminated */, uint32_t *cloneSrc) {
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
     const uint32_t step = sc->step;
@@ -639,26 +639,8 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
         if (fl == 1) {
             // cloneParticles (:1107-1139): the n heaviest by eta*m (ties by id) are split
             const int n = nClone[c];
-            auto makeClone = [&](int slot, int rk, uint32_t id_i) {
-                const long long tailIdx = cloneOffset[c] + rk;
-                const long long dst = (long long)sc->nSlots + tailIdx;
-                if (dst >= capacity) { sc->overflow = 1; return; }
-                const V3 posOld = mk(S.px[slot], S.py[slot], S.pz[slot]);
-                const V3 pos = randomPointInCell(M, key, c, id_i, RNG_CLONE_POS, step);
-                const double mOld = S.m[slot];
-                const double mHalf = mOld / 2.0;
-                S.px[dst] = pos.x; S.py[dst] = pos.y; S.pz[dst] = pos.z;
-                S.ux[dst] = S.ux[slot]; S.uy[dst] = S.uy[slot]; S.uz[dst] = S.uz[slot];
-                S.m[dst] = mHalf; S.omega[dst] = S.omega[slot]; S.rho[dst] = S.rho[slot]; S.eta[dst] = S.eta[slot];
-                for (int k = 0; k < P.nPhi; ++k) S.phi[k][dst] = S.phi[k][slot];
-                S.cell[dst] = c; S.tet[dst] = locateTet(M, pos, c);
-                S.id[dst] = sc->nextId + (uint32_t)tailIdx * (uint32_t)nRanks;
-                if (M.axisym) {
-                    const double d = massPerDepth(M, pos, mHalf) + massPerDepth(M, posOld, mHalf) - massPerDepth(M, posOld, mOld);
-                    dsum[0] += d;
-                    for (int cs = 0; cs < P.nConserved; ++cs) dsum[1 + cs] += d * S.phi[P.conserved[cs]][slot];
-                }
-            };
+            // the clones themselves are created by k_nc_clone, one thread per task
+            auto makeClone = [&](int slot, int rk, uint32_t) { cloneSrc[cloneOffset[c] + rk] = (uint32_t)slot; };
             if (inRegs) {
                 double keyv[4]; uint32_t idv[4]; int slotv[4], rkv[4];
 #pragma unroll
@@ -792,6 +774,34 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
     }
 }
 
+// cloneParticles, second half (:1117-1137): one thread per clone task (source slot, already
+// halved) creates the copy at a random point of the cell; task t lands in slot nSlots + t
+__global__ void k_nc_clone(DMesh M, pdfb200_params P, PState S, const uint32_t *cloneSrc, const int *nTasks, StepScalars *sc,
+                           RngKey key, int nRanks, long long capacity, double *cloneDelta) {
+    const int n = *nTasks;
+    const uint32_t step = sc->step;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const long long dst = (long long)sc->nSlots + t;
+        if (dst >= capacity) { sc->overflow = 1; continue; }
+        const int slot = (int)cloneSrc[t];
+        const int c = S.cell[slot];
+        const V3 posOld = mk(S.px[slot], S.py[slot], S.pz[slot]);
+        const V3 pos = randomPointInCell(M, key, c, S.id[slot], RNG_CLONE_POS, step);
+        const double mHalf = S.m[slot], mOld = 2.0 * mHalf;   // the source was halved by k_nc_apply (exact)
+        S.px[dst] = pos.x; S.py[dst] = pos.y; S.pz[dst] = pos.z;
+        S.ux[dst] = S.ux[slot]; S.uy[dst] = S.uy[slot]; S.uz[dst] = S.uz[slot];
+        S.m[dst] = mHalf; S.omega[dst] = S.omega[slot]; S.rho[dst] = S.rho[slot]; S.eta[dst] = S.eta[slot];
+        for (int k = 0; k < P.nPhi; ++k) S.phi[k][dst] = S.phi[k][slot];
+        S.cell[dst] = c; S.tet[dst] = locateTet(M, pos, c);
+        S.id[dst] = sc->nextId + (uint32_t)t * (uint32_t)nRanks;
+        if (M.axisym) {
+            const double d = massPerDepth(M, pos, mHalf) + massPerDepth(M, posOld, mHalf) - massPerDepth(M, posOld, mOld);
+            cloneDelta[(size_t)t * K1_NC1] = d;
+            for (int cs = 0; cs < K1_MAXCONS; ++cs) cloneDelta[(size_t)t * K1_NC1 + 1 + cs] = cs < P.nConserved ? d * S.phi[P.conserved[cs]][slot] : 0.0;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // end of step: lost-mass shares, report scalars, next deltaT
 // ---------------------------------------------------------------------------
@@ -806,7 +816,8 @@ struct DevReport {
 #define RP_NCDELTA (RP_CELLMAX + 2)      // K1_NC1
 #define RP_INJ (RP_NCDELTA + K1_NC1)     // K1_NC1
 #define RP_LOSTSUM (RP_INJ + K1_NC1)     // 1: total lost mass re-spread
-#define RP_END (RP_LOSTSUM + 1)
+#define RP_CLONEDELTA (RP_LOSTSUM + 1)   // K1_NC1: axisymmetric mass-per-depth change of the clones
+#define RP_END (RP_CLONEDELTA + K1_NC1)
 static_assert(RP_END <= 64, "DevReport too small");
 
 // lostMass_/max(PaNIC,1) (mcParticleCloud.C:1363-1369); partial sums of what is re-spread
@@ -824,8 +835,9 @@ __global__ void k_lost_share(int nCells, const double *lostMass, const double *P
 }
 
 // column sums of an [n][K1_NC1] array: per-CTA partial rows (folded by k_fold_rows)
-__global__ void k_colsum_nc1(int n, const double *in, double *partial) {
+__global__ void k_colsum_nc1(int n, const double *in, double *partial, const int *nDev = nullptr) {
     __shared__ double sm[K1_NC1 * 32];
+    if (nDev) n = *nDev;
     double v[K1_NC1];
 #pragma unroll
     for (int k = 0; k < K1_NC1; ++k) v[k] = 0;
@@ -908,6 +920,7 @@ void Cloud::allocParticles() {
     scanTmp.alloc(8);
     injCount.alloc(std::max(nBnd, 1)); injOffset.alloc(std::max(nBnd, 1) + 1); injSums.alloc((size_t)std::max(nBnd, 1) * K1_NC1);
     ncDelta.alloc((size_t)nCells * K1_NC1);
+    if (axisym) cloneDelta.alloc((size_t)capacity * K1_NC1);
     Un.alloc(std::max(nBnd, 1)); Un.zero(stream);
     inletU.alloc((size_t)std::max(nBnd, 1) * 3); inletR.alloc((size_t)std::max(nBnd, 1) * 6); fwdTrans.alloc((size_t)std::max(nBnd, 1) * 9);
     probVec.alloc(std::max<size_t>(hFaceStart[nFaces] - hFaceStart[nInternalFaces], 1));
@@ -1045,7 +1058,12 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     k1Blocks = std::max(1, std::min(k1Blocks, 16));
     // the kernel specialised for this cloud's parameters and mesh flags, when there is one (jit.cu)
     void *k1Jit = specialisedKernel();
-    if (k1Jit) k1Blocks = K1_MIN_BLOCKS;
+    size_t k1JitSmem = K1_SMEM_BYTES;
+    if (k1Jit) {
+        k1Blocks = K1_MIN_BLOCKS;
+        if (const char *x = std::getenv("PDFB200_K1_BLOCKS")) k1Blocks = std::max(1, std::atoi(x));   // with -DK1_MIN_BLOCKS in PDFB200_JIT_FLAGS
+        if (const char *x = std::getenv("PDFB200_K1_SMEM")) k1JitSmem = (size_t)std::atol(x);          // with flags that change K1_SMEM_BYTES
+    }
     auto mark = [&](int r) { CUDA_CHECK(cudaEventRecord(evMark[r], stream)); };
 
     for (int st = 0; st < nSteps; ++st) {
@@ -1095,7 +1113,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         mark(1);
         if (k1Jit) {
             void *kargs[] = {&A};
-            CUDA_CHECK(cudaLaunchKernel(k1Jit, dim3(gridK1), dim3(K1_THREADS), kargs, K1_SMEM_BYTES, stream));
+            CUDA_CHECK(cudaLaunchKernel(k1Jit, dim3(gridK1), dim3(K1_THREADS), kargs, k1JitSmem, stream));
             ++launches;
         } else {
             LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
@@ -1152,13 +1170,23 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             LAUNCH(this, k_set_slots, 1, 32, 0, scal.p, total);
             const int gN = std::min(gridFor(nCells, 8), numSMs * 16);
             LAUNCH(this, k_nc_apply, gN, 256, 0, dm, prm, S[cur], valsB.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, ncOffset.p,
-                   PaNIC.p, scal.p, key, rank, nRanks, (long long)capacity, ncDelta.p, ncCounts.p);
+                   PaNIC.p, scal.p, key, rank, nRanks, (long long)capacity, ncDelta.p, ncCounts.p, keysA.p);
+            // the clones: one thread per task (scanTmp[1] = number of tasks); keysA is free until the next step
+            LAUNCH(this, k_nc_clone, numSMs * 8, 128, 0, dm, prm, S[cur], keysA.p, scanTmp.p + 1, scal.p, key, nRanks, (long long)capacity,
+                   cloneDelta.p);
             // fold ncDelta over cells deterministically: per-CTA partials, then rows
             const int gR = std::min(gridFor(nCells, 256), numSMs * 4);
             LAUNCH(this, k_colsum_nc1, gR, 256, 0, nCells, ncDelta.p, k1PartSum.p);
             LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
+            if (axisym) {
+                LAUNCH(this, k_colsum_nc1, gR, 256, 0, 0, cloneDelta.p, k1PartSum.p, scanTmp.p + 1);
+                LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_CLONEDELTA, 0);
+            } else {
+                CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
+            }
         } else {
             CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_NCDELTA, 0, K1_NC1 * sizeof(double), stream));
+            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
         }
         // ---- lost mass shares ----
         {
@@ -1201,7 +1229,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             r.etaMax = std::max(0.0, v[RP_K1MAX + ACC_ETAMAX]); r.etaMin = -v[RP_K1MAX + ACC_NEG_ETAMIN];
             r.CoMax = std::max(0.0, v[RP_K1MAX + ACC_COMAX]);
             for (int k = 0; k <= prm.nConserved; ++k) {
-                r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + v[RP_NCDELTA + k];
+                r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + (v[RP_NCDELTA + k] + v[RP_CLONEDELTA + k]);
                 r.massInInst[k] = v[RP_K1SUM + ACC_MASS_IN + k] + v[RP_INJ + k];
                 r.massOutInst[k] = v[RP_K1SUM + ACC_MASS_OUT + k];
             }
