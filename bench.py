@@ -205,10 +205,10 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 def ncu_traffic_bytes(args, n_phi):
     """DRAM bytes of one k_evolve launch as captured by ncu for the default workload
-    (profiles/r01_k_evolve_full_metrics.csv); None when the bench runs another workload."""
+    (profiles/r01_k_evolve_jit_metrics.csv); None when the bench runs another workload."""
     if list(args.cells) != [200, 100, 100] or args.ppc_per_gpu != 64 or n_phi != 1:
         return None
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_k_evolve_full_metrics.csv")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_k_evolve_jit_metrics.csv")
     try:
         tot = 0.0
         with open(path) as f:
@@ -339,7 +339,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_evolve", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(args, n_phi), "peak_source": peak_src,
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve "
-                                           "launch of this workload (profiles/r01_k_evolve_full_metrics.csv); null for other workloads",
+                                           "launch of this workload (profiles/r01_k_evolve_jit_metrics.csv); null for other workloads",
                          "algorithmic_bytes_per_launch": bpp * k_particles,
                          "algorithmic_bytes_per_particle_step": bpp},
             "e2e": {"value": e2e_psteps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
