@@ -34,6 +34,10 @@ METRICS = [
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
     "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
     "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    # sector efficiency and warp divergence (north_star's evidence list)
+    "smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.ratio", "smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio",
+    "smsp__sass_average_branch_targets_threads_uniform.pct", "smsp__thread_inst_executed_pred_on_per_inst_executed.ratio",
+    "dram__cycles_active.avg", "dram__cycles_elapsed.avg",
 ]
 
 
