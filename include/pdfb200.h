@@ -289,6 +289,13 @@ int64_t pdfb200_kernel_launches(pdfb200_cloud *cloud);
 int pdfb200_profile(pdfb200_cloud *cloud, double out[8], int reset);
 /* device time (ms) of the last evolve() call, CUDA events on the library's stream */
 double pdfb200_last_evolve_ms(pdfb200_cloud *cloud);
+/* Run-time selection, GPU style (mcModel::New / run-time selection tables, e.g.
+ * mcVelocityModel.C:54-79): at the first evolve() the particle kernel is compiled once more
+ * with the cloud's parameters and mesh flags as constants (jit.cu). This
+ * returns the translation unit that would be compiled for the given parameters and flags
+ * (host only, no device needed; the CPU test-suite builds it); length of the text or -1. */
+long pdfb200_jit_source(const pdfb200_params *params, int axisym, int hasOpen, int tetBits, const int32_t geometricD[3],
+                        const int32_t solutionD[3], char *buf, long bufLen);
 
 #ifdef __cplusplus
 }

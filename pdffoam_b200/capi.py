@@ -171,7 +171,7 @@ API_SYMBOLS = [
     "upload_cloud_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
-    "kernel_launches", "last_evolve_ms", "profile",
+    "kernel_launches", "last_evolve_ms", "profile", "jit_source",
 ]
 
 
@@ -221,11 +221,26 @@ class Library:
             f("kernel_launches").argtypes = [vp]; f("kernel_launches").restype = C.c_int64
             f("last_evolve_ms").argtypes = [vp]; f("last_evolve_ms").restype = C.c_double
             f("profile").argtypes = [vp, c_double_p, C.c_int]
+        if self.has("jit_source"):
+            f("jit_source").argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_char_p, C.c_long]
+            f("jit_source").restype = C.c_long
 
     def check(self, status: int, what: str):
         if status != 0:
             msg = self.fn("last_error")()
             raise PdfError(f"{self.prefix}{what} failed ({status}): {msg.decode() if msg else ''}")
+
+
+def jit_source(lib: "Library", params: Params, axisym: bool, has_open: bool, tet_bits: int = 0,
+               geometric_d=(1, 1, 1), solution_d=(1, 1, 1)) -> str:
+    """The translation unit the library compiles at run time for these parameters
+    and mesh flags (pdffoam_b200/csrc/jit.cu); host only."""
+    buf = C.create_string_buffer(1 << 16)
+    g = np.asarray(geometric_d, np.int32); sd = np.asarray(solution_d, np.int32)
+    n = lib.fn("jit_source")(C.byref(params), int(axisym), int(has_open), int(tet_bits), _ip(g), _ip(sd), buf, len(buf))
+    if n < 0:
+        raise PdfError("jit_source: buffer too small")
+    return buf.value.decode()
 
 
 _DEVICE_LIB: Optional[Library] = None

@@ -34,16 +34,15 @@ std::string hexDouble(double v) {
 }
 
 // the constants the kernel may rely on: the parameters k_evolve reads and the mesh flags
-std::string prologue(const Cloud &c) {
-    const pdfb200_params &p = c.prm;
+std::string prologue(const pdfb200_params &p, bool axisym, bool hasOpen, int tetBits, const int geoD[3], const int solD[3]) {
     std::ostringstream o;
     o << "#define K1_JIT 1\n";
     o << "#define JIT_NPHI " << (p.nPhi <= 1 ? 1 : p.nPhi == 2 ? 2 : p.nPhi == 3 ? 3 : PDFB200_MAX_PHI) << "\n";
-    o << "#define JIT_AXISYM " << (c.axisym ? 1 : 0) << "\n";
-    o << "#define JIT_HAS_OPEN " << (c.hasOpen ? 1 : 0) << "\n";
-    o << "#define JIT_TETBITS " << c.tetBits << "\n";
-    o << "#define JIT_NGEOD " << c.dm.nGeoD << "\n";
-    for (int k = 0; k < 3; ++k) o << "#define JIT_GEOD" << k << " (" << c.dm.geoD[k] << ")\n#define JIT_SOLD" << k << " (" << c.dm.solD[k] << ")\n";
+    o << "#define JIT_AXISYM " << (axisym ? 1 : 0) << "\n";
+    o << "#define JIT_HAS_OPEN " << (hasOpen ? 1 : 0) << "\n";
+    o << "#define JIT_TETBITS " << tetBits << "\n";
+    o << "#define JIT_NGEOD " << ((geoD[0] > 0) + (geoD[1] > 0) + (geoD[2] > 0)) << "\n";
+    for (int k = 0; k < 3; ++k) o << "#define JIT_GEOD" << k << " (" << geoD[k] << ")\n#define JIT_SOLD" << k << " (" << solD[k] << ")\n";
     o << "#include \"cloud.hpp\"\n";
     o << "struct JitP {\n";
 #define JI(f) o << "    static constexpr int " #f " = " << p.f << ";\n";
@@ -102,12 +101,19 @@ std::string findNvcc() {
     return "nvcc";
 }
 
-std::string cacheDir() {
-    std::string d;
-    if (const char *e = std::getenv("PDFB200_JIT_CACHE")) d = e;
-    else d = "/tmp/pdfb200_jit_" + std::to_string((long)getuid());
+bool writableDir(const std::string &d) {
     ::mkdir(d.c_str(), 0700);
-    return d;
+    return ::access(d.c_str(), W_OK | X_OK) == 0;
+}
+
+// $PDFB200_JIT_CACHE, else $TMPDIR or /tmp, else a directory next to the library
+std::string cacheDir(const std::string &srcDir) {
+    const std::string leaf = "pdfb200_jit_" + std::to_string((long)getuid());
+    if (const char *e = std::getenv("PDFB200_JIT_CACHE")) return writableDir(e) ? std::string(e) : std::string();
+    if (const char *e = std::getenv("TMPDIR")) { const std::string d = std::string(e) + "/" + leaf; if (writableDir(d)) return d; }
+    if (writableDir("/tmp/" + leaf)) return "/tmp/" + leaf;
+    if (writableDir(srcDir + "/jit_cache")) return srcDir + "/jit_cache";
+    return std::string();
 }
 
 }  // namespace
@@ -126,13 +132,18 @@ void *Cloud::specialisedKernel() {
         std::fprintf(stderr, "pdfb200: kernel sources not found in %s; running the generic particle kernel\n", dir.c_str());
         return nullptr;
     }
-    const std::string pro = prologue(*this);
+    const std::string pro = prologue(prm, axisym, hasOpen, tetBits, dm.geoD, dm.solD);
     std::string flags = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false";
     if (const char *x = std::getenv("PDFB200_JIT_FLAGS")) flags += std::string(" ") + x;   // tuning experiments (-DK1_...)
     const uint64_t h = fnv1a(srcA, fnv1a(srcH, fnv1a(srcC, fnv1a(srcK, fnv1a(flags, fnv1a(pro))))));
     char name[64];
     std::snprintf(name, sizeof name, "k_evolve_%016llx", (unsigned long long)h);
-    const std::string cdir = cacheDir(), cubin = cdir + "/" + name + ".cubin";
+    const std::string cdir = cacheDir(dir);
+    if (cdir.empty()) {
+        std::fprintf(stderr, "pdfb200: no writable cache directory for the specialised kernel; running the generic kernel\n");
+        return nullptr;
+    }
+    const std::string cubin = cdir + "/" + name + ".cubin";
     if (!fileExists(cubin)) {
         const std::string cu = cdir + "/" + name + "." + std::to_string((long)getpid()) + ".cu", tmp = cubin + "." + std::to_string((long)getpid());
         { std::ofstream f(cu); f << pro; }
@@ -163,4 +174,16 @@ void *Cloud::specialisedKernel() {
 void Cloud::dropSpecialisedKernel() {
     if (jitLibrary) cudaLibraryUnload(reinterpret_cast<cudaLibrary_t>(jitLibrary));
     jitLibrary = nullptr; jitKernel = nullptr; jitState = 0;
+}
+
+// The translation unit specialisedKernel() would compile for these parameters and mesh flags
+// (host only, no device needed): lets the CPU test-suite check that the kernel source builds
+// under K1_JIT. Returns the length of the text, or -1 when it does not fit.
+extern "C" long pdfb200_jit_source(const pdfb200_params *p, int axisym, int hasOpen, int tetBits, const int32_t geoD[3],
+                                   const int32_t solD[3], char *buf, long bufLen) {
+    const int g[3] = {geoD[0], geoD[1], geoD[2]}, sd[3] = {solD[0], solD[1], solD[2]};
+    const std::string t = prologue(*p, axisym != 0, hasOpen != 0, tetBits, g, sd);
+    if ((long)t.size() + 1 > bufLen) return -1;
+    std::memcpy(buf, t.c_str(), t.size() + 1);
+    return (long)t.size();
 }

@@ -39,7 +39,7 @@ def test_device_library_exports_every_declared_symbol():
     from oracle.oracle import OracleLib
     ol = OracleLib()
     for s in capi.API_SYMBOLS:
-        if s in ("comm_unique_id", "comm_init", "kernel_launches", "last_evolve_ms", "profile"):
+        if s in ("comm_unique_id", "comm_init", "kernel_launches", "last_evolve_ms", "profile", "jit_source"):
             continue
         assert ol.has(s), f"oracle does not export pdforacle_{s}"
 
@@ -130,3 +130,36 @@ def test_wedge_axisymmetry_detection(oracle_lib):
     np.testing.assert_allclose(np.abs(list(mi.centrePlaneNormal)), [0, 0, 1], atol=1e-14)
     # the box is not axisymmetric
     assert capi.CloudHandle(oracle_lib, meshgen.box_mesh(2, 2, 2), cases.default_params(1), capacity=10).mesh_info().isAxiSymmetric == 0
+
+
+def _jit_cases():
+    gold = os.path.join(ROOT, "tests", "golden")
+    yield "synthetic box (bench workload)", cases.synthetic_box(4, 2, 2, ppc=64, closed=False, number_control=True), False, True
+    tab = cases.load_flamelet_tables(os.path.join(gold, "flamelet_sandiaD.npz"))
+    yield "flamelet, 3 scalars", cases.with_scalars(cases.synthetic_box(4, 2, 2, ppc=8, closed=True), ["z", "chi", "T"],
+                                                    "SteadyFlamelet", tab), False, False
+    yield "BurkeSchumann wedge", cases.with_scalars(cases.wedge_jet(nx=4, nr_jet=2, nr_co=2, ppc=8), ["z", "T"], "BurkeSchumann"), True, True
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_specialised_kernel_source_compiles_for_sm100a(tmp_path, idx):
+    """The translation unit the library builds at run time (jit.cu) for three model
+    selections: nvcc must compile it for sm_100a and the cubin must hold k_evolve_jit.
+    (Running it needs a GPU: tests/test_gpu_jit.py.)"""
+    name, case, axisym, has_open = list(_jit_cases())[idx]
+    lib = C.CDLL(capi.device_library_path())
+    holder = capi.Library.__new__(capi.Library)
+    holder.lib, holder.prefix = lib, "pdfb200_"
+    holder._declare()
+    gd = case.mesh.geometric_d
+    src = capi.jit_source(holder, case.params, axisym, has_open, 0, gd, case.mesh.solution_d)
+    assert "struct JitP" in src and f"JIT_AXISYM {int(axisym)}" in src
+    cu = tmp_path / "k.cu"
+    cu.write_text(src)
+    out = tmp_path / "k.cubin"
+    csrc = os.path.join(ROOT, "pdffoam_b200", "csrc")
+    r = subprocess.run(["nvcc", "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                        "-fmad=false", "-I" + csrc, "-o", str(out), str(cu)], capture_output=True, text=True)
+    assert r.returncode == 0, f"{name}: {r.stderr[-3000:]}"
+    sym = subprocess.run(["cuobjdump", "-elf", str(out)], capture_output=True, text=True).stdout
+    assert "k_evolve_jit" in sym
