@@ -66,7 +66,8 @@ enum {
     PDFB200_REACTION_NONE = 0,
     PDFB200_REACTION_COLD = 1,            /* "cold"           */
     PDFB200_REACTION_BURKE_SCHUMANN = 2,  /* "BurkeSchumann"  */
-    PDFB200_REACTION_STEADY_FLAMELET = 3  /* "SteadyFlamelet" */
+    PDFB200_REACTION_STEADY_FLAMELET = 3, /* "SteadyFlamelet" */
+    PDFB200_REACTION_NAIVE_FLAMELET = 4   /* "naiveFlamelet" (mcNaiveFlameletModel.C:64-69): rho = 1 - 3.2 z (1 - z), T = 1e5 / rho */
 };
 enum { PDFB200_POSCORR_NONE = 0, PDFB200_POSCORR_LIMITED_SIMPLE = 1 }; /* "limitedSimple" */
 enum { PDFB200_LTS_NONE = 0, PDFB200_LTS_CELL = 1, PDFB200_LTS_PARTICLE = 2 }; /* "cell","particle" */

@@ -389,6 +389,12 @@ void Cloud::reactionCorrect(Particle &p) const {
         p.Phi[prm.TIdx] = T;
         break;
     }
+    case PDFB200_REACTION_NAIVE_FLAMELET: {      // mcNaiveFlameletModel.C:64-69
+        const double z = p.Phi[prm.zIdx];
+        p.rho = (1. - 3.2 * z * (1. - z));
+        p.Phi[prm.TIdx] = 1e5 / p.rho;
+        break;
+    }
     case PDFB200_REACTION_STEADY_FLAMELET: {     // mcSteadyFlamelet.C:304-329
         const double z = p.Phi[prm.zIdx];
         const double zVar = interp(zVarN, p);

@@ -21,7 +21,7 @@ from .meshgen import PolyMesh
 VELOCITY_MODELS = {"none": 0, "SLMFull": 1}                 # mcSLMFullVelocityModel.C:39-45
 MIXING_MODELS = {"none": 0, "IEM": 1, "modifiedCurl": 2}     # mcIEMMixingModel.C:37-43; modifiedCurl is new
 OMEGA_MODELS = {"none": 0, "RAS": 1}                        # mcRASOmegaModel.C:63-69
-REACTION_MODELS = {"none": 0, "cold": 1, "BurkeSchumann": 2, "SteadyFlamelet": 3}
+REACTION_MODELS = {"none": 0, "cold": 1, "BurkeSchumann": 2, "SteadyFlamelet": 3, "naiveFlamelet": 4}
 POSITION_CORRECTIONS = {"none": 0, "limitedSimple": 1}
 LOCAL_TIME_STEPPING = {"none": 0, "off": 0, "false": 0, "cell": 1, "particle": 2}   # mcLocalTimeStepping.C:56-97
 INTERPOLATION_SCHEMES = {"cell": 0, "cellPointFace": 1}
@@ -269,6 +269,8 @@ def with_scalars(case: Case, names: Sequence[str], reaction: str, tables: Option
                     bsTstoi=2000.0, bsZstoi=0.5)
         case.fv["p"] = case.fv["p"] + 1.0e5          # absolute pressure for rho = p/(R T)
         case.fv["pb"] = case.fv["pb"] + 1.0e5
+    elif reaction == "naiveFlamelet":
+        base.update(TIdx=names.index("T"))
     base.update(kw)
     case.params = default_params(n_phi, mixed=[0], conserved=[0], **base)
     return case

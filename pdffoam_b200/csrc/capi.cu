@@ -51,12 +51,15 @@ static void validateParams(const pdfb200_params &p) {
     if (p.velocityModel < 0 || p.velocityModel > PDFB200_VELOCITY_SLMFULL) throw std::invalid_argument("Unknown mcVelocityModel type");
     if (p.mixingModel < 0 || p.mixingModel > PDFB200_MIXING_MODCURL) throw std::invalid_argument("Unknown mcMixingModel type");
     if (p.omegaModel < 0 || p.omegaModel > PDFB200_OMEGA_RAS) throw std::invalid_argument("Unknown mcOmegaModel type");
-    if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_STEADY_FLAMELET) throw std::invalid_argument("Unknown mcReactionModel type");
+    if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_NAIVE_FLAMELET) throw std::invalid_argument("Unknown mcReactionModel type");
     if (p.positionCorrection < 0 || p.positionCorrection > PDFB200_POSCORR_LIMITED_SIMPLE) throw std::invalid_argument("Unknown mcPositionCorrection type");
     if (p.localTimeStepping < 0 || p.localTimeStepping > PDFB200_LTS_PARTICLE) throw std::invalid_argument("Unknown mcLocalTimeStepping type");
-    if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET)
+    if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET ||
+        p.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET)
         if (p.zIdx < 0 || p.zIdx >= p.nPhi) throw std::invalid_argument("reaction model: zIdx out of range");
-    if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN && (p.TIdx < 0 || p.TIdx >= p.nPhi)) throw std::invalid_argument("BurkeSchumann: TIdx out of range");
+    if ((p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET) &&
+        (p.TIdx < 0 || p.TIdx >= p.nPhi))
+        throw std::invalid_argument("reaction model: TIdx out of range");
     if (p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET) {
         if (p.chiIdx < 0 || p.chiIdx >= p.nPhi) throw std::invalid_argument("SteadyFlamelet: chiIdx out of range");
         if (p.nAdded < 0 || p.nAdded > PDFB200_MAX_ADDED) throw std::invalid_argument("SteadyFlamelet: too many added scalars");

@@ -37,6 +37,7 @@ struct HostPatch { int start, size, geom, handler, reflecting; };
 
 // layout of the particle kernel's per-thread accumulators
 #define K1_THREADS 128
+#define K1_JIT_MIN_BLOCKS 3   // CTAs per SM the run-time specialised kernel is compiled for
 #ifndef K1_MAXCONS
 #define K1_MAXCONS 3
 #endif

@@ -229,6 +229,12 @@ __device__ __forceinline__ void reactionCorrect(const KParams &P, const Flamelet
         rho = pCell / RT;
 #pragma unroll
         for (int k = 0; k < NPHI; ++k) if (k == P.TIdx) phi[k] = Tt;
+    } else if (P.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET) {   // mcNaiveFlameletModel.C:64-69
+        const double z = pickPhi(phi, P.zIdx);
+        rho = (1. - 3.2 * z * (1. - z));
+        const double Tt = 1e5 / rho;
+#pragma unroll
+        for (int k = 0; k < NPHI; ++k) if (k == P.TIdx) phi[k] = Tt;
     } else if (P.reactionModel == PDFB200_REACTION_STEADY_FLAMELET) {
         const double z = pickPhi(phi, P.zIdx);
         const double chi = fmax(P.Cchi * Omega * zVar, PDF_SMALL);

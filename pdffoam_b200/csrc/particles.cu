@@ -1060,7 +1060,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     void *k1Jit = specialisedKernel();
     size_t k1JitSmem = K1_SMEM_BYTES;
     if (k1Jit) {
-        k1Blocks = K1_MIN_BLOCKS;
+        k1Blocks = K1_JIT_MIN_BLOCKS;
         if (const char *x = std::getenv("PDFB200_K1_BLOCKS")) k1Blocks = std::max(1, std::atoi(x));   // with -DK1_MIN_BLOCKS in PDFB200_JIT_FLAGS
         if (const char *x = std::getenv("PDFB200_K1_SMEM")) k1JitSmem = (size_t)std::atol(x);          // with flags that change K1_SMEM_BYTES
     }

@@ -133,3 +133,16 @@ def test_axisymmetric_wedge_jet(device_lib, oracle_lib):
     assert sum(r[0].nInjected for r in reps) > 0
     P = dev.download_particles()
     assert np.all(P["pos"][:, 2] == 0.0)                          # particles stay on the centre plane
+
+
+def test_naive_flamelet(device_lib, oracle_lib):
+    """mcNaiveFlameletModel.C:64-69: rho = 1 - 3.2 z (1 - z), T = 1e5 / rho."""
+    case = cases.with_scalars(cases.synthetic_box(6, 4, 4, ppc=18, closed=False), ["z", "T"], "naiveFlamelet")
+    case.params.deltaT0 = 2e-3
+    P = case.random_particles(18, seed=8)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=5, rtol=RTOL, atol=ATOL)
+    Q = dev.download_particles()
+    z, T = Q["Phi"][0], Q["Phi"][1]
+    old = Q["id"] < P["m"].shape[0]                      # injected particles carry the patch values until their first step
+    np.testing.assert_allclose(Q["rho"][old], 1 - 3.2 * z[old] * (1 - z[old]), rtol=1e-14)
+    np.testing.assert_allclose(T[old], 1e5 / Q["rho"][old], rtol=1e-14)

@@ -239,3 +239,16 @@ def test_error_behaviour(oracle_lib, tmp_path):
         h.evolve(1)                                            # no fields yet
     with pytest.raises(PdfError, match="monotonically"):
         h.set_flamelet_tables(np.array([1.0, 0.5]), np.array([0.0, 1.0]), [np.zeros((2, 2))])
+
+
+def test_naive_flamelet_relation(oracle_lib):
+    """mcNaiveFlameletModel.C:64-69 on the CPU restatement."""
+    case = cases.with_scalars(cases.synthetic_box(4, 3, 3, ppc=12, closed=True), ["z", "T"], "naiveFlamelet")
+    case.params.deltaT0 = 2e-3
+    h = case.make_cloud(oracle_lib)
+    h.upload_particles(case.random_particles(12, seed=2))
+    h.evolve(3)
+    Q = h.download_particles()
+    z = Q["Phi"][0]
+    np.testing.assert_allclose(Q["rho"], 1 - 3.2 * z * (1 - z), rtol=1e-15)
+    np.testing.assert_allclose(Q["Phi"][1], 1e5 / Q["rho"], rtol=1e-15)
