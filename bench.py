@@ -98,7 +98,7 @@ def build_case(args, n_ranks):
     return case
 
 
-def cpu_baseline(args, sample_cells=(40, 20, 20), steps=3):
+def cpu_baseline(args, sample_cells=(40, 20, 20), steps=10):
     """The oracle ("port" of the reference's evolve) timed single-threaded on a
     bounded sample of the same workload (same ppc, same fields, fewer cells)."""
     from pdffoam_b200 import cases
