@@ -124,7 +124,7 @@ struct Cloud {
     DBuf<int> injPatchTail;
     DBuf<unsigned char> cubTemp;
     DBuf<int> cellStart, cellEnd, ncFlag, ncCount, ncOffset, scanTmp, scanTileSums, scanTileOffs;
-    DBuf<int> injCount, injOffset;
+    DBuf<int> injCount, injOffset, csCount, csCursor;
     DBuf<double> injSums;
     DBuf<double> k1PartSum, k1PartMax, cellPartSum, finalSums;   // deterministic reductions
     DBuf<double> ncDelta, cloneDelta;   // cloneDelta: [capacity][K1_NC1], axisymmetric cases only

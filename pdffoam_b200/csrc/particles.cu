@@ -138,6 +138,106 @@ __global__ void k_cell_bounds(int n, const uint32_t *keys, int tetBits, int *cel
     if (kn == KEY_DEAD) sc->nSorted = i + 1;
 }
 
+// ---------------------------------------------------------------------------
+// Counting sort by cell (used when the key is the cell label alone): histogram, exclusive scan,
+// scatter — warp-aggregated integer atomics, so the *set* of entries of a cell is exact but
+// their order depends on timing — and then every cell's segment is put into ascending order
+// of the previous index by a bitonic network in registers. That is exactly the permutation a
+// stable sort by cell produces (what cub::DeviceRadixSort::SortPairs gave in three 8-bit passes
+// over 1 GB each), at one pass over the keys per kernel.
+// ---------------------------------------------------------------------------
+__global__ void k_cs_hist(int n, const uint32_t *keys, int *count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t key = i < n ? keys[i] : KEY_DEAD;
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    if (key != KEY_DEAD && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(count + key, __popc(m));
+}
+
+__global__ void k_cs_scatter(int n, const uint32_t *keys, const int *cellStart, int *cursor, uint32_t *perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t key = i < n ? keys[i] : KEY_DEAD;
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (key != KEY_DEAD && lane == leader) base = atomicAdd(cursor + key, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key != KEY_DEAD) perm[cellStart[key] + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+}
+
+// bitonic sort of 32*K values held K per lane (element index = k*32 + lane), ascending
+template <int K>
+__device__ __forceinline__ void warpBitonic(uint32_t (&v)[K], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int ks = stride >> 5;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if ((k & ks) == 0) {
+                        const bool asc = ((k << 5) & size) == 0;
+                        const uint32_t a = v[k], b = v[k | ks];
+                        const uint32_t lo = min(a, b), hi = max(a, b);
+                        v[k] = asc ? lo : hi; v[k | ks] = asc ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t p = __shfl_xor_sync(0xffffffffu, v[k], stride);
+                    const bool asc = (((k << 5) | lane) & size) == 0;
+                    const bool lower = (lane & stride) == 0;
+                    v[k] = (lower == asc) ? min(v[k], p) : max(v[k], p);
+                }
+            }
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void sortSegment(uint32_t *seg, int n, int lane) {
+    uint32_t v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; v[k] = j < n ? seg[j] : 0xffffffffu; }
+    warpBitonic<K>(v, lane);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; if (j < n) seg[j] = v[k]; }
+}
+
+// one warp per cell: segment end + canonical (ascending) order of the segment
+__global__ void k_cs_order(int nCells, const int *cellStart, const int *count, int *cellEnd, uint32_t *perm, uint32_t *scratch) {
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    for (int c = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); c < nCells; c += gridDim.x * warpsPerBlock) {
+        const int s = cellStart[c], n = count[c];
+        if (lane == 0) cellEnd[c] = s + n;
+        if (n <= 1) continue;
+        uint32_t *seg = perm + s;
+        if (n <= 32) sortSegment<1>(seg, n, lane);
+        else if (n <= 64) sortSegment<2>(seg, n, lane);
+        else if (n <= 128) sortSegment<4>(seg, n, lane);
+        else if (n <= 256) sortSegment<8>(seg, n, lane);
+        else {
+            // very full cells: rank by counting through the scratch array (values are distinct)
+            for (int j = lane; j < n; j += 32) {
+                const uint32_t x = seg[j];
+                int rk = 0;
+                for (int q = 0; q < n; ++q) rk += seg[q] < x ? 1 : 0;
+                scratch[s + rk] = x;
+            }
+            __syncwarp();
+            for (int j = lane; j < n; j += 32) seg[j] = scratch[s + j];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void k_cs_finish(const int *total, StepScalars *sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSorted = *total;
+}
+
 // updateCloudPDF first half (mcParticleCloud.C:929-956): one warp per cell,
 // lanes stride over the cell's segment of the sorted order, butterfly reduction
 // in a fixed order -> deterministic sums without atomics.
@@ -918,6 +1018,7 @@ void Cloud::allocParticles() {
     cubTemp.alloc(tempBytes + 256);
     cellStart.alloc(nCells); cellEnd.alloc(nCells); ncFlag.alloc(nCells); ncCount.alloc(nCells + 1); ncOffset.alloc(nCells + 1);
     scanTmp.alloc(8);
+    csCount.alloc(nCells); csCursor.alloc(nCells);
     injCount.alloc(std::max(nBnd, 1)); injOffset.alloc(std::max(nBnd, 1) + 1); injSums.alloc((size_t)std::max(nBnd, 1) * K1_NC1);
     ncDelta.alloc((size_t)nCells * K1_NC1);
     if (axisym) cloneDelta.alloc((size_t)capacity * K1_NC1);
@@ -1123,15 +1224,29 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
         cur ^= 1;
 
-        // ---- radix sort by (cell, tet) + segment bounds + moments ----
-        size_t tempBytes = cubTemp.n;
-        if (total > 0)
-            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
-        mark(3);
-        CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
-        CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
-        if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellStart.p, cellEnd.p, scal.p);
-        else { hScal->nSorted = 0; }
+        // ---- sort by cell + segment bounds ----
+        static const bool forceRadix = [] { const char *e = std::getenv("PDFB200_SORT"); return e && std::string(e) == "radix"; }();
+        if (tetBits == 0 && !forceRadix) {
+            // counting sort by cell (see k_cs_*): same permutation as the stable radix sort
+            CUDA_CHECK(cudaMemsetAsync(csCount.p, 0, nCells * sizeof(int), stream));
+            CUDA_CHECK(cudaMemsetAsync(csCursor.p, 0, nCells * sizeof(int), stream));
+            if (total > 0) LAUNCH(this, k_cs_hist, gridFor(total, 256), 256, 0, total, keysA.p, csCount.p);
+            scanInts(*this, nCells, csCount.p, cellStart.p, scanTmp.p + 2);
+            if (total > 0) LAUNCH(this, k_cs_scatter, gridFor(total, 256), 256, 0, total, keysA.p, cellStart.p, csCursor.p, valsB.p);
+            mark(3);
+            LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, cellStart.p, csCount.p, cellEnd.p, valsB.p, keysB.p);
+            LAUNCH(this, k_cs_finish, 1, 32, 0, scanTmp.p + 2, scal.p);
+        } else {
+            // radix sort by (cell, tet)
+            size_t tempBytes = cubTemp.n;
+            if (total > 0)
+                CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
+            mark(3);
+            CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
+            CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
+            if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellStart.p, cellEnd.p, scal.p);
+            else { hScal->nSorted = 0; }
+        }
         // "modifiedCurl" pair mixing on the sorted order, before the moments are taken
         if (prm.mixingModel == PDFB200_MIXING_MODCURL && prm.nMixed > 0 && total > 0) {
             if (valsA.n < (size_t)capacity) valsA.alloc(capacity);
