@@ -87,10 +87,13 @@ __global__ void k_prep_cells(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
 }
 
 __global__ void k_prep_reduce1(int nRows, const double *partials, pdfb200_params P, StepScalars *sc, double *scratch) {
-    // single warp, fixed order
-    if (threadIdx.x != 0) return;
+    // one warp; maxima are order-independent, so the lanes may share the rows
     double v[4] = {0.0, -PDF_VGREAT, -PDF_VGREAT, -PDF_VGREAT};
-    for (int r = 0; r < nRows; ++r) for (int k = 0; k < 4; ++k) v[k] = fmax(v[k], partials[r * 4 + k]);
+    for (int r = threadIdx.x; r < nRows; r += 32) for (int k = 0; k < 4; ++k) v[k] = fmax(v[k], partials[r * 4 + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 4; ++k) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+    if (threadIdx.x != 0) return;
     scratch[0] = tanh(10. * v[0]);                                  // phiLim
     sc->omegaClip = (v[1] > P.Omega0) ? P.Omega0 : 1.7976931348623157e308;
     if (P.localTimeStepping == PDFB200_LTS_CELL) {
@@ -138,9 +141,11 @@ __global__ void k_prep_grad(DMesh M, FieldPtrs F, const StepScalars *sc, double 
 }
 
 __global__ void k_prep_reduce2(int nRows, const double *partials, pdfb200_params P, StepScalars *sc, const double *scratch) {
-    if (threadIdx.x != 0) return;
     double Co = 0;
-    for (int r = 0; r < nRows; ++r) Co = fmax(Co, partials[r]);
+    for (int r = threadIdx.x; r < nRows; r += 32) Co = fmax(Co, partials[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Co = fmax(Co, __shfl_xor_sync(0xffffffffu, Co, o));
+    if (threadIdx.x != 0) return;
     double corr = 0.;
     if (Co > PDF_SMALL) corr = P.pcCFL / Co * P.pcC * scratch[0];
     sc->pcCorr = corr;

@@ -699,7 +699,7 @@ __global__ void k_inject_finish(int nBnd, const int *total, StepScalars *sc, lon
 // particle-number control (mcParticleCloud.C:1014-1221)
 // ---------------------------------------------------------------------------
 __global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, const int *cellStart, const int *cellEnd,
-                              int *flag, int *nClone, int nRanks) {
+                              int *flag, int *nClone, int nRanks, int *list, int *nList) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= M.nCells) return;
     const int Npc = P.particlesPerCell;
@@ -715,17 +715,22 @@ __global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, co
         n = min(n, nLocal);
     }
     flag[c] = fl; nClone[c] = n;
+    // cells that need work go on a list (its order does not matter: cells are independent)
+    if (fl > 0) list[atomicAdd(nList, 1)] = c;
 }
 
 // one warp per flagged cell
 __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
                            const int *cellEnd, const int *flag, const int *nClone, const int *cloneOffset,
                            double *PaNIC, StepScalars *sc, RngKey key, int rank, int nRanks, long long capacity,
-                           double *ncDelta, int *ncCounts /* [2]: cloned, eliminated */, uint32_t *cloneSrc) {
+                           double *ncDelta, int *ncCounts /* [2]: cloned, eliminated */, uint32_t *cloneSrc, const int *list,
+                           const int *nListPtr) {
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
     const uint32_t step = sc->step;
-    for (int c = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); c < M.nCells; c += gridDim.x * warpsPerBlock) {
+    const int nList = *nListPtr;
+    for (int li = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); li < nList; li += gridDim.x * warpsPerBlock) {
+        const int c = list[li];
         const int fl = flag[c];
         if (fl <= 0) continue;
         const int s = cellStart[c], e = cellEnd[c];
@@ -1278,14 +1283,16 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         CUDA_CHECK(cudaMemsetAsync(ncCounts.p, 0, 2 * sizeof(int), stream));
         const bool nc = prm.particleNumberControl != 0;
         if (nc) {
-            LAUNCH(this, k_nc_classify, gridFor(nCells, 256), 256, 0, dm, prm, PaNIC.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, nRanks);
+            CUDA_CHECK(cudaMemsetAsync(scanTmp.p + 3, 0, sizeof(int), stream));
+            LAUNCH(this, k_nc_classify, gridFor(nCells, 256), 256, 0, dm, prm, PaNIC.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, nRanks,
+                   csCursor.p, scanTmp.p + 3);
             scanInts(*this, nCells, ncCount.p, ncOffset.p, scanTmp.p + 1);
             CUDA_CHECK(cudaMemsetAsync(ncDelta.p, 0, (size_t)nCells * K1_NC1 * sizeof(double), stream));
             // nSlots for the clones = this step's entry count
             LAUNCH(this, k_set_slots, 1, 32, 0, scal.p, total);
             const int gN = std::min(gridFor(nCells, 8), numSMs * 16);
             LAUNCH(this, k_nc_apply, gN, 256, 0, dm, prm, S[cur], valsB.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, ncOffset.p,
-                   PaNIC.p, scal.p, key, rank, nRanks, (long long)capacity, ncDelta.p, ncCounts.p, keysA.p);
+                   PaNIC.p, scal.p, key, rank, nRanks, (long long)capacity, ncDelta.p, ncCounts.p, keysA.p, csCursor.p, scanTmp.p + 3);
             // the clones: one thread per task (scanTmp[1] = number of tasks); keysA is free until the next step
             LAUNCH(this, k_nc_clone, numSMs * 8, 128, 0, dm, prm, S[cur], keysA.p, scanTmp.p + 1, scal.p, key, nRanks, (long long)capacity,
                    cloneDelta.p);
