@@ -242,8 +242,11 @@ __global__ void k_cs_finish(const int *total, StepScalars *sc) {
 // lanes stride over the cell's segment of the sorted order, butterfly reduction
 // in a fixed order -> deterministic sums without atomics.
 // Block layout per cell: N, M, V, MU(3), MPhi(nPhi), MPhiPhi(nCov), MUU(6).
+#ifndef MOM_MIN_BLOCKS
+#define MOM_MIN_BLOCKS 4
+#endif
 template <int NPHI>
-__global__ void k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
+__global__ void __launch_bounds__(256, MOM_MIN_BLOCKS) k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
                           double *block, int nMom) {
     constexpr int NCOV = NPHI * (NPHI + 1) / 2;
     constexpr int NACC = 11 + NPHI + NCOV;   // all but the count
