@@ -36,7 +36,9 @@ struct HostPatch { int start, size, geom, handler, reflecting; };
 #define BLOCK_TAIL 32
 
 // layout of the particle kernel's per-thread accumulators
+#ifndef K1_THREADS
 #define K1_THREADS 128
+#endif
 #define K1_JIT_MIN_BLOCKS 3   // CTAs per SM the run-time specialised kernel is compiled for
 #ifndef K1_MAXCONS
 #define K1_MAXCONS 3
