@@ -94,7 +94,7 @@ struct Cloud {
         linWeights, pointWeights, patchFaceT;
     DBuf<double4> cellCentre4, bfNormal;
     DBuf<int> faceStart, facePoints, owner, neighbour, cellFaceStart, cellFaces, cellTetStart, faceTetStartOwn,
-        faceTetStartNei, pointCellStart, pointCells, bfInfo, openCellStart, openCellFaces;
+        faceTetStartNei, pointCellStart, pointCells, bfInfo, openCellStart, openCellFaces, cellRank, cellOfRank;
     DBuf<TetRec> tets;
 
     // ---- fields ----
@@ -126,7 +126,7 @@ struct Cloud {
     DBuf<int> injPatchTail;
     DBuf<unsigned char> cubTemp;
     DBuf<int> cellStart, cellEnd, ncFlag, ncCount, ncOffset, scanTmp, scanTileSums, scanTileOffs;
-    DBuf<int> injCount, injOffset, csCount, csCursor;
+    DBuf<int> injCount, injOffset, csCount, csCursor, csStart;
     DBuf<double> injSums;
     DBuf<double> k1PartSum, k1PartMax, cellPartSum, finalSums;   // deterministic reductions
     DBuf<double> ncDelta, cloneDelta;   // cloneDelta: [capacity][K1_NC1], axisymmetric cases only

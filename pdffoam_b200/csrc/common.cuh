@@ -93,6 +93,7 @@ struct DMesh {
     const int *faceStart, *facePoints, *owner, *neighbour;
     const int *cellFaceStart, *cellFaces;
     const int *cellTetStart;     // [nCells+1]
+    const int *cellRank, *cellOfRank;   // processing order of the cells (Morton curve through the centres) and its inverse
     const int *faceTetStartOwn, *faceTetStartNei;
     const double *faceCentres, *faceAreas, *magSf;   // [nFaces*3],[nFaces*3],[nFaces]
     const double4 *cellCentre4;  // xyz + hNum

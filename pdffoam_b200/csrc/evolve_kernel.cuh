@@ -681,9 +681,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 #pragma unroll
         for (int k = 0; k < NPHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
         A.out.cell[i] = cell; A.out.tet[i] = tet; A.out.id[i] = id;
-        // tetBits == 0: sort by cell only (the stable sort keeps the previous order inside a cell)
-        A.keyOut[i] = (MESH_TETBITS(M) == 0) ? (uint32_t)cell
-                                             : (((uint32_t)cell << MESH_TETBITS(M)) | (uint32_t)(tet - __ldg(M.cellTetStart + cell)));
+        // key: rank of the cell in the processing order (tetBits == 0: nothing else; the stable sort keeps
+        // the previous order inside a cell), else followed by the local tet
+        const uint32_t rank = (uint32_t)__ldg(M.cellRank + cell);
+        A.keyOut[i] = (MESH_TETBITS(M) == 0) ? rank
+                                             : ((rank << MESH_TETBITS(M)) | (uint32_t)(tet - __ldg(M.cellTetStart + cell)));
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {

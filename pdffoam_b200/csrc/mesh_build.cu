@@ -343,6 +343,49 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     LAUNCH(this, k_cell_co, gridFor((long long)hCF.size(), B), B, 0, (int)hCF.size(), cellFaces.p, courantCoeffs.p, cellCo.p);
     CUDA_CHECK(cudaMemcpyAsync(volumeOrArea.p, cellVolumes.p, nCells * sizeof(double), cudaMemcpyDeviceToDevice, s));
 
+    // ---- processing order of the cells ----
+    // Particles are sorted by the rank of their cell along a Morton curve through the cell
+    // centres rather than by the caller's cell label: cells that are neighbours in space are
+    // then processed close together in time, so the tet/node records and the state sectors a
+    // crossing particle touches are still in L2. PDFB200_CELL_ORDER=native keeps label order.
+    {
+        std::vector<double4> hC(nCells);
+        CUDA_CHECK(cudaMemcpyAsync(hC.data(), cellCentre4.p, (size_t)nCells * sizeof(double4), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<int> hRank(nCells), hOfRank(nCells);
+        const char *ord = std::getenv("PDFB200_CELL_ORDER");
+        if (ord && std::string(ord) == "native") {
+            for (int c = 0; c < nCells; ++c) hRank[c] = hOfRank[c] = c;
+        } else {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int c = 0; c < nCells; ++c) {
+                const double x[3] = {hC[c].x, hC[c].y, hC[c].z};
+                for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], x[k]); hi[k] = std::max(hi[k], x[k]); }
+            }
+            const double ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-300));
+            auto spread = [](unsigned long long v) {   // 21 bits -> every third bit
+                v &= 0x1fffffULL;
+                v = (v | v << 32) & 0x1f00000000ffffULL;
+                v = (v | v << 16) & 0x1f0000ff0000ffULL;
+                v = (v | v << 8) & 0x100f00f00f00f00fULL;
+                v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+                v = (v | v << 2) & 0x1249249249249249ULL;
+                return v;
+            };
+            std::vector<std::pair<unsigned long long, int>> code(nCells);
+            for (int c = 0; c < nCells; ++c) {
+                const double x[3] = {hC[c].x, hC[c].y, hC[c].z};
+                unsigned long long q[3];
+                for (int k = 0; k < 3; ++k) q[k] = (unsigned long long)std::min(2097151.0, std::max(0.0, (x[k] - lo[k]) / ext * 2097151.0));
+                code[c] = {spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), c};
+            }
+            std::sort(code.begin(), code.end());
+            for (int r = 0; r < nCells; ++r) { hOfRank[r] = code[r].second; hRank[code[r].second] = r; }
+        }
+        cellRank.upload(hRank.data(), nCells, s); cellOfRank.upload(hOfRank.data(), nCells, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+
     // ---- axisymmetry (mcParticleCloud.C:661-717, wedgePolyPatch::initTransforms) ----
     const int nGeoD = (m.geometricD[0] > 0) + (m.geometricD[1] > 0) + (m.geometricD[2] > 0);
     axisym = false;
@@ -395,6 +438,7 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     dm.nGeoD = nGeoD; dm.axisym = axisym; dm.openingAngle = openingAngle;
     dm.points = points.p; dm.faceStart = faceStart.p; dm.facePoints = facePoints.p; dm.owner = owner.p; dm.neighbour = neighbour.p;
     dm.cellFaceStart = cellFaceStart.p; dm.cellFaces = cellFaces.p; dm.cellTetStart = cellTetStart.p;
+    dm.cellRank = cellRank.p; dm.cellOfRank = cellOfRank.p;
     dm.faceTetStartOwn = faceTetStartOwn.p; dm.faceTetStartNei = faceTetStartNei.p;
     dm.faceCentres = faceCentres.p; dm.faceAreas = faceAreas.p; dm.magSf = magSf.p; dm.cellCentre4 = cellCentre4.p;
     dm.cellVolumes = cellVolumes.p; dm.volumeOrArea = volumeOrArea.p; dm.bbMin = bbMin.p; dm.bbMax = bbMax.p;

@@ -126,15 +126,17 @@ __global__ void k_scan_single(int n, const int *in, int *out, int *total) {
 // ---------------------------------------------------------------------------
 // segment bounds of the sorted keys and the per-cell moment reduction
 // ---------------------------------------------------------------------------
-__global__ void k_cell_bounds(int n, const uint32_t *keys, int tetBits, int *cellStart, int *cellEnd, StepScalars *sc) {
+// keys hold the cell's rank in the processing order; the bounds are stored per cell label
+__global__ void k_cell_bounds(int n, const uint32_t *keys, int tetBits, const int *cellOfRank, int *cellStart, int *cellEnd,
+                              StepScalars *sc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t k = keys[i];
     if (k == KEY_DEAD) { if (i == 0) sc->nSorted = 0; return; }
-    const uint32_t c = k >> tetBits;
-    if (i == 0 || (keys[i - 1] >> tetBits) != c) cellStart[c] = i;
+    const uint32_t r = k >> tetBits;
+    if (i == 0 || (keys[i - 1] >> tetBits) != r) cellStart[cellOfRank[r]] = i;
     const uint32_t kn = (i + 1 < n) ? keys[i + 1] : KEY_DEAD;
-    if (kn == KEY_DEAD || (kn >> tetBits) != c) cellEnd[c] = i + 1;
+    if (kn == KEY_DEAD || (kn >> tetBits) != r) cellEnd[cellOfRank[r]] = i + 1;
     if (kn == KEY_DEAD) sc->nSorted = i + 1;
 }
 
@@ -207,12 +209,13 @@ __device__ __forceinline__ void sortSegment(uint32_t *seg, int n, int lane) {
 }
 
 // one warp per cell: segment end + canonical (ascending) order of the segment
-__global__ void k_cs_order(int nCells, const int *cellStart, const int *count, int *cellEnd, uint32_t *perm, uint32_t *scratch) {
+__global__ void k_cs_order(int nCells, const int *rankStart, const int *count, const int *cellOfRank, int *cellStart, int *cellEnd,
+                           uint32_t *perm, uint32_t *scratch) {
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    for (int c = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); c < nCells; c += gridDim.x * warpsPerBlock) {
-        const int s = cellStart[c], n = count[c];
-        if (lane == 0) cellEnd[c] = s + n;
+    for (int r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < nCells; r += gridDim.x * warpsPerBlock) {
+        const int s = rankStart[r], n = count[r];
+        if (lane == 0) { const int c = cellOfRank[r]; cellStart[c] = s; cellEnd[c] = s + n; }
         if (n <= 1) continue;
         uint32_t *seg = perm + s;
         if (n <= 32) sortSegment<1>(seg, n, lane);
@@ -252,7 +255,8 @@ __global__ void __launch_bounds__(256, MOM_MIN_BLOCKS) k_moments(DMesh M, PState
     constexpr int NACC = 11 + NPHI + NCOV;   // all but the count
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    for (int c = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); c < M.nCells; c += gridDim.x * warpsPerBlock) {
+    for (int r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < M.nCells; r += gridDim.x * warpsPerBlock) {
+        const int c = M.cellOfRank[r];   // cells in processing order: neighbouring segments of the sorted arrays
         const int s = cellStart[c], e = cellEnd[c];
         double a[NACC];
 #pragma unroll
@@ -1026,7 +1030,7 @@ void Cloud::allocParticles() {
     cubTemp.alloc(tempBytes + 256);
     cellStart.alloc(nCells); cellEnd.alloc(nCells); ncFlag.alloc(nCells); ncCount.alloc(nCells + 1); ncOffset.alloc(nCells + 1);
     scanTmp.alloc(8);
-    csCount.alloc(nCells); csCursor.alloc(nCells);
+    csCount.alloc(nCells); csCursor.alloc(nCells); csStart.alloc(nCells);
     injCount.alloc(std::max(nBnd, 1)); injOffset.alloc(std::max(nBnd, 1) + 1); injSums.alloc((size_t)std::max(nBnd, 1) * K1_NC1);
     ncDelta.alloc((size_t)nCells * K1_NC1);
     if (axisym) cloneDelta.alloc((size_t)capacity * K1_NC1);
@@ -1239,10 +1243,11 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             CUDA_CHECK(cudaMemsetAsync(csCount.p, 0, nCells * sizeof(int), stream));
             CUDA_CHECK(cudaMemsetAsync(csCursor.p, 0, nCells * sizeof(int), stream));
             if (total > 0) LAUNCH(this, k_cs_hist, gridFor(total, 256), 256, 0, total, keysA.p, csCount.p);
-            scanInts(*this, nCells, csCount.p, cellStart.p, scanTmp.p + 2);
-            if (total > 0) LAUNCH(this, k_cs_scatter, gridFor(total, 256), 256, 0, total, keysA.p, cellStart.p, csCursor.p, valsB.p);
+            scanInts(*this, nCells, csCount.p, csStart.p, scanTmp.p + 2);
+            if (total > 0) LAUNCH(this, k_cs_scatter, gridFor(total, 256), 256, 0, total, keysA.p, csStart.p, csCursor.p, valsB.p);
             mark(3);
-            LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, cellStart.p, csCount.p, cellEnd.p, valsB.p, keysB.p);
+            LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, csStart.p, csCount.p, cellOfRank.p, cellStart.p,
+                   cellEnd.p, valsB.p, keysB.p);
             LAUNCH(this, k_cs_finish, 1, 32, 0, scanTmp.p + 2, scal.p);
         } else {
             // radix sort by (cell, tet)
@@ -1252,7 +1257,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             mark(3);
             CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
             CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
-            if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellStart.p, cellEnd.p, scal.p);
+            if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellOfRank.p, cellStart.p, cellEnd.p, scal.p);
             else { hScal->nSorted = 0; }
         }
         // "modifiedCurl" pair mixing on the sorted order, before the moments are taken
