@@ -422,6 +422,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         int tet = A.in.tet[slot];
         const uint32_t id = A.in.id[slot];
         if (anyLost) m += A.lostShare[cell];
+        // numerical-diffusion length of the start cell (used at E9, after the particle is put back): loaded here
+        // so that its latency is hidden behind the half step
+        const double hNumStart = __ldg(reinterpret_cast<const double *>(M.cellCentre4 + cell) + 3);
         const bool injected = (i >= nSorted + nInjStart);
         const int injPatch = injected ? A.injPatchTail[i - nSorted] : -1;
 
@@ -654,7 +657,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             pos = posOld;
             if (tet != tetOld) { tet = tetOld; loadTet(M.tets, stage, tet, T); }
             if (reflected) Utrack = Uold; else Utrack = 0.5 * (Uold + U);
-            const double hNum = __ldg(reinterpret_cast<const double *>(M.cellCentre4 + T.cell) + 3);
+            const double hNum = hNumStart;   // T.cell is the start cell again
             const double C = P.DNum * sqrt(hNum * deltaT * mag3(Utrack)) / deltaT;
             Utrack = Utrack + mk(C * gd0, C * gd1, C * gd2);
             Utrack = Utrack + Ucorr;
