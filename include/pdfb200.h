@@ -280,6 +280,12 @@ int pdfb200_download_tets(pdfb200_cloud *cloud, double *gradN, int32_t *nbr,
 int pdfb200_download_geometry(pdfb200_cloud *cloud, double *faceCentres, double *faceAreas,
                               double *cellCentres, double *cellVolumes,
                               double *courantCoeffs, double *hNum);
+/* The keyed counter-based generator (Philox4x32-10, counter = (entity, step, purpose << 24 | sub),
+ * key = seed) evaluated on `device` for n entities: out6[6*i..] = two uniforms in [0,1) and four
+ * N(0,1) deviates (single-precision Box-Muller). Replaces OpenFOAM's Random (seeded at
+ * mcParticleCloud.C:332); lets the tests hold the device generator to the CPU restatement bit for bit. */
+int pdfb200_rng_probe(int device, uint64_t seed, int64_t n, const uint64_t *entity, uint32_t step,
+                      uint32_t purpose, uint32_t sub, double *out6);
 /* number of kernels of this library launched since the handle was created  */
 int64_t pdfb200_kernel_launches(pdfb200_cloud *cloud);
 /* accumulated device time (ms, CUDA events on the library's stream) of the regions

@@ -46,7 +46,7 @@ class OracleLibrary(Library):
         f("binterp").restype = C.c_double
         f("inlet_random").argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, c_double_p]
         f("inlet_random_sample").argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_int64, c_double_p]
-        f("rng_probe").argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
+        f("rng_probe").argtypes = [C.c_uint64, C.c_int64, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
         f("philox").argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         f("rotation_tensor").argtypes = [c_double_p, c_double_p, c_double_p]
 

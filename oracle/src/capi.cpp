@@ -297,13 +297,16 @@ int pdforacle_inlet_random_sample(double UMean, double uRms, uint64_t seed, int6
     return PDFB200_OK;
 }
 
-// RNG probes (keyed Philox): uniforms and normals for (entity, step, purpose, sub)
-int pdforacle_rng_probe(uint64_t seed, uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double *out4) {
+// RNG probe (keyed Philox): for each entity two uniforms and four normals of (entity, step, purpose, sub)
+int pdforacle_rng_probe(uint64_t seed, int64_t n, const uint64_t *entity, uint32_t step, uint32_t purpose, uint32_t sub, double *out6) {
     KeyedRng k; k.setSeed(seed);
-    k.uniform2(entity, step, purpose, sub, out4[0], out4[1]);
-    k.normal2(entity, step, purpose, sub, out4[2], out4[3]);
+    for (int64_t i = 0; i < n; ++i) {
+        k.uniform2(entity[i], step, purpose, sub, out6[6 * i], out6[6 * i + 1]);
+        k.normal4(entity[i], step, purpose, sub, out6 + 6 * i + 2);
+    }
     return PDFB200_OK;
 }
+int pdforacle_normal_pair(uint32_t a, uint32_t b, float *out2) { normalPairF32(a, b, out2[0], out2[1]); return PDFB200_OK; }
 int pdforacle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); return PDFB200_OK; }
 
 // rotationTensor probe

@@ -345,9 +345,8 @@ void Cloud::curlMixing() {
                 uint32_t h;
                 if (prm.rngMode == 1) h = (uint32_t)(srng.scalar01() * 4294967296.0);
                 else {
-                    const uint32_t ctr[4] = {particles[i].id, step, RNG_MIX_HASH, (uint32_t)r};
                     uint32_t o[4];
-                    philox4x32_10(ctr, krng.key, o);
+                    krng.words(particles[i].id, step, RNG_MIX_HASH, (uint32_t)r, o);
                     h = o[0];
                 }
                 ord.push_back({h, particles[i].id, i});
@@ -448,9 +447,8 @@ void Cloud::stepNormals(const Particle &p, double out[6], int phase) {
     if (prm.rngMode == 1) {
         for (int i = 3 * phase; i < 3 * phase + 3; ++i) out[i] = srng.GaussNormal();
     } else if (phase == 0) {
-        krng.normal2(p.id, step, RNG_STEP_NORMALS, 0, out[0], out[1]);
-        krng.normal2(p.id, step, RNG_STEP_NORMALS, 1, out[2], out[3]);
-        krng.normal2(p.id, step, RNG_STEP_NORMALS, 2, out[4], out[5]);
+        krng.normal4(p.id, step, RNG_STEP_NORMALS, 0, out);
+        krng.normal2(p.id, step, RNG_STEP_NORMALS, 1, out[4], out[5]);
     }
 }
 
@@ -948,7 +946,13 @@ void Cloud::evolveEnd(pdfb200_step_report *rep, const std::vector<double> &block
     // E13 (:1359)
     particleNumberControl();
     // E14 (:1363-1369)
-    for (int c = 0; c < mesh.nCells; ++c) lostMass[c] = lostMass[c] / std::max(PaNIC[c], 1.);
+    // lostMass_/max(PaNIC,1): with one rank PaNIC is the number of particles now in the cell; particle-sharded
+    // ranks each re-spread what they lost over the particles they hold (same number when nRanks == 1)
+    {
+        std::vector<double> nLocal(mesh.nCells, 0.0);
+        for (const Particle &p : particles) nLocal[p.cell] += 1.0;
+        for (int c = 0; c < mesh.nCells; ++c) lostMass[c] = lostMass[c] / std::max(nRanks > 1 ? nLocal[c] : PaNIC[c], 1.);
+    }
     for (Particle &p : particles) p.m += lostMass[p.cell];
     std::fill(lostMass.begin(), lostMass.end(), 0.0);
     nLostTotal += nLost;

@@ -2,6 +2,7 @@
 // conditions, cell->node interpolation tables and the updateInternals() part
 // of every sub-model.
 #include <algorithm>
+#include <cstring>
 #include <stdexcept>
 
 #include "pdforacle.hpp"
@@ -29,26 +30,83 @@ void philox4x32_10(const uint32_t ctrIn[4], const uint32_t keyIn[2], uint32_t ou
 
 static inline uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-void KeyedRng::uniform2(uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
-                        double &u0, double &u1) const {
-    const uint32_t ctr[4] = {entity, step, purpose, sub};
-    uint32_t o[4];
+// counter = (entity low word, entity high word, step, purpose << 24 | sub): 64-bit entities, sub < 2^24
+void KeyedRng::words(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, uint32_t o[4]) const {
+    const uint32_t ctr[4] = {(uint32_t)entity, (uint32_t)(entity >> 32), step, (purpose << 24) | sub};
     philox4x32_10(ctr, key, o);
+}
+
+void KeyedRng::uniform2(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
+                        double &u0, double &u1) const {
+    uint32_t o[4];
+    words(entity, step, purpose, sub, o);
     u0 = (double)(pack64(o[0], o[1]) >> 11) * 0x1.0p-53;
     u1 = (double)(pack64(o[2], o[3]) >> 11) * 0x1.0p-53;
 }
 
-void KeyedRng::normal2(uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
+// Two N(0,1) deviates from two 32-bit words: single-precision Box-Muller. The device evaluates the
+// same sequence of single-precision operations (explicit fused multiply-adds only; both sides are
+// compiled without contraction), so the deviates agree bit for bit. Radius from u = (a+1) 2^-32,
+// angle from b: two quadrant bits and a 30-bit position inside the quadrant; log, sin and cos by the
+// Cephes single-precision polynomials.
+static inline float bitsToFloat(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t floatToBits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+void normalPairF32(uint32_t a, uint32_t b, float &n0, float &n1) {
+    const float x = (float)a + 1.0f;
+    const int32_t xi = (int32_t)floatToBits(x);
+    int e = (xi >> 23) - 127;
+    float m = bitsToFloat(((uint32_t)xi & 0x007fffffu) | 0x3f800000u);
+    if (m > 1.41421354f) { m *= 0.5f; e += 1; }
+    const float f = m - 1.0f, z = f * f;
+    float p = 7.0376836292E-2f;
+    p = std::fmaf(p, f, -1.1514610310E-1f);
+    p = std::fmaf(p, f, 1.1676998740E-1f);
+    p = std::fmaf(p, f, -1.2420140846E-1f);
+    p = std::fmaf(p, f, 1.4249322787E-1f);
+    p = std::fmaf(p, f, -1.6668057665E-1f);
+    p = std::fmaf(p, f, 2.0000714765E-1f);
+    p = std::fmaf(p, f, -2.4999993993E-1f);
+    p = std::fmaf(p, f, 3.3333331174E-1f);
+    const float lnm = std::fmaf(f * z, p, std::fmaf(-0.5f, z, f));
+    const float L = std::fmaf((float)(32 - e), 0.693147182f, -lnm);
+    const float r = std::sqrt(2.0f * L);
+    const uint32_t q = b >> 30;
+    const float t = (float)(b & 0x3fffffffu) * 0x1p-30f;
+    const bool sw = t > 0.5f;
+    const float th = (sw ? 1.0f - t : t) * 1.57079637f;
+    const float z2 = th * th;
+    float sp = -1.9515295891E-4f;
+    sp = std::fmaf(sp, z2, 8.3321608736E-3f);
+    sp = std::fmaf(sp, z2, -1.6666654611E-1f);
+    const float s0 = std::fmaf(sp * z2, th, th);
+    float cp = 2.443315711809948E-5f;
+    cp = std::fmaf(cp, z2, -1.388731625493765E-3f);
+    cp = std::fmaf(cp, z2, 4.166664568298827E-2f);
+    const float c0 = std::fmaf(cp * z2, z2, std::fmaf(-0.5f, z2, 1.0f));
+    const float s1 = sw ? c0 : s0, c1 = sw ? s0 : c0;
+    const bool odd = (q & 1u) != 0;
+    float sn = odd ? c1 : s1, cs = odd ? s1 : c1;
+    if (q >= 2u) sn = -sn;
+    if (q == 1u || q == 2u) cs = -cs;
+    n0 = r * cs; n1 = r * sn;
+}
+
+void KeyedRng::normal2(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
                        double &n0, double &n1) const {
-    const uint32_t ctr[4] = {entity, step, purpose, sub};
     uint32_t o[4];
-    philox4x32_10(ctr, key, o);
-    const double u0 = (double)((pack64(o[0], o[1]) >> 11) + 1) * 0x1.0p-53;   // (0,1]
-    const double u1 = (double)(pack64(o[2], o[3]) >> 11) * 0x1.0p-53;         // [0,1)
-    const double r = std::sqrt(-2.0 * std::log(u0));
-    const double th = 2.0 * M_PI * u1;
-    n0 = r * std::cos(th);
-    n1 = r * std::sin(th);
+    words(entity, step, purpose, sub, o);
+    float a, b;
+    normalPairF32(o[0], o[1], a, b);
+    n0 = (double)a; n1 = (double)b;
+}
+
+void KeyedRng::normal4(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double n[4]) const {
+    uint32_t o[4];
+    words(entity, step, purpose, sub, o);
+    float a, b, c, d;
+    normalPairF32(o[0], o[1], a, b);
+    normalPairF32(o[2], o[3], c, d);
+    n[0] = (double)a; n[1] = (double)b; n[2] = (double)c; n[3] = (double)d;
 }
 
 double SeqRandom::scalar01() {

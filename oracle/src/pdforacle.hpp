@@ -181,9 +181,10 @@ private:
 
 // counter-based Philox4x32-10 (Salmon et al. 2011); identical on the device
 void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void normalPairF32(uint32_t a, uint32_t b, float &n0, float &n1);
 
 enum RngPurpose : uint32_t {
-    RNG_STEP_NORMALS = 1,   // entity = particle id; sub 0..2 -> 6 normals
+    RNG_STEP_NORMALS = 1,   // entity = particle id; sub 0 -> 4 normals, sub 1 -> 2 normals
     RNG_INLET_STEPFRAC = 2, // entity = particle id
     RNG_NC_PARTICLE = 3,    // entity = particle id (eliminate: selection draws)
     RNG_NC_CELL = 4,        // entity = cell (eliminate: which population dies)
@@ -200,12 +201,14 @@ struct KeyedRng {
         key[0] = (uint32_t)(seed & 0xffffffffu);
         key[1] = (uint32_t)(seed >> 32);
     }
+    void words(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, uint32_t o[4]) const;
     // two uniforms in [0,1) from one Philox call
-    void uniform2(uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
+    void uniform2(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
                   double &u0, double &u1) const;
-    // two N(0,1) deviates from one Philox call (Box-Muller)
-    void normal2(uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
+    // two / four N(0,1) deviates from one Philox call (single-precision Box-Muller, normalPairF32)
+    void normal2(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub,
                  double &n0, double &n1) const;
+    void normal4(uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double n[4]) const;
 };
 
 // Sequential generator with OpenFOAM Random's interface (B.3): scalar01 is a

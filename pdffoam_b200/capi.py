@@ -171,7 +171,7 @@ API_SYMBOLS = [
     "upload_cloud_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
-    "kernel_launches", "last_evolve_ms", "profile", "jit_source",
+    "kernel_launches", "last_evolve_ms", "profile", "jit_source", "rng_probe",
 ]
 
 
@@ -221,6 +221,8 @@ class Library:
             f("kernel_launches").argtypes = [vp]; f("kernel_launches").restype = C.c_int64
             f("last_evolve_ms").argtypes = [vp]; f("last_evolve_ms").restype = C.c_double
             f("profile").argtypes = [vp, c_double_p, C.c_int]
+        if self.has("rng_probe") and self.prefix == "pdfb200_":
+            f("rng_probe").argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
         if self.has("jit_source"):
             f("jit_source").argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_char_p, C.c_long]
             f("jit_source").restype = C.c_long

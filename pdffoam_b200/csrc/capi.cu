@@ -192,15 +192,25 @@ int pdfb200_download_tets(pdfb200_cloud *c, double *gradN, int32_t *nbr, int32_t
     USE_DEVICE(c);
     return guarded([&] {
         Cloud &C = c->c;
-        std::vector<TetRec> h((size_t)C.nTets);
-        CUDA_CHECK(cudaMemcpy(h.data(), C.tets.p, h.size() * sizeof(TetRec), cudaMemcpyDeviceToHost));
-        for (size_t t = 0; t < h.size(); ++t) {
-            if (gradN) for (int k = 0; k < 9; ++k) gradN[9 * t + k] = h[t].g[k];
-            if (nbr) for (int k = 0; k < 4; ++k) nbr[4 * t + k] = h[t].nbr[k];
-            if (faceLabel) faceLabel[t] = h[t].face;
-            if (ptB) ptB[t] = h[t].ptB;
-            if (ptC) ptC[t] = h[t].ptC;
-            if (cell) cell[t] = h[t].cell;
+        const size_t n = (size_t)C.nTets;
+        std::vector<TetA> hA(n);
+        std::vector<D4> hB(n), hC(n);
+        std::vector<int2> hP(n);
+        CUDA_CHECK(cudaMemcpy(hA.data(), C.tetA.p, n * sizeof(TetA), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(hB.data(), C.tetB.p, n * sizeof(D4), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(hC.data(), C.tetC.p, n * sizeof(D4), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(hP.data(), C.tetPts.p, n * sizeof(int2), cudaMemcpyDeviceToHost));
+        if (cell) CUDA_CHECK(cudaMemcpy(cell, C.tetCell.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < n; ++t) {
+            if (gradN) {
+                double *g = gradN + 9 * t;
+                g[0] = hA[t].g0; g[1] = hB[t].x; g[2] = hB[t].y; g[3] = hB[t].z; g[4] = hB[t].w;
+                g[5] = hC[t].x; g[6] = hC[t].y; g[7] = hC[t].z; g[8] = hC[t].w;
+            }
+            if (nbr) for (int k = 0; k < 4; ++k) nbr[4 * t + k] = hA[t].nbr[k];
+            if (faceLabel) faceLabel[t] = hA[t].face;
+            if (ptB) ptB[t] = hP[t].x;
+            if (ptC) ptC[t] = hP[t].y;
         }
     });
 }

@@ -39,7 +39,7 @@ struct HostPatch { int start, size, geom, handler, reflecting; };
 #ifndef K1_THREADS
 #define K1_THREADS 128
 #endif
-#define K1_JIT_MIN_BLOCKS 3   // CTAs per SM the run-time specialised kernel is compiled for
+#define K1_JIT_MIN_BLOCKS 5   // CTAs per SM the run-time specialised kernel is compiled for (96 registers; measured best of 3..6)
 #ifndef K1_MAXCONS
 #define K1_MAXCONS 3
 #endif
@@ -90,12 +90,15 @@ struct Cloud {
 
     // ---- device mesh ----
     DMesh dm{};
-    DBuf<double> points, faceCentres, faceAreas, magSf, cellVolumes, volumeOrArea, bbMin, bbMax, courantCoeffs, cellCo,
+    DBuf<double> points, faceCentres, faceAreas, magSf, cellVolumes, volumeOrArea, bbMin, bbMax, courantCoeffs,
         linWeights, pointWeights, patchFaceT;
     DBuf<double4> cellCentre4, bfNormal;
     DBuf<int> faceStart, facePoints, owner, neighbour, cellFaceStart, cellFaces, cellTetStart, faceTetStartOwn,
         faceTetStartNei, pointCellStart, pointCells, bfInfo, openCellStart, openCellFaces, cellRank, cellOfRank;
-    DBuf<TetRec> tets;
+    DBuf<TetA> tetA;
+    DBuf<D4> tetB, tetC, cellCo4;
+    DBuf<int2> tetPts;
+    DBuf<int> tetCell;
 
     // ---- fields ----
     // FV-owned
@@ -106,6 +109,9 @@ struct Cloud {
     DBuf<double> Phi_c, Phi_b, Cov_c, Cov_b;       // [nPhi][nCells] etc.
     DBuf<uint8_t> PhiFixed, CovFixed;              // [nPhi][nBnd]
     DBuf<double> PaNIC, lostMass, lostShare;
+    DBuf<LostRec> lostList, lostSorted;           // particles lost in the current step (k_lost_reduce)
+    DBuf<unsigned> lostCount;
+    bool lostDirty = false;                        // lostMass holds non-zero entries from the last step
     // time-averaged moments
     DBuf<double> mMom, VMom, UMom, UUMom, PhiMom, PhiPhiMom;
     DBuf<double> momentBlock;                      // [nCells*nMom + BLOCK_TAIL]

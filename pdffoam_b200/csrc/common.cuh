@@ -33,17 +33,42 @@
 #define RNG_MIX_HASH 8u   // entity = particle id; sub = round (modifiedCurl matching order)
 #define RNG_MIX_PAIR 9u   // entity = id of the pair's first particle; sub = round
 
-struct __align__(16) TetRec {
+// The tet table is three planes of 32-byte chunks indexed by the tet label (DMesh::tetA/B/C):
+//   A[t] = { nbr[4], face, nbrCell, g0 }   B[t] = { g1..g4 }   C[t] = { g5..g8 }
+// (g = gradN of vertices a (face centre), b, c, row-major; g_d = -(g_a+g_b+g_c)).
+// The particles of a warp sit in one or two cells (they are processed in sorted order) and the tets
+// of a cell are consecutive labels, so one 256-bit load of a plane touches the 6 lines that hold the
+// cell's 24 chunks instead of one line per lane: the L1 cost of a record gather is the number of
+// distinct 128-byte lines per load instruction, and it was what bounded the particle kernel in
+// round 1 (one 128-byte record per tet: 4 loads x up to 32 lines).
+// Point labels of b and c (only needed by the interpolations) live in DMesh::tetPts, the centre of
+// the cell (vertex d) in DMesh::cellCentre4.
+struct __align__(32) TetA {
     int nbr[4];       // tet across the face opposite a, b, c, d (-1: boundary)
     int face;         // mesh face the tet stands on (tetFace_)
-    int ptB, ptC;     // global point labels of b and c
-    int cell;
-    double g[9];      // gradN of vertices a (face centre), b, c; g_d = -(g_a+g_b+g_c)
-    double centre[3]; // centre of `cell` (vertex d): saves the dependent cell-centre load in the walk
+    int nbrCell;      // cell across that face (-1: boundary)
+    double g0;
 };
-static_assert(sizeof(TetRec) == 128, "TetRec must be one 128-byte line");
+static_assert(sizeof(TetA) == 32, "TetA must be one 32-byte sector");
+
+// 256-bit read-only global load (SASS: LDG.E.ENL2.256.CONSTANT, new on sm_100): one instruction per
+// 32-byte chunk. The address must be 32-byte aligned.
+struct __align__(32) D4 { double x, y, z, w; };
+__device__ __forceinline__ D4 ld256(const void *p) {
+    D4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
 
 #define NODE_MID_STRIDE 12   // doubles per mid-point node record
+// The mid-point node values are stored as NODE_MID_STRIDE/4 planes of 32-byte chunks per node
+// (cells, then points, then faces): value k of node n is at nmIdx(nNodes, n, k). Points with
+// neighbouring labels then share 128-byte lines in every plane.
+__host__ __device__ inline size_t nmIdx(size_t nNodes, size_t node, int k) { return ((size_t)(k >> 2) * nNodes + node) * 4 + (size_t)(k & 3); }
+struct NodeRef {   // nm[k] access to one node of the planes
+    double *base; size_t nNodes, node;
+    __host__ __device__ double &operator[](int k) const { return base[nmIdx(nNodes, node, k)]; }
+};
 // offsets inside a mid-point node record
 #define NM_U 0
 #define NM_K 3
@@ -52,6 +77,10 @@ static_assert(sizeof(TetRec) == 128, "TetRec must be one 128-byte line");
 #define NM_PSTAR 8
 #define NM_ETA 9
 #define NM_ZVAR 10
+
+// one entry of the list of particles lost in a step (k_lost_reduce sums them per cell in a
+// fixed order: no floating-point atomics)
+struct __align__(16) LostRec { uint32_t idx; int cell; double m; };
 
 // particle state columns (SoA)
 struct PState {
@@ -100,10 +129,13 @@ struct DMesh {
     const double *cellVolumes, *volumeOrArea;
     const double *bbMin, *bbMax; // [nCells*3]
     const double *courantCoeffs; // [nFaces*3], zero on empty patches
-    const double *cellCo;        // [cellFaceStart[nCells]*3] coefficients in cell-face order
+    const D4 *cellCo4;           // [cellFaceStart[nCells]] coefficients in cell-face order (xyz, w = 0)
     const double *linWeights;    // [nInternalFaces]
     const int *pointCellStart, *pointCells; const double *pointWeights;
-    const TetRec *tets;
+    const TetA *tetA;            // tet table, three planes of 32-byte chunks (see TetA)
+    const D4 *tetB, *tetC;
+    const int2 *tetPts;          // global point labels of b and c
+    const int *tetCell;          // cell of each tet (the particle kernel tracks it instead)
     // boundary faces
     const int *bfInfo;           // handler | reflecting<<4 | geom<<8 | patch<<16
     const double4 *bfNormal;     // unit normal xyz (w unused)
@@ -134,16 +166,6 @@ __device__ inline V3 ld3(const double *p, long long i) { return mk(p[3 * i], p[3
 __device__ inline void st3(double *p, long long i, V3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
 // fused dot product of the tet walk: the same fma chain as oracle dotf()
 __device__ inline double dotf(double gx, double gy, double gz, V3 r) { return fma(gx, r.x, fma(gy, r.y, gz * r.z)); }
-
-// 256-bit read-only global load (SASS: LDG.E.ENL2.256.CONSTANT, new on sm_100). One
-// instruction per 32-byte chunk instead of two: half the L1 wavefronts for the
-// record gathers of the particle kernel. The address must be 32-byte aligned.
-struct __align__(32) D4 { double x, y, z, w; };
-__device__ __forceinline__ D4 ld256(const void *p) {
-    D4 r;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
 
 // rotationTensor(n1,n2) (OpenFOAM transform.H), row-major
 __host__ __device__ inline void rotationTensor(V3 n1, V3 n2, double T[9]) {
@@ -178,21 +200,78 @@ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 struct RngKey { uint32_t k0, k1; };
-__device__ inline void rngUniform2(RngKey key, uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double &u0, double &u1) {
+// counter = (entity low word, entity high word, step, purpose << 24 | sub): entities are 64-bit
+// (particle ids), sub < 2^24
+__device__ inline void rngWords(RngKey key, uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, uint32_t o[4]) {
+    philox4x32_10((uint32_t)entity, (uint32_t)(entity >> 32), step, (purpose << 24) | sub, key.k0, key.k1, o);
+}
+__device__ inline void rngUniform2(RngKey key, uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double &u0, double &u1) {
     uint32_t o[4];
-    philox4x32_10(entity, step, purpose, sub, key.k0, key.k1, o);
+    rngWords(key, entity, step, purpose, sub, o);
     u0 = (double)((((unsigned long long)o[1] << 32) | o[0]) >> 11) * 0x1.0p-53;
     u1 = (double)((((unsigned long long)o[3] << 32) | o[2]) >> 11) * 0x1.0p-53;
 }
-__device__ inline void rngNormal2(RngKey key, uint32_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double &n0, double &n1) {
+
+// Two N(0,1) deviates from two 32-bit words: Box-Muller evaluated in single precision with explicit
+// fused multiply-adds only (polynomials of the Cephes logf / sinf / cosf), so that the CPU oracle
+// reproduces every bit with fmaf() and the double-precision pipe stays free for the physics: the
+// six normals of a particle step were 15 % of the particle kernel when drawn with the
+// double-precision log / sincospi. Radius from u = (a+1) 2^-32 in (0,1] (tail up to 6.66 sigma),
+// angle from b: two quadrant bits and a 30-bit position inside the quadrant.
+__device__ inline void normalPairF32(uint32_t a, uint32_t b, float &n0, float &n1) {
+    const float x = (float)a + 1.0f;   // [1, 2^32]
+    const int xi = __float_as_int(x);
+    int e = (xi >> 23) - 127;
+    float m = __int_as_float((xi & 0x007fffff) | 0x3f800000);   // [1, 2)
+    if (m > 1.41421354f) { m *= 0.5f; e += 1; }
+    const float f = m - 1.0f, z = f * f;
+    float p = 7.0376836292E-2f;
+    p = fmaf(p, f, -1.1514610310E-1f);
+    p = fmaf(p, f, 1.1676998740E-1f);
+    p = fmaf(p, f, -1.2420140846E-1f);
+    p = fmaf(p, f, 1.4249322787E-1f);
+    p = fmaf(p, f, -1.6668057665E-1f);
+    p = fmaf(p, f, 2.0000714765E-1f);
+    p = fmaf(p, f, -2.4999993993E-1f);
+    p = fmaf(p, f, 3.3333331174E-1f);
+    const float lnm = fmaf(f * z, p, fmaf(-0.5f, z, f));            // ln(m)
+    const float L = fmaf((float)(32 - e), 0.693147182f, -lnm);      // -ln(u) >= 0
+    const float r = __fsqrt_rn(2.0f * L);
+    const uint32_t q = b >> 30;
+    const float t = (float)(b & 0x3fffffffu) * 0x1p-30f;            // [0, 1]
+    const bool sw = t > 0.5f;
+    const float th = (sw ? 1.0f - t : t) * 1.57079637f;             // [0, pi/4]
+    const float z2 = th * th;
+    float sp = -1.9515295891E-4f;
+    sp = fmaf(sp, z2, 8.3321608736E-3f);
+    sp = fmaf(sp, z2, -1.6666654611E-1f);
+    const float s0 = fmaf(sp * z2, th, th);
+    float cp = 2.443315711809948E-5f;
+    cp = fmaf(cp, z2, -1.388731625493765E-3f);
+    cp = fmaf(cp, z2, 4.166664568298827E-2f);
+    const float c0 = fmaf(cp * z2, z2, fmaf(-0.5f, z2, 1.0f));
+    const float s1 = sw ? c0 : s0, c1 = sw ? s0 : c0;               // angle inside the quadrant
+    const bool odd = (q & 1u) != 0;
+    float sn = odd ? c1 : s1, cs = odd ? s1 : c1;                   // + q * pi/2
+    if (q >= 2u) sn = -sn;
+    if (q == 1u || q == 2u) cs = -cs;
+    n0 = r * cs; n1 = r * sn;
+}
+__device__ inline void rngNormal2(RngKey key, uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double &n0, double &n1) {
     uint32_t o[4];
-    philox4x32_10(entity, step, purpose, sub, key.k0, key.k1, o);
-    const double u0 = (double)(((((unsigned long long)o[1] << 32) | o[0]) >> 11) + 1ull) * 0x1.0p-53;
-    const double u1 = (double)((((unsigned long long)o[3] << 32) | o[2]) >> 11) * 0x1.0p-53;
-    const double r = sqrt(-2.0 * log(u0));
-    double s, c;
-    sincospi(2.0 * u1, &s, &c);
-    n0 = r * c; n1 = r * s;
+    rngWords(key, entity, step, purpose, sub, o);
+    float a, b;
+    normalPairF32(o[0], o[1], a, b);
+    n0 = (double)a; n1 = (double)b;
+}
+__device__ inline void rngNormal4(RngKey key, uint64_t entity, uint32_t step, uint32_t purpose, uint32_t sub, double &n0, double &n1,
+                                  double &n2, double &n3) {
+    uint32_t o[4];
+    rngWords(key, entity, step, purpose, sub, o);
+    float a, b, c, d;
+    normalPairF32(o[0], o[1], a, b);
+    normalPairF32(o[2], o[3], c, d);
+    n0 = (double)a; n1 = (double)b; n2 = (double)c; n3 = (double)d;
 }
 
 // ---------------------------------------------------------------------------

@@ -59,7 +59,9 @@ struct K1Args {
     int auxStride;
     const double *Un;
     const double *lostShare;
-    double *lostMass;
+    LostRec *lostList;     // particles lost in this step (k_lost_reduce)
+    unsigned *lostCount;
+    unsigned lostCap;
     const int *injPatchTail;
     const double *flChi, *flZ, *flFields;
     int nChi, nZ;
@@ -72,65 +74,27 @@ struct K1Args {
 // or the compiler would move it to local memory)
 struct TetL {
     int n0, n1, n2, n3;          // neighbours across the faces opposite a, b, c, d
-    int face, ptB, ptC, cell;
+    int face, nbrCell;           // mesh face of the tet, cell across it
     double g0, g1, g2, g3, g4, g5, g6, g7, g8;   // gradN of a, b, c
-    double cx, cy, cz;           // centre of the cell (vertex d)
 };
 
-// OPTIONAL (-DK1_STAGE, off by default: measured no gain on B200, see profiles/README.md).
-// Per-warp staging of tet records in shared memory ("cell geometry staged in
-// shared memory"): at the start of an iteration each warp copies the records
-// of the cells its 32 particles start in (coalesced 128-bit loads) into its own
-// shared-memory window; the walk then reads a record from the window when the
-// tet is inside it and from global memory otherwise, through one generic load
-// path (no divergence). Records sit at a 144-byte stride to spread the banks.
-#define STAGE_RECORDS 32
-#define STAGE_STRIDE_B 144
-struct TetStage {
-    const char *base;   // this warp's window (generic address of shared memory)
-    int lo, n;          // first staged tet, number of staged records
-};
-
-__device__ __forceinline__ void loadTet(const TetRec *tets, const TetStage &S, int t, TetL &T) {
-#ifndef K1_STAGE
-    const char *rec = reinterpret_cast<const char *>(tets + t);
-#else
-    const unsigned off = (unsigned)(t - S.lo);
-    const char *rec = (off < (unsigned)S.n) ? S.base + (size_t)off * STAGE_STRIDE_B : reinterpret_cast<const char *>(tets + t);
-#endif
-#ifndef K1_STAGE
-    // four 256-bit loads (LDG.E.256, sm_100): half the L1 wavefronts of 128-bit loads for a
-    // record gather in which most lanes touch different 128-byte lines
-    const D4 r0 = ld256(rec), r1 = ld256(rec + 32), r2 = ld256(rec + 64), r3 = ld256(rec + 96);
+// three 256-bit loads, one per plane of the tet table (see TetA in common.cuh)
+__device__ __forceinline__ void loadTet(const DMesh &M, int t, TetL &T) {
+    const D4 r0 = ld256(M.tetA + t), r1 = ld256(M.tetB + t), r2 = ld256(M.tetC + t);
     T.n0 = __double2loint(r0.x); T.n1 = __double2hiint(r0.x); T.n2 = __double2loint(r0.y); T.n3 = __double2hiint(r0.y);
-    T.face = __double2loint(r0.z); T.ptB = __double2hiint(r0.z); T.ptC = __double2loint(r0.w); T.cell = __double2hiint(r0.w);
-    T.g0 = r1.x; T.g1 = r1.y; T.g2 = r1.z; T.g3 = r1.w; T.g4 = r2.x; T.g5 = r2.y; T.g6 = r2.z; T.g7 = r2.w;
-    T.g8 = r3.x; T.cx = r3.y; T.cy = r3.z; T.cz = r3.w;
-    return;
-#else
-    const int4 *pi = reinterpret_cast<const int4 *>(rec);
-    const double2 *pd = reinterpret_cast<const double2 *>(rec) + 2;
-    const int4 a = pi[0], b = pi[1];
-    const double2 g0 = pd[0], g1 = pd[1], g2 = pd[2], g3 = pd[3], g4 = pd[4], g5 = pd[5];
-    T.n0 = a.x; T.n1 = a.y; T.n2 = a.z; T.n3 = a.w;
-    T.face = b.x; T.ptB = b.y; T.ptC = b.z; T.cell = b.w;
-    T.g0 = g0.x; T.g1 = g0.y; T.g2 = g1.x; T.g3 = g1.y; T.g4 = g2.x; T.g5 = g2.y;
-    T.g6 = g3.x; T.g7 = g3.y; T.g8 = g4.x;
-    T.cx = g4.y; T.cy = g5.x; T.cz = g5.y;
-#endif
-}
-// plain global path (kernels without staging)
-__device__ __forceinline__ void loadTet(const TetRec *tets, int t, TetL &T) {
-    TetStage S;
-    S.base = nullptr; S.lo = 0; S.n = 0;
-    loadTet(tets, S, t, T);
+    T.face = __double2loint(r0.z); T.nbrCell = __double2hiint(r0.z);
+    T.g0 = r0.w; T.g1 = r1.x; T.g2 = r1.y; T.g3 = r1.z; T.g4 = r1.w; T.g5 = r2.x; T.g6 = r2.y; T.g7 = r2.z; T.g8 = r2.w;
 }
 
+// centre of a cell (vertex d of its tets) and its numerical-diffusion length: one 256-bit load
+__device__ __forceinline__ V3 cellCentreH(const DMesh &M, int c, double &hNum) {
+    const D4 a = ld256(M.cellCentre4 + c);
+    hNum = a.w;
+    return mk(a.x, a.y, a.z);
+}
 __device__ __forceinline__ V3 cellCentre(const DMesh &M, int c) {
-    const double2 *p = reinterpret_cast<const double2 *>(M.cellCentre4 + c);
-    const double2 a = __ldg(p);
-    const double z = __ldg(reinterpret_cast<const double *>(p + 1));
-    return mk(a.x, a.y, z);
+    double h;
+    return cellCentreH(M, c, h);
 }
 
 __device__ __forceinline__ void baryAt(const TetL &T, V3 r, double &w0, double &w1, double &w2, double &w3) {
@@ -256,23 +220,21 @@ __device__ __forceinline__ void reactionCorrect(const KParams &P, const Flamelet
 // records of the tet (points b and c, face centre, cell centre) blended with
 // the clamped barycentric weights (order a, b, c, d); pst receives the four p*
 // node values for gradInterpolationConstantTet (order a, b, c, d).
-__device__ __forceinline__ void interpMid(const DMesh &M, const KParams &P, const double *nodeMid, const TetL &T,
+__device__ __forceinline__ void interpMid(const DMesh &M, const KParams &P, const double *nodeMid, int face, int ptB, int ptC, int cell,
                                           double w0, double w1, double w2, double w3, double (&val)[NODE_MID_STRIDE],
                                           double (&pst)[4]) {
-    const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
-    const double *nb = nodeMid + (nodeP + T.ptB) * NODE_MID_STRIDE;
-    const double *nc = nodeMid + (nodeP + T.ptC) * NODE_MID_STRIDE;
-    const double *na = nodeMid + (nodeF + T.face) * NODE_MID_STRIDE;
-    const double *nd = nodeMid + (size_t)T.cell * NODE_MID_STRIDE;
+    const size_t nNodes = (size_t)M.nCells + M.nPoints + M.nFaces;
+    const size_t ib = (size_t)M.nCells + ptB, ic = (size_t)M.nCells + ptC, ia = (size_t)M.nCells + M.nPoints + face, id = (size_t)cell;
     const double fb = clamp01(w1), fc = clamp01(w2), fa = clamp01(w0), fd = clamp01(w3);
     const bool anyCell = (P.interpU == PDFB200_INTERP_CELL) | (P.interpk == PDFB200_INTERP_CELL) |
                          (P.interpDiffU == PDFB200_INTERP_CELL) | (P.interpOmega == PDFB200_INTERP_CELL) |
                          (P.interpEta == PDFB200_INTERP_CELL) | (P.interpZVar == PDFB200_INTERP_CELL);
     double cv[NODE_MID_STRIDE];
-    // 96-byte node records: three 256-bit loads per node
+    // one 256-bit load per node and plane
 #pragma unroll
     for (int k = 0; k < NODE_MID_STRIDE / 4; ++k) {
-        const D4 vb = ld256(nb + 4 * k), vc = ld256(nc + 4 * k), va = ld256(na + 4 * k), vd = ld256(nd + 4 * k);
+        const double *pl = nodeMid + (size_t)k * nNodes * 4;
+        const D4 vb = ld256(pl + ib * 4), vc = ld256(pl + ic * 4), va = ld256(pl + ia * 4), vd = ld256(pl + id * 4);
         val[4 * k] = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
         val[4 * k + 1] = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
         val[4 * k + 2] = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
@@ -298,8 +260,9 @@ __device__ inline int locateTet(const DMesh &M, V3 pos, int cell) {
     double bestMin = -PDF_VGREAT;
     const int ts = M.cellTetStart[cell], te = M.cellTetStart[cell + 1];
     for (int t = ts; t < te; ++t) {
-        const double *g = M.tets[t].g;
-        const double pa = dotf(g[0], g[1], g[2], r), pb = dotf(g[3], g[4], g[5], r), pc = dotf(g[6], g[7], g[8], r);
+        TetL T;
+        loadTet(M, t, T);
+        const double pa = dotf(T.g0, T.g1, T.g2, r), pb = dotf(T.g3, T.g4, T.g5, r), pc = dotf(T.g6, T.g7, T.g8, r);
         const double pd = 1.0 - ((pa + pb) + pc);
         const double mn = fmin(fmin(pa, pb), fmin(pc, pd));
         if (mn > bestMin) { bestMin = mn; best = t; }
@@ -321,7 +284,7 @@ __device__ inline bool pointInCell(const DMesh &M, V3 pt, int cell) {
 }
 
 // mcParticleCloud::randomPointsInCell (mcParticleCloud.C:2040-2085), one point
-__device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uint32_t entity, uint32_t purpose, uint32_t stepCtr) {
+__device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uint64_t entity, uint32_t purpose, uint32_t stepCtr) {
     const V3 minb = ld3(M.bbMin, cell);
     const V3 dimb = ld3(M.bbMax, cell) - minb;
     V3 position = minb;
@@ -339,23 +302,40 @@ __device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uin
     return position;
 }
 
-// computeCourantNo (mcParticleCloud.C:2120-2148)
+// computeCourantNo (mcParticleCloud.C:2120-2148); one 256-bit load per face of the cell
 __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack) {
     double Co = 0.;
     const int js = __ldg(M.cellFaceStart + cell), je = __ldg(M.cellFaceStart + cell + 1);
-    for (int j = js; j < je; ++j) Co = fmax(Co, fabs(dot3(ld3(M.cellCo, j), Utrack)));
+    for (int j = js; j < je; ++j) {
+        const D4 c4 = ld256(M.cellCo4 + j);
+        Co = fmax(Co, fabs(dot3(mk(c4.x, c4.y, c4.z), Utrack)));
+    }
     return Co;
 }
 
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 4
 #endif
-// dynamic shared memory: thread-private accumulators + one staging window per warp
-#ifdef K1_STAGE
-#define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double) + (K1_THREADS / 32) * STAGE_RECORDS * STAGE_STRIDE_B)
-#else
-#define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX) * K1_THREADS * sizeof(double))
-#endif
+// dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
+// (the correction velocity, which must survive both tet walks without occupying registers)
+#define K1_NPARK 3
+#define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX + K1_NPARK) * K1_THREADS * sizeof(double))
+
+// Loads of this thread's own state columns that the compiler must not merge with an earlier load
+// of the same address: the kernel deliberately drops cold values (m, Omega, rho, phi, id, the old
+// position and velocity) during the tet walks and reads them again where they are used — the
+// lines are still in L1/L2 — so that the walks run with half the live registers of round 1 and
+// more warps are resident to cover their dependent loads.
+__device__ __forceinline__ double reloadD(const double *p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int reloadI(const int *p) {
+    int v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // NPHI = compile-time bound on the particle scalars held in registers (nPhi <= NPHI)
 template <int NPHI>
@@ -363,6 +343,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     extern __shared__ double smem[];
     double *accS = smem + threadIdx.x;                         // sums: accS[k*K1_THREADS]
     double *accM = smem + ACC_NSUM * K1_THREADS + threadIdx.x;  // maxima
+    double *park = smem + (ACC_NSUM + ACC_NMAX) * K1_THREADS + threadIdx.x;   // park[k*K1_THREADS]: Ucorr
 #pragma unroll
     for (int k = 0; k < ACC_NSUM; ++k) accS[k * K1_THREADS] = 0.0;
 #pragma unroll
@@ -383,137 +364,123 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     const int nPhi = P.nPhi;
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
 
-    const int lane = threadIdx.x & 31;
-    char *const stageWin = reinterpret_cast<char *>(smem + (ACC_NSUM + ACC_NMAX) * K1_THREADS) +
-                           (size_t)(threadIdx.x >> 5) * STAGE_RECORDS * STAGE_STRIDE_B;
-
     for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
-        const bool active = i < total;
-        const int slot = !active ? 0 : (i < nSorted) ? (int)A.perm[i] : nSlotsIn + (i - nSorted);
-        int cell = active ? A.in.cell[slot] : -1;
-
-        // ---- stage the tet records of the warp's start cells in shared memory ----
-        TetStage stage;
-#ifndef K1_STAGE
-        stage.base = nullptr; stage.lo = 0; stage.n = 0;
-#else
-        {
-            const int myLo = (cell >= 0) ? __ldg(M.cellTetStart + cell) : 0x7fffffff;
-            const int lo = __reduce_min_sync(0xffffffffu, myLo);
-            const long long room = M.nTets - lo;
-            const int n = (lo == 0x7fffffff) ? 0 : (int)(room < STAGE_RECORDS ? room : STAGE_RECORDS);
-            __syncwarp();   // every lane has finished reading the previous window
-            const int4 *src = reinterpret_cast<const int4 *>(M.tets + lo);
-            for (int j = lane; j < n * 8; j += 32)
-                *reinterpret_cast<int4 *>(stageWin + (j >> 3) * STAGE_STRIDE_B + (j & 7) * 16) = __ldg(src + j);
-            __syncwarp();
-            stage.base = stageWin; stage.lo = lo; stage.n = n;
-        }
-#endif
-        if (!active) continue;
-        if (cell < 0) { A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
+        if (i >= total) continue;
+        const int slot = (i < nSorted) ? (int)A.perm[i] : nSlotsIn + (i - nSorted);
+        const int cell0 = A.in.cell[slot];
+        if (cell0 < 0) { A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
         V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
-        V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
-        double m = A.in.m[slot], Omega = A.in.omega[slot], rho = A.in.rho[slot], eta = A.in.eta[slot];
-        double phi[NPHI];
-#pragma unroll
-        for (int k = 0; k < NPHI; ++k) phi[k] = (k < nPhi) ? A.in.phi[k][slot] : 0.0;
         int tet = A.in.tet[slot];
-        const uint32_t id = A.in.id[slot];
-        if (anyLost) m += A.lostShare[cell];
-        // numerical-diffusion length of the start cell (used at E9, after the particle is put back): loaded here
-        // so that its latency is hidden behind the half step
-        const double hNumStart = __ldg(reinterpret_cast<const double *>(M.cellCentre4 + cell) + 3);
         const bool injected = (i >= nSorted + nInjStart);
-        const int injPatch = injected ? A.injPatchTail[i - nSorted] : -1;
 
+        // the particle's mass at the start of the step: the stored one plus its share of the mass lost in the
+        // previous step (mcParticleCloud.C:1363-1369; particles injected since then get none)
+        auto massIn = [&]() {
+            double mm = reloadD(A.in.m + slot);
+            if (anyLost && !injected) mm += A.lostShare[cell0];
+            return mm;
+        };
         int status = 0;   // 0 alive, 1 deleted at an open boundary, 2 lost
-        // ---- E1: mcOpenBoundary::correct(false), cull behind the moving outflow plane ----
-        if (hasOpen) {
-            const int ks = __ldg(M.openCellStart + cell), ke = __ldg(M.openCellStart + cell + 1);
-            for (int k = ks; k < ke && status == 0; ++k) {
-                const int bf = M.openCellFaces[k];
-                const int info = M.bfInfo[bf];
-                if (BF_PATCH(info) <= injPatch || !BF_REFLECTING(info)) continue;
-                const double Un = A.Un[bf];
-                if (!(Un < 0.)) {
-                    const double4 n4 = M.bfNormal[bf];
-                    const V3 Cf = ld3(M.faceCentres, M.nInternalFaces + bf);
-                    const double xp = dot3(mk(n4.x, n4.y, n4.z), Cf - pos);
-                    if (xp < eta * (Un * deltaT)) {
-                        const double mpd = massPerDepth(M, pos, m);
-                        accS[ACC_MASS_OUT * K1_THREADS] -= mpd;
-                        for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
-                        status = 1;
+        // ---- E1 + E2 need the mass and the conserved scalars; both are read again at the mid-point ----
+        {
+            const double m = massIn();
+            // ---- E1: mcOpenBoundary::correct(false), cull behind the moving outflow plane ----
+            if (hasOpen) {
+                const int injPatch = injected ? A.injPatchTail[i - nSorted] : -1;
+                const int ks = __ldg(M.openCellStart + cell0), ke = __ldg(M.openCellStart + cell0 + 1);
+                for (int k = ks; k < ke && status == 0; ++k) {
+                    const int bf = M.openCellFaces[k];
+                    const int info = M.bfInfo[bf];
+                    if (BF_PATCH(info) <= injPatch || !BF_REFLECTING(info)) continue;
+                    const double Un = A.Un[bf];
+                    if (!(Un < 0.)) {
+                        const double4 n4 = M.bfNormal[bf];
+                        const V3 Cf = ld3(M.faceCentres, M.nInternalFaces + bf);
+                        const double xp = dot3(mk(n4.x, n4.y, n4.z), Cf - pos);
+                        if (xp < A.in.eta[slot] * (Un * deltaT)) {
+                            const double mpd = massPerDepth(M, pos, m);
+                            accS[ACC_MASS_OUT * K1_THREADS] -= mpd;
+                            for (int cs = 0; cs < P.nConserved; ++cs)
+                                accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * A.in.phi[PRM_AT(P, conserved, cs)][slot];
+                            status = 1;
+                        }
                     }
                 }
             }
-        }
-        if (status != 0) { accS[ACC_N_DELETED * K1_THREADS] += 1; A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
-
-        // ---- E2 ----
-        {
+            if (status != 0) { accS[ACC_N_DELETED * K1_THREADS] += 1; A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
+            // ---- E2 ----
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_MINUS * K1_THREADS] -= mpd;
-            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
+            for (int cs = 0; cs < P.nConserved; ++cs)
+                accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * A.in.phi[PRM_AT(P, conserved, cs)][slot];
         }
-        // ---- E3: position correction gather ----
+        // the walk state: tet record, the cell the tet belongs to and its centre (vertex d)
         TetL T;
-        loadTet(M.tets, stage, tet, T);
-        V3 Ucorr = mk(0, 0, 0);
-        if (P.positionCorrection != PDFB200_POSCORR_NONE) {
-            if (P.interpUPosCorr == PDFB200_INTERP_CELL) {
-                const double *q = A.nodePC + (size_t)T.cell * 4;
-                Ucorr = mk(q[0], q[1], q[2]);
-            } else {
-                double a0, a1, a2, a3;
-                baryAt(T, pos - mk(T.cx, T.cy, T.cz), a0, a1, a2, a3);
-                const double fb = clamp01(a1), fc = clamp01(a2), fa = clamp01(a0), fd = clamp01(a3);
-                // 32-byte node records: one 256-bit load per node
-                const D4 vb = ld256(A.nodePC + (nodeP + T.ptB) * 4), vc = ld256(A.nodePC + (nodeP + T.ptC) * 4);
-                const D4 va = ld256(A.nodePC + (nodeF + T.face) * 4), vd = ld256(A.nodePC + (size_t)T.cell * 4);
-                Ucorr.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
-                Ucorr.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
-                Ucorr.z = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
+        loadTet(M, tet, T);
+        int cell = cell0;
+        V3 ctr = cellCentre(M, cell0);
+        // ---- E3: position correction gather ----
+        V3 Utrack;
+        {
+            V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
+            V3 Ucorr = mk(0, 0, 0);
+            if (P.positionCorrection != PDFB200_POSCORR_NONE) {
+                if (P.interpUPosCorr == PDFB200_INTERP_CELL) {
+                    const D4 q = ld256(A.nodePC + (size_t)cell0 * 4);
+                    Ucorr = mk(q.x, q.y, q.z);
+                } else {
+                    double a0, a1, a2, a3;
+                    baryAt(T, pos - ctr, a0, a1, a2, a3);
+                    const double fb = clamp01(a1), fc = clamp01(a2), fa = clamp01(a0), fd = clamp01(a3);
+                    const int2 pts = __ldg(M.tetPts + tet);
+                    // 32-byte node records: one 256-bit load per node
+                    const D4 vb = ld256(A.nodePC + (nodeP + pts.x) * 4), vc = ld256(A.nodePC + (nodeP + pts.y) * 4);
+                    const D4 va = ld256(A.nodePC + (nodeF + T.face) * 4), vd = ld256(A.nodePC + (size_t)cell0 * 4);
+                    Ucorr.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
+                    Ucorr.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
+                    Ucorr.z = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
+                }
             }
+            // ---- E4 ----
+            Utrack = U + Ucorr;
+            constrainParticle(M, deltaT / 2, pos, U, Ucorr, Utrack);
+            park[0] = Ucorr.x; park[K1_THREADS] = Ucorr.y; park[2 * K1_THREADS] = Ucorr.z;
+            // the velocity after E4 ("Uold") equals the stored one except on axisymmetric meshes, where
+            // constrainParticle has rotated it: parked in this particle's (still unwritten) output slot
+            if (MESH_AXISYM(M)) { A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z; }
         }
-        // ---- E4 ----
-        V3 Utrack = U + Ucorr;
-        constrainParticle(M, deltaT / 2, pos, U, Ucorr, Utrack);
         bool reflected = false;
         int reflBf = -1;   // boundary face of the last open-boundary reflection (mcOpenBoundary.C:201-204)
-        const V3 Uold = U, posOld = pos;
-        const int tetOld = tet;
         double w0 = 0, w1 = 0, w2 = 0, w3 = 0, CoKeep = 0;
 
         // ---- E5 (phase 0: eta*deltaT/2) and E10 (phase 1: eta*deltaT): mcParticle::move on the
         //      tet walk (see oracle/src/cloud.cpp Cloud::move; identical expressions) ----
 #pragma unroll 1
-#ifdef K1_EXP_ONEPHASE   // timing experiment only: skips the full-step walk
-        for (int phase = 0; phase < 1; ++phase) {
-#else
         for (int phase = 0; phase < 2; ++phase) {
-#endif
-            double stepFraction = 0.0;
-            if (phase == 0 && injected) { double u0, u1; rngUniform2(A.key, id, step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
-            const double trackTime = (phase == 0) ? eta * (deltaT / 2.) : eta * deltaT;
-            double tEnd = (1.0 - stepFraction) * trackTime;
-#ifdef K1_EXP_NOWALK   // timing experiment only
-            tEnd = 0;
-#endif
+            double tEnd;
+            {
+                double stepFraction = 0.0;
+                if (phase == 0 && injected) { double u0, u1; rngUniform2(A.key, A.in.id[slot], step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
+                // phase 0 tracks with the old local time step, phase 1 with the new one (written to out.eta at the mid-point)
+                const double eta = (phase == 0) ? reloadD(A.in.eta + slot) : reloadD(A.out.eta + i);
+                const double trackTime = (phase == 0) ? eta * (deltaT / 2.) : eta * deltaT;
+                tEnd = (1.0 - stepFraction) * trackTime;
+            }
             const double dtMax = tEnd;
             int entry = -1, nSteps = 0;
             bool haveW = false;
             while (tEnd > 0 && status == 0) {
                 double dt = fmin(dtMax, tEnd);
-                V3 dest = pos + dt * Utrack;
-                constrainDir(MESH_GEOD3(M), dest);
-                const V3 x0 = pos;
-                const V3 dx = dest - x0;
+                V3 dx;
+                {
+                    V3 dest = pos + dt * Utrack;
+                    constrainDir(MESH_GEOD3(M), dest);
+                    dx = dest - pos;
+                }
                 double tf = 1.0;
                 for (;;) {
-                    const V3 r = x0 - mk(T.cx, T.cy, T.cz);
+                    const V3 r = pos - ctr;
                     double p0, p1, p2, p3;
                     baryAt(T, r, p0, p1, p2, p3);
                     const double q0 = dotf(T.g0, T.g1, T.g2, dx), q1 = dotf(T.g3, T.g4, T.g5, dx), q2 = dotf(T.g6, T.g7, T.g8, dx);
@@ -533,6 +500,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     const bool t3 = c3 & ((best < 0) | (p3 * qb > pb * q3));
                     best = t3 ? 3 : best;
                     if (best < 0) {
+                        // the destination is recomputed (same expression, same bits) instead of kept in registers
+                        V3 dest = pos + dt * Utrack;
+                        constrainDir(MESH_GEOD3(M), dest);
                         pos = dest;
                         w0 = p0 + q0; w1 = p1 + q1; w2 = p2 + q2; w3 = p3 + q3;
                         haveW = true;
@@ -545,14 +515,17 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         int nb = (best == 0) ? T.n0 : T.n1;
                         nb = (best == 2) ? T.n2 : nb;
                         tet = (best == 3) ? T.n3 : nb;
-                        loadTet(M.tets, stage, tet, T);
+                        // across the mesh face: the cell changes, and with it the centre the tets hang on
+                        // (requested together with the next record, not after it)
+                        if (best == 3) { cell = T.nbrCell; ctr = cellCentre(M, cell); }
+                        loadTet(M, tet, T);
                         entry = best ^ (((best == 1) | (best == 2)) ? 3 : 0);   // the shared face is opposite c (b) in the tet across b (c)
                         continue;
                     }
                     // boundary face
                     double s = p3 / (-q3);
                     s = fmin(1.0, fmax(0.0, s));
-                    pos = x0 + s * dx;
+                    pos = pos + s * dx;
                     tf = s;
                     const int bf = T.face - M.nInternalFaces;
                     const int info = __ldg(M.bfInfo + bf);
@@ -563,16 +536,41 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     if (handler != PDFB200_BC_SLIP) {
                         const double Un = A.Un[bf];
                         if (Un < 0 || !BF_REFLECTING(info)) {
-                            const double mpd = massPerDepth(M, pos, m);
-                            const int base = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
-                            accS[base * K1_THREADS] -= mpd;
-                            for (int cs = 0; cs < P.nConserved; ++cs) accS[(base + 1 + cs) * K1_THREADS] -= mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
+                            // the particle leaves through an open face: its mass and scalars as they are at this point
+                            const double mpd = massPerDepth(M, pos, massIn());
+                            const int baseAcc = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
+                            accS[baseAcc * K1_THREADS] -= mpd;
+                            for (int cs = 0; cs < P.nConserved; ++cs) {
+                                const int sIdx = PRM_AT(P, conserved, cs);
+                                const double ph = (phase == 0) ? reloadD(A.in.phi[sIdx] + slot) : reloadD(A.out.phi[sIdx] + i);
+                                accS[(baseAcc + 1 + cs) * K1_THREADS] -= mpd * ph;
+                            }
                             status = 1;
                             break;
                         }
                         reflBf = bf;
                     }
-                    U = reflectVec(U, nw); Ucorr = reflectVec(Ucorr, nw); Utrack = reflectVec(Utrack, nw);
+                    // reflection (rare): the particle velocity and the correction velocity are not held in registers
+                    // during the walk. Phase 0: U lives in out.p* (parked there by the first reflection), Ucorr in
+                    // shared memory. Phase 1: U is this step's new velocity in out.u*.
+                    {
+                        V3 Uc = mk(park[0], park[K1_THREADS], park[2 * K1_THREADS]);
+                        Uc = reflectVec(Uc, nw);
+                        park[0] = Uc.x; park[K1_THREADS] = Uc.y; park[2 * K1_THREADS] = Uc.z;
+                    }
+                    if (phase == 0) {
+                        V3 Ur;
+                        if (reflected) Ur = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
+                        else if (MESH_AXISYM(M)) Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
+                        else Ur = mk(reloadD(A.in.ux + slot), reloadD(A.in.uy + slot), reloadD(A.in.uz + slot));
+                        Ur = reflectVec(Ur, nw);
+                        A.out.px[i] = Ur.x; A.out.py[i] = Ur.y; A.out.pz[i] = Ur.z;
+                    } else {
+                        V3 Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
+                        Ur = reflectVec(Ur, nw);
+                        A.out.ux[i] = Ur.x; A.out.uy[i] = Ur.y; A.out.uz[i] = Ur.z;
+                    }
+                    Utrack = reflectVec(Utrack, nw);
                     reflected = true;
                     entry = 3;
                     break;
@@ -581,22 +579,37 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 tEnd -= dt;
             }
             if (status != 0) break;
-            if (!haveW) baryAt(T, pos - mk(T.cx, T.cy, T.cz), w0, w1, w2, w3);   // zero-length track or ended on a boundary
+            if (!haveW) baryAt(T, pos - ctr, w0, w1, w2, w3);   // zero-length track or ended on a boundary
             if (phase == 1) break;
 
             // ================= mid-point: E6, E7, E9 =================
-            cell = T.cell;
             double Co = courantNo(M, cell, Utrack);
             double val[NODE_MID_STRIDE];
-            double pst[4];
-            interpMid(M, P, A.nodeMid, T, w0, w1, w2, w3, val, pst);
+            V3 gradP;
+            {
+                double pst[4];
+                const int2 pts = __ldg(M.tetPts + tet);
+                interpMid(M, P, A.nodeMid, T.face, pts.x, pts.y, cell, w0, w1, w2, w3, val, pst);
+                // gradInterpolationConstantTet: g_d*cell + g_b*ptB + g_c*ptC + g_a*face (the record is dead afterwards)
+                const V3 ga = mk(T.g0, T.g1, T.g2), gb = mk(T.g3, T.g4, T.g5), gc = mk(T.g6, T.g7, T.g8);
+                const V3 gdv = -((ga + gb) + gc);
+                gradP = (gdv * pst[3] + gb * pst[1]) + gc * pst[2];
+                gradP = gradP + ga * pst[0];
+            }
             const double *aux = A.cellAux + (size_t)cell * A.auxStride;
+            // the particle's scalars, read again (see reloadD)
+            const double etaOld = reloadD(A.in.eta + slot);
+            double Omega = reloadD(A.in.omega + slot), rho = reloadD(A.in.rho + slot);
+            double phi[NPHI];
+#pragma unroll
+            for (int k = 0; k < NPHI; ++k) phi[k] = (k < nPhi) ? reloadD(A.in.phi[k] + slot) : 0.0;
+            const uint32_t id = (uint32_t)reloadI(reinterpret_cast<const int *>(A.in.id) + slot);
             // mcRASOmegaModel::correct
             if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
             // mcIEMMixingModel::correct
             if (P.mixingModel == PDFB200_MIXING_IEM) {
                 const double Cmix2 = 0.5 * P.Cmix;
-                const double fac = 1.0 - exp(-Cmix2 * Omega * eta * deltaT);
+                const double fac = 1.0 - exp(-Cmix2 * Omega * etaOld * deltaT);
                 for (int mI = 0; mI < P.nMixed; ++mI) {
                     const int s = PRM_AT(P, mixed, mI);
                     const double mean = __ldg(aux + 2 + s);
@@ -611,36 +624,47 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 FT.chi = A.flChi; FT.z = A.flZ; FT.fields = A.flFields; FT.nChi = A.nChi; FT.nZ = A.nZ;
                 reactionCorrect(P, FT, Omega, val[NM_ZVAR], aux[1], phi, rho);
             }
-            // the six normals of the step
-            double xi0, xi1, xi2, gd0, gd1, gd2;
+            // the scalars have their final values: written now, not carried through the second walk
+            A.out.omega[i] = Omega; A.out.rho[i] = rho;
+#pragma unroll
+            for (int k = 0; k < NPHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
+            A.out.id[i] = id;
+            A.out.m[i] = massIn();
+            // the six normals of the step: two Philox calls, single-precision Box-Muller (common.cuh)
+            // (= rngNormal4(sub 0) -> xi0 xi1 xi2 gd0, rngNormal2(sub 1) -> gd1 gd2; written as a rolled loop so that
+            // the kernel holds one copy of the Philox rounds and of the Box-Muller code: its instruction footprint
+            // is what the round-1 kernel was most sensitive to)
+            double xi0 = 0, xi1 = 0, xi2 = 0, gd0 = 0, gd1 = 0, gd2 = 0;
             {
-                // one copy of the Philox + Box-Muller code (instruction-cache footprint)
-                double na = 0, nb2 = 0, nc2 = 0, nd2 = 0, ne = 0, nf = 0;
+                uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
 #pragma unroll 1
-                for (uint32_t sub = 0; sub < 3; ++sub) {
-                    double a, b;
-#ifdef K1_EXP_NORNG   // timing experiment only: results are wrong
-                    a = 0.1 * sub; b = -0.1 * sub;
-#else
-                    rngNormal2(A.key, id, step, RNG_STEP_NORMALS, sub, a, b);
-#endif
-                    if (sub == 0) { na = a; nb2 = b; } else if (sub == 1) { nc2 = a; nd2 = b; } else { ne = a; nf = b; }
+                for (int pair = 0; pair < 3; ++pair) {
+                    if (pair != 1) {
+                        uint32_t o[4];
+                        rngWords(A.key, id, step, RNG_STEP_NORMALS, (uint32_t)(pair >> 1), o);
+                        o0 = o[0]; o1 = o[1]; o2 = o[2]; o3 = o[3];
+                    }
+                    float na, nb;
+                    normalPairF32(pair == 1 ? o2 : o0, pair == 1 ? o3 : o1, na, nb);
+                    if (pair == 0) { xi0 = (double)na; xi1 = (double)nb; }
+                    else if (pair == 1) { xi2 = (double)na; gd0 = (double)nb; }
+                    else { gd1 = (double)na; gd2 = (double)nb; }
                 }
-                xi0 = na; xi1 = nb2; xi2 = nc2; gd0 = nd2; gd1 = ne; gd2 = nf;
             }
+            // the velocity before the half step ("Uold") and the velocity the half step ended with
+            V3 Uold;
+            if (MESH_AXISYM(M)) Uold = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
+            else Uold = mk(reloadD(A.in.ux + slot), reloadD(A.in.uy + slot), reloadD(A.in.uz + slot));
+            V3 U = Uold;
+            if (reflected) U = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
             // mcSLMFullVelocityModel::correct
             if (P.velocityModel != PDFB200_VELOCITY_NONE) {
-                const double dTp = eta * deltaT;
+                const double dTp = etaOld * deltaT;
                 const V3 UFap = mk(val[NM_U], val[NM_U + 1], val[NM_U + 2]);
-                // gradInterpolationConstantTet: g_d*cell + g_b*ptB + g_c*ptC + g_a*face
-                const V3 ga = mk(T.g0, T.g1, T.g2), gb = mk(T.g3, T.g4, T.g5), gc = mk(T.g6, T.g7, T.g8);
-                const V3 gdv = -((ga + gb) + gc);
-                V3 gradP = (gdv * pst[3] + gb * pst[1]) + gc * pst[2];
-                gradP = gradP + ga * pst[0];
                 const double kFap = fmax(val[NM_K], P.kMin);
                 const V3 diffUap = mk(val[NM_DU], val[NM_DU + 1], val[NM_DU + 2]);
                 const double Acoef = -(0.5 * P.C1 + 0.75 * P.C0) * Omega;
-                const V3 B = -(gradP * (1.0 / rho) + Acoef * UFap);   // one reciprocal instead of three divisions
+                const V3 B = -(gradP / rho + Acoef * UFap);   // mcSLMFullVelocityModel.C:174
                 const double sq = sqrt(P.C0 * kFap * Omega * dTp);
                 const V3 deltaU = (B + Acoef * U) * dTp + sq * mk(xi0, xi1, xi2);
                 const V3 Ubefore = U;
@@ -649,41 +673,56 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             }
             CoKeep = Co;
             // local time stepping
+            double eta;
             if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
             else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) eta = fmin(P.CFL / stabilise(deltaT * Co, PDF_VSMALL), P.ltsUpperBound);
             else eta = 1.0;
+            A.out.eta[i] = eta;
 
             // ---- E9: mid-point rule from the old position ----
-            pos = posOld;
-            if (tet != tetOld) { tet = tetOld; loadTet(M.tets, stage, tet, T); }
+            pos = mk(reloadD(A.in.px + slot), reloadD(A.in.py + slot), reloadD(A.in.pz + slot));
+            tet = reloadI(A.in.tet + slot);
+            loadTet(M, tet, T);
+            cell = cell0;
+            double hNum;   // numerical-diffusion length of the start cell (mcParticleCloud.C:1937-1971)
+            ctr = cellCentreH(M, cell0, hNum);
             if (reflected) Utrack = Uold; else Utrack = 0.5 * (Uold + U);
-            const double hNum = hNumStart;   // T.cell is the start cell again
             const double C = P.DNum * sqrt(hNum * deltaT * mag3(Utrack)) / deltaT;
             Utrack = Utrack + mk(C * gd0, C * gd1, C * gd2);
-            Utrack = Utrack + Ucorr;
-            constrainParticle(M, deltaT, pos, U, Ucorr, Utrack);
+            {
+                V3 Ucorr = mk(park[0], park[K1_THREADS], park[2 * K1_THREADS]);
+                Utrack = Utrack + Ucorr;
+                constrainParticle(M, deltaT, pos, U, Ucorr, Utrack);
+                park[0] = Ucorr.x; park[K1_THREADS] = Ucorr.y; park[2 * K1_THREADS] = Ucorr.z;
+            }
+            A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
+            reflected = false;   // from here on: "reflected during the full step" (not used further)
         }
         if (status != 0) {
-            if (status == 2) { atomicAdd(A.lostMass + T.cell, m); accS[ACC_N_LOST * K1_THREADS] += 1; }
-            else accS[ACC_N_DELETED * K1_THREADS] += 1;
+            if (status == 2) {
+                // lost (mcParticleCloud.C:1257-1260, 1346-1351, notifyLostParticle :2088-2092): its mass goes on the
+                // list that k_lost_reduce sums per cell in a fixed order (no floating-point atomics). Lost during
+                // the half step: the mass has not been copied to `out` yet, so it is read from `in` either way.
+                const double m = massIn();
+                const unsigned k = atomicAdd(A.lostCount, 1u);
+                if (k < A.lostCap) { LostRec r; r.idx = (uint32_t)i; r.cell = cell; r.m = m; A.lostList[k] = r; }
+                accS[ACC_N_LOST * K1_THREADS] += 1;
+            } else accS[ACC_N_DELETED * K1_THREADS] += 1;
             A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1;
             continue;
         }
-        cell = T.cell;
         // ---- E11: mcOpenBoundary::correct(true) ----
+        V3 U = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
         if (reflBf >= 0) {
             const double4 n4 = M.bfNormal[reflBf];
             const V3 reflBV = mk(n4.x, n4.y, n4.z) * A.Un[reflBf];
             U = U + 2 * reflBV;
+            A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
         }
 
-        // ---- write back in sorted order ----
+        // ---- write back in sorted order (the scalars were written at the mid-point) ----
         A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
-        A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
-        A.out.m[i] = m; A.out.omega[i] = Omega; A.out.rho[i] = rho; A.out.eta[i] = eta;
-#pragma unroll
-        for (int k = 0; k < NPHI; ++k) if (k < nPhi) A.out.phi[k][i] = phi[k];
-        A.out.cell[i] = cell; A.out.tet[i] = tet; A.out.id[i] = id;
+        A.out.cell[i] = cell; A.out.tet[i] = tet;
         // key: rank of the cell in the processing order (tetBits == 0: nothing else; the stable sort keeps
         // the previous order inside a cell), else followed by the local tet
         const uint32_t rank = (uint32_t)__ldg(M.cellRank + cell);
@@ -692,10 +731,13 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {
+            const double m = reloadD(A.out.m + i), eta = reloadD(A.out.eta + i);
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_PLUS * K1_THREADS] += mpd;
-            for (int cs = 0; cs < P.nConserved; ++cs) accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * pickPhi(phi, PRM_AT(P, conserved, cs));
+            for (int cs = 0; cs < P.nConserved; ++cs)
+                accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * reloadD(A.out.phi[PRM_AT(P, conserved, cs)] + i);
             accS[ACC_N_ALIVE * K1_THREADS] += 1;
+            const V3 Ucorr = mk(park[0], park[K1_THREADS], park[2 * K1_THREADS]);
             accM[ACC_UMAX * K1_THREADS] = fmax(accM[ACC_UMAX * K1_THREADS], mag3(U));
             accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
             accM[ACC_ETAMAX * K1_THREADS] = fmax(accM[ACC_ETAMAX * K1_THREADS], eta);

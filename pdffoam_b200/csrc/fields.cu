@@ -70,7 +70,8 @@ __global__ void k_prep_cells(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
                 for (int j = M.cellFaceStart[c]; j < M.cellFaceStart[c + 1]; ++j) {
                     const int f = M.cellFaces[j];
                     if (f >= M.nInternalFaces && BF_GEOM(M.bfInfo[f - M.nInternalFaces]) == PDFB200_PATCH_EMPTY) continue;
-                    const V3 co = ld3(M.cellCo, j);
+                    const D4 co4 = M.cellCo4[j];
+                    const V3 co = mk(co4.x, co4.y, co4.z);
                     dtc = fmin(dtc, 1. / (fabs(dot3(co, U)) + fabs(dot3(co, urms2)) + PDF_SMALL));
                 }
                 const double e = dtc / deltaT;
@@ -132,7 +133,8 @@ __global__ void k_prep_grad(DMesh M, FieldPtrs F, const StepScalars *sc, double 
         const V3 upc = -g;
         st3(F.UPC_c, c, upc);
         for (int j = M.cellFaceStart[c]; j < M.cellFaceStart[c + 1]; ++j) {
-            const V3 co = deltaT * ld3(M.cellCo, j);
+            const D4 co4 = M.cellCo4[j];
+            const V3 co = deltaT * mk(co4.x, co4.y, co4.z);
             v[0] = fmax(v[0], fabs(dot3(co, upc)));
         }
     }
@@ -159,7 +161,7 @@ __global__ void k_nodes_cell(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= M.nCells) return;
     const double TU = fmax(P.relaxTimeU, P.minRelaxTime), Tk = fmax(P.relaxTimek, P.minRelaxTime);
-    double *nm = F.nodeMid + (size_t)c * NODE_MID_STRIDE;
+    const NodeRef nm{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)c};
     const V3 U = ld3(F.Ufv_c, c), Up = ld3(F.Updf_c, c);
     const double k = F.kfv_c[c];
     nm[NM_U] = U.x; nm[NM_U + 1] = U.y; nm[NM_U + 2] = U.z;
@@ -193,13 +195,13 @@ __global__ void k_nodes_point(DMesh M, FieldPtrs F) {
     for (int j = M.pointCellStart[p]; j < M.pointCellStart[p + 1]; ++j) {
         const double w = M.pointWeights[j];
         const int c = M.pointCells[j];
-        const double *nm = F.nodeMid + (size_t)c * NODE_MID_STRIDE;
+        const NodeRef nm{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)c};
 #pragma unroll
         for (int k = 0; k < NODE_MID_STRIDE; ++k) acc[k] += w * nm[k];
         const double *q = F.nodePC + (size_t)c * 4;
         pc[0] += w * q[0]; pc[1] += w * q[1]; pc[2] += w * q[2];
     }
-    double *o = F.nodeMid + (size_t)(M.nCells + p) * NODE_MID_STRIDE;
+    const NodeRef o{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)(M.nCells + p)};
 #pragma unroll
     for (int k = 0; k < NODE_MID_STRIDE; ++k) o[k] = acc[k];
     double *oq = F.nodePC + (size_t)(M.nCells + p) * 4;
@@ -209,15 +211,15 @@ __global__ void k_nodes_point(DMesh M, FieldPtrs F) {
 __global__ void k_nodes_face(DMesh M, FieldPtrs F, pdfb200_params P, const StepScalars *sc, int covZZ) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= M.nFaces) return;
-    double *o = F.nodeMid + (size_t)(M.nCells + M.nPoints + f) * NODE_MID_STRIDE;
+    const NodeRef o{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)(M.nCells + M.nPoints + f)};
     double *oq = F.nodePC + (size_t)(M.nCells + M.nPoints + f) * 4;
     const int ow = M.owner[f];
-    const double *no = F.nodeMid + (size_t)ow * NODE_MID_STRIDE;
+    const NodeRef no{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)ow};
     const double *qo = F.nodePC + (size_t)ow * 4;
     if (f < M.nInternalFaces) {
         const double w = M.linWeights[f];
         const int nb = M.neighbour[f];
-        const double *nn = F.nodeMid + (size_t)nb * NODE_MID_STRIDE;
+        const NodeRef nn{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)nb};
         const double *qn = F.nodePC + (size_t)nb * 4;
 #pragma unroll
         for (int k = 0; k < NODE_MID_STRIDE; ++k) o[k] = w * no[k] + (1 - w) * nn[k];

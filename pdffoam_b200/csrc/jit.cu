@@ -37,7 +37,7 @@ std::string hexDouble(double v) {
 std::string prologue(const pdfb200_params &p, bool axisym, bool hasOpen, int tetBits, const int geoD[3], const int solD[3]) {
     std::ostringstream o;
     o << "#define K1_JIT 1\n";
-    // the specialised kernel runs best with 3 CTAs per SM (168 registers, no spills; profiles/README.md)
+    // CTAs per SM the specialised kernel is compiled for (profiles/README.md)
     o << "#ifndef K1_MIN_BLOCKS\n#define K1_MIN_BLOCKS " << K1_JIT_MIN_BLOCKS << "\n#endif\n";
     o << "#define JIT_NPHI " << (p.nPhi <= 1 ? 1 : p.nPhi == 2 ? 2 : p.nPhi == 3 ? 3 : PDFB200_MAX_PHI) << "\n";
     o << "#define JIT_AXISYM " << (axisym ? 1 : 0) << "\n";

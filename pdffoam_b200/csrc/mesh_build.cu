@@ -94,7 +94,8 @@ __global__ void k_cell_geom(int nCells, const int *cellFaceStart, const int *cel
 __global__ void k_build_tets(int nCells, int nInternalFaces, const int *cellFaceStart, const int *cellFaces,
                              const int *cellTetStart, const int *faceTetStartOwn, const int *faceTetStartNei,
                              const int *owner, const int *faceStart, const int *facePoints, const double *points,
-                             const double *faceCentres, const double4 *cellCentre4, TetRec *tets) {
+                             const int *neighbour, const double *faceCentres, const double4 *cellCentre4, TetA *tetA, D4 *tetB, D4 *tetC,
+                             int2 *tetPts, int *tetCell) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const double4 cc = cellCentre4[c];
@@ -116,33 +117,41 @@ __global__ void k_build_tets(int nCells, int nInternalFaces, const int *cellFace
             const V3 Sb = 0.5 * cross3(d - a, cpt - a);
             const V3 Sc = 0.5 * cross3(b - a, d - a);
             const double vol = (1.0 / 6.0) * dot3(cross3(b - a, cpt - a), d - a);
-            TetRec T;
+            double g[9];
             if (vol > 0) {
                 const double den = -3. * vol;
                 const V3 ga = Sa / den, gb = Sb / den, gc = Sc / den;
-                T.g[0] = ga.x; T.g[1] = ga.y; T.g[2] = ga.z;
-                T.g[3] = gb.x; T.g[4] = gb.y; T.g[5] = gb.z;
-                T.g[6] = gc.x; T.g[7] = gc.y; T.g[8] = gc.z;
+                g[0] = ga.x; g[1] = ga.y; g[2] = ga.z;
+                g[3] = gb.x; g[4] = gb.y; g[5] = gb.z;
+                g[6] = gc.x; g[7] = gc.y; g[8] = gc.z;
             } else {
-                for (int k = 0; k < 9; ++k) T.g[k] = 0;
+                for (int k = 0; k < 9; ++k) g[k] = 0;
             }
             const int prev = t0 + (i == 0 ? n - 1 : i - 1), next = t0 + (i == n - 1 ? 0 : i + 1);
-            T.nbr[0] = -1;
-            T.nbr[1] = own ? prev : next;
-            T.nbr[2] = own ? next : prev;
-            if (f < nInternalFaces) T.nbr[3] = (own ? faceTetStartNei[f] : faceTetStartOwn[f]) + i;
-            else T.nbr[3] = -1;
-            T.face = f; T.ptB = ptBI; T.ptC = ptCI; T.cell = c;
-            T.centre[0] = d.x; T.centre[1] = d.y; T.centre[2] = d.z;
-            tets[t] = T;
+            TetA A;
+            A.nbr[0] = -1;
+            A.nbr[1] = own ? prev : next;
+            A.nbr[2] = own ? next : prev;
+            if (f < nInternalFaces) { A.nbr[3] = (own ? faceTetStartNei[f] : faceTetStartOwn[f]) + i; A.nbrCell = own ? neighbour[f] : owner[f]; }
+            else { A.nbr[3] = -1; A.nbrCell = -1; }
+            A.face = f; A.g0 = g[0];
+            tetA[t] = A;
+            D4 b4, c4;
+            b4.x = g[1]; b4.y = g[2]; b4.z = g[3]; b4.w = g[4];
+            c4.x = g[5]; c4.y = g[6]; c4.z = g[7]; c4.w = g[8];
+            tetB[t] = b4; tetC[t] = c4;
+            tetPts[t] = make_int2(ptBI, ptCI);
+            tetCell[t] = c;
         }
     }
     // the other face of this cell sharing mesh edge (b,c)
     for (int t1 = tBegin; t1 < tEnd; ++t1) {
-        const int lo1 = min(tets[t1].ptB, tets[t1].ptC), hi1 = max(tets[t1].ptB, tets[t1].ptC);
+        const int2 p1 = tetPts[t1];
+        const int lo1 = min(p1.x, p1.y), hi1 = max(p1.x, p1.y);
         for (int t2 = tBegin; t2 < tEnd; ++t2) {
             if (t2 == t1) continue;
-            if (min(tets[t2].ptB, tets[t2].ptC) == lo1 && max(tets[t2].ptB, tets[t2].ptC) == hi1) { tets[t1].nbr[0] = t2; break; }
+            const int2 p2 = tetPts[t2];
+            if (min(p2.x, p2.y) == lo1 && max(p2.x, p2.y) == hi1) { tetA[t1].nbr[0] = t2; break; }
         }
     }
 }
@@ -193,10 +202,13 @@ __global__ void k_face_tables(int nFaces, int nInternalFaces, const int *owner, 
     }
 }
 
-__global__ void k_cell_co(int nSlots, const int *cellFaces, const double *courantCoeffs, double *cellCo) {
+__global__ void k_cell_co(int nSlots, const int *cellFaces, const double *courantCoeffs, D4 *cellCo4) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nSlots) return;
-    st3(cellCo, j, ld3(courantCoeffs, cellFaces[j]));
+    const V3 co = ld3(courantCoeffs, cellFaces[j]);
+    D4 v;
+    v.x = co.x; v.y = co.y; v.z = co.z; v.w = 0.0;
+    cellCo4[j] = v;
 }
 
 static int ilog2ceil(long long v) {
@@ -327,20 +339,22 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     faceCentres.alloc((size_t)nFaces * 3); faceAreas.alloc((size_t)nFaces * 3); magSf.alloc(nFaces);
     cellCentre4.alloc(nCells); cellVolumes.alloc(nCells); volumeOrArea.alloc(nCells);
     bbMin.alloc((size_t)nCells * 3); bbMax.alloc((size_t)nCells * 3);
-    courantCoeffs.alloc((size_t)nFaces * 3); cellCo.alloc(hCF.size() * 3);
+    courantCoeffs.alloc((size_t)nFaces * 3); cellCo4.alloc(hCF.size());
     linWeights.alloc(std::max(nInternalFaces, 1)); pointWeights.alloc(hPC.size());
-    bfNormal.alloc(nBnd); tets.alloc((size_t)nTets);
+    bfNormal.alloc(nBnd);
+    tetA.alloc((size_t)nTets); tetB.alloc((size_t)nTets); tetC.alloc((size_t)nTets); tetPts.alloc((size_t)nTets); tetCell.alloc((size_t)nTets);
 
     const int B = 128;
     LAUNCH(this, k_face_geom, gridFor(nFaces, B), B, 0, nFaces, faceStart.p, facePoints.p, points.p, faceCentres.p, faceAreas.p, magSf.p);
     LAUNCH(this, k_cell_geom, gridFor(nCells, B), B, 0, nCells, cellFaceStart.p, cellFaces.p, owner.p, faceStart.p, facePoints.p,
            points.p, faceCentres.p, faceAreas.p, cellCentre4.p, cellVolumes.p, bbMin.p, bbMax.p, m.geometricD[0], m.geometricD[1], m.geometricD[2]);
     LAUNCH(this, k_build_tets, gridFor(nCells, 64), 64, 0, nCells, nInternalFaces, cellFaceStart.p, cellFaces.p, cellTetStart.p,
-           faceTetStartOwn.p, faceTetStartNei.p, owner.p, faceStart.p, facePoints.p, points.p, faceCentres.p, cellCentre4.p, tets.p);
+           faceTetStartOwn.p, faceTetStartNei.p, owner.p, faceStart.p, facePoints.p, points.p, neighbour.p, faceCentres.p, cellCentre4.p,
+           tetA.p, tetB.p, tetC.p, tetPts.p, tetCell.p);
     LAUNCH(this, k_point_weights, gridFor(nPoints, B), B, 0, nPoints, pointCellStart.p, pointCells.p, points.p, cellCentre4.p, pointWeights.p);
     LAUNCH(this, k_face_tables, gridFor(nFaces, B), B, 0, nFaces, nInternalFaces, owner.p, neighbour.p, faceCentres.p, faceAreas.p,
            magSf.p, cellCentre4.p, bfInfo.p, linWeights.p, courantCoeffs.p, bfNormal.p);
-    LAUNCH(this, k_cell_co, gridFor((long long)hCF.size(), B), B, 0, (int)hCF.size(), cellFaces.p, courantCoeffs.p, cellCo.p);
+    LAUNCH(this, k_cell_co, gridFor((long long)hCF.size(), B), B, 0, (int)hCF.size(), cellFaces.p, courantCoeffs.p, cellCo4.p);
     CUDA_CHECK(cudaMemcpyAsync(volumeOrArea.p, cellVolumes.p, nCells * sizeof(double), cudaMemcpyDeviceToDevice, s));
 
     // ---- processing order of the cells ----
@@ -442,9 +456,9 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     dm.faceTetStartOwn = faceTetStartOwn.p; dm.faceTetStartNei = faceTetStartNei.p;
     dm.faceCentres = faceCentres.p; dm.faceAreas = faceAreas.p; dm.magSf = magSf.p; dm.cellCentre4 = cellCentre4.p;
     dm.cellVolumes = cellVolumes.p; dm.volumeOrArea = volumeOrArea.p; dm.bbMin = bbMin.p; dm.bbMax = bbMax.p;
-    dm.courantCoeffs = courantCoeffs.p; dm.cellCo = cellCo.p; dm.linWeights = linWeights.p;
+    dm.courantCoeffs = courantCoeffs.p; dm.cellCo4 = cellCo4.p; dm.linWeights = linWeights.p;
     dm.pointCellStart = pointCellStart.p; dm.pointCells = pointCells.p; dm.pointWeights = pointWeights.p;
-    dm.tets = tets.p; dm.bfInfo = bfInfo.p; dm.bfNormal = bfNormal.p;
+    dm.tetA = tetA.p; dm.tetB = tetB.p; dm.tetC = tetC.p; dm.tetPts = tetPts.p; dm.tetCell = tetCell.p; dm.bfInfo = bfInfo.p; dm.bfNormal = bfNormal.p;
     dm.openCellStart = openCellStart.p; dm.openCellFaces = openCellFaces.p; dm.patchFaceT = patchFaceT.p;
     CUDA_CHECK(cudaStreamSynchronize(s));
 }

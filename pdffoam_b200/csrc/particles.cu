@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
         };
         auto hashOf = [&](uint32_t id, int r) {
             uint32_t o[4];
-            philox4x32_10(id, step, RNG_MIX_HASH, (uint32_t)r, key.k0, key.k1, o);
+            rngWords(key, id, step, RNG_MIX_HASH, (uint32_t)r, o);
             return o[0];
         };
         for (int r = 0; r < R; ++r) {
@@ -451,18 +451,20 @@ __global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const V3 pos = mk(S.px[i], S.py[i], S.pz[i]);
+    const int tet = S.tet[i], cell = S.cell[i];
     TetL T;
-    loadTet(M.tets, S.tet[i], T);
+    loadTet(M, tet, T);
     double w0, w1, w2, w3;
-    baryAt(T, pos - cellCentre(M, T.cell), w0, w1, w2, w3);
+    baryAt(T, pos - cellCentre(M, cell), w0, w1, w2, w3);
     double val[NODE_MID_STRIDE], pst[4];
-    interpMid(M, P, nodeMid, T, w0, w1, w2, w3, val, pst);
+    const int2 pts = M.tetPts[tet];
+    interpMid(M, P, nodeMid, T.face, pts.x, pts.y, cell, w0, w1, w2, w3, val, pst);
     double eta = 1.0;
     if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
     else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
         V3 Ut = mk(S.ux[i], S.uy[i], S.uz[i]);
         constrainDir(MESH_GEOD3(M), Ut);
-        eta = fmin(P.CFL / stabilise(sc->deltaT * courantNo(M, T.cell, Ut), PDF_VSMALL), P.ltsUpperBound);
+        eta = fmin(P.CFL / stabilise(sc->deltaT * courantNo(M, cell, Ut), PDF_VSMALL), P.ltsUpperBound);
     }
     S.eta[i] = eta;
     S.m[i] = S.m[i] / eta;
@@ -473,7 +475,7 @@ __global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const 
 #pragma unroll
     for (int k = 0; k < PDFB200_MAX_PHI; ++k) phi[k] = k < P.nPhi ? S.phi[k][i] : 0.0;
     double rho = S.rho[i];
-    reactionCorrect(P, FT, Omega, val[NM_ZVAR], cellAux[(size_t)T.cell * auxStride + 1], phi, rho);
+    reactionCorrect(P, FT, Omega, val[NM_ZVAR], cellAux[(size_t)cell * auxStride + 1], phi, rho);
     S.rho[i] = rho;
 #pragma unroll
     for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k < P.nPhi) S.phi[k][i] = phi[k];
@@ -634,10 +636,11 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
                 double eta = 1.0;
                 if (P.localTimeStepping == PDFB200_LTS_CELL) {
                     TetL TL;
-                    loadTet(M.tets, tet, TL);
+                    loadTet(M, tet, TL);
                     double w0, w1, w2, w3, val[NODE_MID_STRIDE], pst[4];
                     baryAt(TL, pos - cellCentre(M, cellI), w0, w1, w2, w3);
-                    interpMid(M, P, nodeMid, TL, w0, w1, w2, w3, val, pst);
+                    const int2 pts = M.tetPts[tet];
+                    interpMid(M, P, nodeMid, TL.face, pts.x, pts.y, cellI, w0, w1, w2, w3, val, pst);
                     eta = val[NM_ETA];
                 } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
                     V3 Ut = Up;
@@ -932,15 +935,49 @@ struct DevReport {
 #define RP_END (RP_CLONEDELTA + K1_NC1)
 static_assert(RP_END <= 64, "DevReport too small");
 
-// lostMass_/max(PaNIC,1) (mcParticleCloud.C:1363-1369); partial sums of what is re-spread
+// Lost particles (mcParticleCloud.C:1257-1260,1346-1351, notifyLostParticle :2088-2092): the particle
+// kernel appends (entry index, cell, mass) records to a list in whatever order its atomic counter
+// hands out. This kernel (one CTA) puts the list into (cell, entry index) order by counting ranks and
+// then sums every cell's records front to back, so lostMass does not depend on that order and no
+// floating-point atomic is needed. The list is short (a healthy run loses nothing).
+__global__ void k_lost_reduce(const LostRec *list, LostRec *sorted, const unsigned *count, unsigned cap, double *lostMass, StepScalars *sc) {
+    unsigned n = *count;
+    if (n == 0) return;
+    if (n > cap) { n = cap; if (threadIdx.x == 0) sc->overflow = 2; }
+    for (unsigned r = threadIdx.x; r < n; r += blockDim.x) {
+        const LostRec me = list[r];
+        const unsigned long long key = ((unsigned long long)(unsigned)me.cell << 32) | me.idx;
+        unsigned rank = 0;
+        for (unsigned q = 0; q < n; ++q) {
+            const LostRec o = list[q];
+            rank += ((((unsigned long long)(unsigned)o.cell << 32) | o.idx) < key) ? 1u : 0u;
+        }
+        sorted[rank] = me;
+    }
+    __syncthreads();
+    for (unsigned r = threadIdx.x; r < n; r += blockDim.x) {
+        const int c = sorted[r].cell;
+        if (r > 0 && sorted[r - 1].cell == c) continue;   // not the head of its cell's run
+        double sum = 0;
+        for (unsigned q = r; q < n && sorted[q].cell == c; ++q) sum += sorted[q].m;
+        lostMass[c] = sum;
+    }
+}
+
+// lostMass_/max(PaNIC,1) (mcParticleCloud.C:1363-1369); partial sums of what is re-spread.
+// The mass a rank lost is shared among the particles this rank holds in the cell after number
+// control: nLocal = (segment length) + (PaNIC - N), where N is the all-reduced count of the moment
+// block and PaNIC has since been updated by this rank's clones and eliminations. With one rank that
+// is PaNIC itself (the reference's expression); with several it conserves the mass rank by rank.
 __global__ void k_lost_share(int nCells, const double *lostMass, const double *PaNIC, const int *cellStart,
-                             const int *cellEnd, const int *nClone, double *lostShare, double *partial) {
+                             const int *cellEnd, const double *block, int nMom, double *lostShare, double *partial) {
     __shared__ double sm[32];
     double v[1] = {0.0};
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
-        const double sh = lostMass[c] / fmax(PaNIC[c], 1.);
+        const double nLocal = (double)(cellEnd[c] - cellStart[c]) + (PaNIC[c] - block[(size_t)c * nMom]);
+        const double sh = lostMass[c] / fmax(nLocal, 1.);
         lostShare[c] = sh;
-        v[0] += sh * (double)((cellEnd[c] - cellStart[c]) + (nClone ? nClone[c] : 0));
+        v[0] += sh * nLocal;
     }
     blockReduce<1, false>(v, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
@@ -980,6 +1017,14 @@ __global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int
     sc->nLostTotal += (long long)rp->v[RP_K1SUM + ACC_N_LOST];
 }
 
+__global__ void k_rng_probe(RngKey key, int n, const uint64_t *entity, uint32_t step, uint32_t purpose, uint32_t sub, double *out6) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *o = out6 + 6 * (size_t)i;
+    rngUniform2(key, entity[i], step, purpose, sub, o[0], o[1]);
+    rngNormal4(key, entity[i], step, purpose, sub, o[2], o[3], o[4], o[5]);
+}
+
 // ===========================================================================
 // host side
 // ===========================================================================
@@ -1007,6 +1052,23 @@ static FlameletTables tablesOf(const Cloud &c) {
     FlameletTables f;
     f.chi = c.flChi.p; f.z = c.flZ.p; f.fields = c.flFields.p; f.nChi = c.nChi; f.nZ = c.nZ;
     return f;
+}
+
+extern "C" int pdfb200_rng_probe(int device, uint64_t seed, int64_t n, const uint64_t *entity, uint32_t step, uint32_t purpose,
+                                 uint32_t sub, double *out6) {
+    if (n <= 0) return PDFB200_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return PDFB200_ERR_CUDA;
+    uint64_t *dE = nullptr;
+    double *dO = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dE, n * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dO, n * 6 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(dE, entity, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_rng_probe<<<gridFor(n, 256), 256>>>(makeKey(seed), (int)n, dE, step, purpose, sub, dO);
+        e = cudaMemcpy(out6, dO, n * 6 * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dE); cudaFree(dO);
+    return e == cudaSuccess ? PDFB200_OK : PDFB200_ERR_CUDA;
 }
 
 void Cloud::allocParticles() {
@@ -1040,6 +1102,8 @@ void Cloud::allocParticles() {
     const int maxGrid = numSMs * 16;
     k1PartSum.alloc((size_t)maxGrid * ACC_NSUM); k1PartMax.alloc((size_t)std::max(maxGrid * ACC_NMAX, numSMs * 64));
     cellPartSum.alloc((size_t)maxGrid * 8); finalSums.alloc(256);
+    const size_t lostCap = (size_t)std::min<int64_t>(capacity, 65536);
+    lostList.alloc(lostCap); lostSorted.alloc(lostCap); lostCount.alloc(1); lostCount.zero(stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
@@ -1093,6 +1157,17 @@ void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
     nParticlesHost = n; nSlotsHost = 0; sortedValid = false;
 }
 
+// adds the share of the mass lost in the last step to the particles now (the particle kernel would do it at the
+// start of the next step), so that a download shows the state the reference has after mcParticleCloud.C:1363-1369
+__global__ void k_materialise_lost(int n, int nSorted, int nSlots, const uint32_t *perm, PState S, const double *lostShare, StepScalars *sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) sc->anyLost = 0;
+    if (i >= n) return;
+    const int slot = i < nSorted ? (int)perm[i] : nSlots + (i - nSorted);
+    const int c = S.cell[slot];
+    if (c >= 0) S.m[slot] += lostShare[c];
+}
+
 // gathers column `src` through idx (or identity for the tail) into `dst`
 __global__ void k_gather_d(int n, int nSorted, int nSlots, const uint32_t *perm, const double *src, double *dst, const int *cell, int *alive) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1112,6 +1187,10 @@ void Cloud::downloadParticles(int64_t maxn, pdfb200_particles &out, int64_t *nOu
     CUDA_CHECK(cudaMemcpy(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost));
     const int nSorted = hScal->nSorted, nTail = hScal->nTail, nSlots = hScal->nSlots;
     const int n = nSorted + nTail;
+    if (hScal->anyLost && n > 0) {
+        LAUNCH(this, k_materialise_lost, gridFor(n, 256), 256, 0, n, nSorted, nSlots, valsB.p, S[cur], lostShare.p, scal.p);
+        hScal->anyLost = 0;
+    }
     // logical order: sorted particles, then the tail; eliminated ones (cell < 0) are skipped
     DBuf<double> d; d.alloc(std::max(n, 1));
     DBuf<int> di, alive; di.alloc(std::max(n, 1)); alive.alloc(std::max(n, 1));
@@ -1218,11 +1297,15 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         A.M = dm; A.P = prm; A.in = S[cur]; A.out = S[cur ^ 1];
         A.perm = valsB.p; A.keyOut = keysA.p; A.sc = scal.p;
         A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride;
-        A.Un = Un.p; A.lostShare = lostShare.p; A.lostMass = lostMass.p; A.injPatchTail = injPatchTail.p;
+        A.Un = Un.p; A.lostShare = lostShare.p; A.lostList = lostList.p; A.lostCount = lostCount.p; A.lostCap = (unsigned)lostList.n;
+        A.injPatchTail = injPatchTail.p;
         A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ;
         A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
         const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
-        CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
+        // lost-particle bookkeeping of this step starts empty; the cells are only touched when the previous step
+        // left something in them
+        if (lostDirty) { CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream)); lostDirty = false; }
+        CUDA_CHECK(cudaMemsetAsync(lostCount.p, 0, sizeof(unsigned), stream));
         mark(1);
         if (k1Jit) {
             void *kargs[] = {&A};
@@ -1232,6 +1315,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
         }
         mark(2);
+        LAUNCH(this, k_lost_reduce, 1, 1024, 0, lostList.p, lostSorted.p, lostCount.p, (unsigned)lostList.n, lostMass.p, scal.p);
         LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
         LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
         cur ^= 1;
@@ -1321,7 +1405,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         // ---- lost mass shares ----
         {
             const int gL = std::min(gridFor(nCells, 256), numSMs * 4);
-            LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, nc ? ncCount.p : nullptr, lostShare.p, k1PartMax.p);
+            LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, momentBlock.p, nMom, lostShare.p, k1PartMax.p);
             LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gL, 1, k1PartMax.p, dRep->v + RP_LOSTSUM, 0);
         }
         LAUNCH(this, k_step_end, 1, 32, 0, scal.p, dRep, prm, 0, nc ? ncCounts.p : nullptr, total, nRanks);
@@ -1342,8 +1426,10 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         }
         profParticleSteps += (double)total;
         ++profSteps;
+        if (hScal->overflow == 2) throw std::runtime_error("evolve: more than " + std::to_string(lostList.n) + " particles lost in one step");
         if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
         const double *v = hFinal;
+        if (v[RP_K1SUM + ACC_N_LOST] > 0) lostDirty = true;
         nParticlesHost = (int64_t)hScal->nSorted + hNc[0] - hNc[1];
         nSlotsHost = total;
         deltaTHost = hScal->deltaT;
