@@ -301,8 +301,8 @@ double pdfb200_last_evolve_ms(pdfb200_cloud *cloud);
  * with the cloud's parameters and mesh flags as constants (jit.cu). This
  * returns the translation unit that would be compiled for the given parameters and flags
  * (host only, no device needed; the CPU test-suite builds it); length of the text or -1. */
-long pdfb200_jit_source(const pdfb200_params *params, int axisym, int hasOpen, int tetBits, const int32_t geometricD[3],
-                        const int32_t solutionD[3], char *buf, long bufLen);
+long pdfb200_jit_source(const pdfb200_params *params, int axisym, int hasOpen, int tetBits, int cellFacesUniform,
+                        const int32_t geometricD[3], const int32_t solutionD[3], char *buf, long bufLen);
 
 #ifdef __cplusplus
 }

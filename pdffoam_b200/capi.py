@@ -224,7 +224,7 @@ class Library:
         if self.has("rng_probe") and self.prefix == "pdfb200_":
             f("rng_probe").argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
         if self.has("jit_source"):
-            f("jit_source").argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_char_p, C.c_long]
+            f("jit_source").argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_char_p, C.c_long]
             f("jit_source").restype = C.c_long
 
     def check(self, status: int, what: str):
@@ -234,12 +234,12 @@ class Library:
 
 
 def jit_source(lib: "Library", params: Params, axisym: bool, has_open: bool, tet_bits: int = 0,
-               geometric_d=(1, 1, 1), solution_d=(1, 1, 1)) -> str:
+               geometric_d=(1, 1, 1), solution_d=(1, 1, 1), cell_faces: int = 6) -> str:
     """The translation unit the library compiles at run time for these parameters
     and mesh flags (pdffoam_b200/csrc/jit.cu); host only."""
     buf = C.create_string_buffer(1 << 16)
     g = np.asarray(geometric_d, np.int32); sd = np.asarray(solution_d, np.int32)
-    n = lib.fn("jit_source")(C.byref(params), int(axisym), int(has_open), int(tet_bits), _ip(g), _ip(sd), buf, len(buf))
+    n = lib.fn("jit_source")(C.byref(params), int(axisym), int(has_open), int(tet_bits), int(cell_faces), _ip(g), _ip(sd), buf, len(buf))
     if n < 0:
         raise PdfError("jit_source: buffer too small")
     return buf.value.decode()

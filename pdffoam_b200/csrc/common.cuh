@@ -114,6 +114,7 @@ struct DMesh {
     int nCells, nFaces, nInternalFaces, nPoints, nBnd, nPatches;
     long long nTets;
     int tetBits;             // sort key = (cell << tetBits) | localTet
+    int cellFacesUniform;    // faces per cell when every cell has the same number (hex meshes: 6), else 0
     int geoD[3], solD[3];
     int nGeoD;
     int axisym;

@@ -32,6 +32,7 @@
 #define MESH_SOLD(M, k) (JIT_SOLD##k)
 #define MESH_NGEOD(M) (JIT_NGEOD)
 #define MESH_TETBITS(M) (JIT_TETBITS)
+#define MESH_CELLFACES(M) (JIT_CELLFACES)
 // JitP (generated): the parameters the kernel reads as static constexpr members, the index lists
 // as constexpr functions mixedAt(i) / conservedAt(i) / addedIdxAt(i)
 typedef JitP KParams;
@@ -44,6 +45,7 @@ typedef pdfb200_params KParams;
 #define MESH_SOLD(M, k) ((M).solD[k])
 #define MESH_NGEOD(M) ((M).nGeoD)
 #define MESH_TETBITS(M) ((M).tetBits)
+#define MESH_CELLFACES(M) ((M).cellFacesUniform)
 #endif
 #define MESH_GEOD3(M) MESH_GEOD(M, 0), MESH_GEOD(M, 1), MESH_GEOD(M, 2)
 #define MESH_SOLD3(M) MESH_SOLD(M, 0), MESH_SOLD(M, 1), MESH_SOLD(M, 2)
@@ -53,7 +55,6 @@ struct K1Args {
     pdfb200_params P;
     PState in, out;
     const uint32_t *perm;
-    uint32_t *keyOut;
     const StepScalars *sc;
     const double *nodeMid, *nodePC, *cellAux;
     int auxStride;
@@ -75,15 +76,22 @@ struct K1Args {
 struct TetL {
     int n0, n1, n2, n3;          // neighbours across the faces opposite a, b, c, d
     int face, nbrCell;           // mesh face of the tet, cell across it
+    int ptB, ptC;                // global point labels of b and c
     double g0, g1, g2, g3, g4, g5, g6, g7, g8;   // gradN of a, b, c
 };
 
-// three 256-bit loads, one per plane of the tet table (see TetA in common.cuh)
+// three 256-bit loads, one per plane of the tet table (see TetA in common.cuh); the point labels of b and c
+// are fetched where an interpolation needs them (loadPts), not with every visited record
 __device__ __forceinline__ void loadTet(const DMesh &M, int t, TetL &T) {
     const D4 r0 = ld256(M.tetA + t), r1 = ld256(M.tetB + t), r2 = ld256(M.tetC + t);
     T.n0 = __double2loint(r0.x); T.n1 = __double2hiint(r0.x); T.n2 = __double2loint(r0.y); T.n3 = __double2hiint(r0.y);
     T.face = __double2loint(r0.z); T.nbrCell = __double2hiint(r0.z);
     T.g0 = r0.w; T.g1 = r1.x; T.g2 = r1.y; T.g3 = r1.z; T.g4 = r1.w; T.g5 = r2.x; T.g6 = r2.y; T.g7 = r2.z; T.g8 = r2.w;
+}
+
+__device__ __forceinline__ void loadPts(const DMesh &M, int t, TetL &T) {
+    const int2 pts = __ldg(M.tetPts + t);
+    T.ptB = pts.x; T.ptC = pts.y;
 }
 
 // centre of a cell (vertex d of its tets) and its numerical-diffusion length: one 256-bit load
@@ -305,7 +313,9 @@ __device__ inline V3 randomPointInCell(const DMesh &M, RngKey key, int cell, uin
 // computeCourantNo (mcParticleCloud.C:2120-2148); one 256-bit load per face of the cell
 __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack) {
     double Co = 0.;
-    const int js = __ldg(M.cellFaceStart + cell), je = __ldg(M.cellFaceStart + cell + 1);
+    // every cell with the same number of faces (hex meshes): the row of the cell is known without looking it up
+    const int nF = MESH_CELLFACES(M);
+    const int js = nF > 0 ? cell * nF : __ldg(M.cellFaceStart + cell), je = nF > 0 ? js + nF : __ldg(M.cellFaceStart + cell + 1);
     for (int j = js; j < je; ++j) {
         const D4 c4 = ld256(M.cellCo4 + j);
         Co = fmax(Co, fabs(dot3(mk(c4.x, c4.y, c4.z), Utrack)));
@@ -317,8 +327,8 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #define K1_MIN_BLOCKS 4
 #endif
 // dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
-// (the correction velocity, which must survive both tet walks without occupying registers)
-#define K1_NPARK 3
+// (the correction velocity and the Courant number, which must survive the tet walks without occupying registers)
+#define K1_NPARK 4
 #define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX + K1_NPARK) * K1_THREADS * sizeof(double))
 
 // Loads of this thread's own state columns that the compiler must not merge with an earlier load
@@ -330,6 +340,10 @@ __device__ __forceinline__ double reloadD(const double *p) {
     double v;
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
+}
+// the same for the input state, which the kernel never writes: no ordering against its stores needed
+__device__ __forceinline__ double reloadInD(const double *p) {
+    return reloadD(p);
 }
 __device__ __forceinline__ int reloadI(const int *p) {
     int v;
@@ -364,20 +378,33 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     const int nPhi = P.nPhi;
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
 
+    // the slot of an entry comes through the permutation of the last sort: requested one iteration ahead so that
+    // the state loads of an iteration do not start with a dependent load
+    int slotNext = 0;
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < nSorted) slotNext = (int)A.perm[i0];
+    }
     for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
         const int i = base + threadIdx.x;
+        const int slotPerm = slotNext;
+        {
+            const int iN = i + gridDim.x * blockDim.x;
+            if (iN < nSorted) slotNext = (int)A.perm[iN];
+        }
         if (i >= total) continue;
-        const int slot = (i < nSorted) ? (int)A.perm[i] : nSlotsIn + (i - nSorted);
+        const int slot = (i < nSorted) ? slotPerm : nSlotsIn + (i - nSorted);
         const int cell0 = A.in.cell[slot];
-        if (cell0 < 0) { A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
+        if (cell0 < 0) { A.out.cell[i] = -1; continue; }
         V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
-        int tet = A.in.tet[slot];
+        const int tet0 = A.in.tet[slot];
+        int tet = tet0;
         const bool injected = (i >= nSorted + nInjStart);
 
         // the particle's mass at the start of the step: the stored one plus its share of the mass lost in the
         // previous step (mcParticleCloud.C:1363-1369; particles injected since then get none)
         auto massIn = [&]() {
-            double mm = reloadD(A.in.m + slot);
+            double mm = reloadInD(A.in.m + slot);
             if (anyLost && !injected) mm += A.lostShare[cell0];
             return mm;
         };
@@ -408,7 +435,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     }
                 }
             }
-            if (status != 0) { accS[ACC_N_DELETED * K1_THREADS] += 1; A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1; continue; }
+            if (status != 0) { accS[ACC_N_DELETED * K1_THREADS] += 1; A.out.cell[i] = -1; continue; }
             // ---- E2 ----
             const double mpd = massPerDepth(M, pos, m);
             accS[ACC_DM_MINUS * K1_THREADS] -= mpd;
@@ -433,9 +460,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     double a0, a1, a2, a3;
                     baryAt(T, pos - ctr, a0, a1, a2, a3);
                     const double fb = clamp01(a1), fc = clamp01(a2), fa = clamp01(a0), fd = clamp01(a3);
-                    const int2 pts = __ldg(M.tetPts + tet);
+                    loadPts(M, tet, T);
                     // 32-byte node records: one 256-bit load per node
-                    const D4 vb = ld256(A.nodePC + (nodeP + pts.x) * 4), vc = ld256(A.nodePC + (nodeP + pts.y) * 4);
+                    const D4 vb = ld256(A.nodePC + (nodeP + T.ptB) * 4), vc = ld256(A.nodePC + (nodeP + T.ptC) * 4);
                     const D4 va = ld256(A.nodePC + (nodeF + T.face) * 4), vd = ld256(A.nodePC + (size_t)cell0 * 4);
                     Ucorr.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
                     Ucorr.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
@@ -452,7 +479,6 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         }
         bool reflected = false;
         int reflBf = -1;   // boundary face of the last open-boundary reflection (mcOpenBoundary.C:201-204)
-        double w0 = 0, w1 = 0, w2 = 0, w3 = 0, CoKeep = 0;
 
         // ---- E5 (phase 0: eta*deltaT/2) and E10 (phase 1: eta*deltaT): mcParticle::move on the
         //      tet walk (see oracle/src/cloud.cpp Cloud::move; identical expressions) ----
@@ -463,15 +489,14 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 double stepFraction = 0.0;
                 if (phase == 0 && injected) { double u0, u1; rngUniform2(A.key, A.in.id[slot], step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
                 // phase 0 tracks with the old local time step, phase 1 with the new one (written to out.eta at the mid-point)
-                const double eta = (phase == 0) ? reloadD(A.in.eta + slot) : reloadD(A.out.eta + i);
+                const double eta = (phase == 0) ? reloadInD(A.in.eta + slot) : reloadD(A.out.eta + i);
                 const double trackTime = (phase == 0) ? eta * (deltaT / 2.) : eta * deltaT;
                 tEnd = (1.0 - stepFraction) * trackTime;
             }
-            const double dtMax = tEnd;
             int entry = -1, nSteps = 0;
-            bool haveW = false;
             while (tEnd > 0 && status == 0) {
-                double dt = fmin(dtMax, tEnd);
+                // mcParticle.C:137: dt = min(dtMax, tEnd) with dtMax the initial tEnd; tEnd only decreases, so this is tEnd
+                double dt = tEnd;
                 V3 dx;
                 {
                     V3 dest = pos + dt * Utrack;
@@ -504,8 +529,6 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         V3 dest = pos + dt * Utrack;
                         constrainDir(MESH_GEOD3(M), dest);
                         pos = dest;
-                        w0 = p0 + q0; w1 = p1 + q1; w2 = p2 + q2; w3 = p3 + q3;
-                        haveW = true;
                         tf = 1.0;
                         break;
                     }
@@ -542,7 +565,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                             accS[baseAcc * K1_THREADS] -= mpd;
                             for (int cs = 0; cs < P.nConserved; ++cs) {
                                 const int sIdx = PRM_AT(P, conserved, cs);
-                                const double ph = (phase == 0) ? reloadD(A.in.phi[sIdx] + slot) : reloadD(A.out.phi[sIdx] + i);
+                                const double ph = (phase == 0) ? reloadInD(A.in.phi[sIdx] + slot) : reloadD(A.out.phi[sIdx] + i);
                                 accS[(baseAcc + 1 + cs) * K1_THREADS] -= mpd * ph;
                             }
                             status = 1;
@@ -562,7 +585,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         V3 Ur;
                         if (reflected) Ur = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
                         else if (MESH_AXISYM(M)) Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
-                        else Ur = mk(reloadD(A.in.ux + slot), reloadD(A.in.uy + slot), reloadD(A.in.uz + slot));
+                        else Ur = mk(reloadInD(A.in.ux + slot), reloadInD(A.in.uy + slot), reloadInD(A.in.uz + slot));
                         Ur = reflectVec(Ur, nw);
                         A.out.px[i] = Ur.x; A.out.py[i] = Ur.y; A.out.pz[i] = Ur.z;
                     } else {
@@ -579,8 +602,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 tEnd -= dt;
             }
             if (status != 0) break;
-            if (!haveW) baryAt(T, pos - ctr, w0, w1, w2, w3);   // zero-length track or ended on a boundary
             if (phase == 1) break;
+            // barycentric coordinates of the mid-point in its tet (oracle Cloud::baryWeights: the same expression)
+            double w0, w1, w2, w3;
+            baryAt(T, pos - ctr, w0, w1, w2, w3);
+            loadPts(M, tet, T);
 
             // ================= mid-point: E6, E7, E9 =================
             double Co = courantNo(M, cell, Utrack);
@@ -588,8 +614,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             V3 gradP;
             {
                 double pst[4];
-                const int2 pts = __ldg(M.tetPts + tet);
-                interpMid(M, P, A.nodeMid, T.face, pts.x, pts.y, cell, w0, w1, w2, w3, val, pst);
+                interpMid(M, P, A.nodeMid, T.face, T.ptB, T.ptC, cell, w0, w1, w2, w3, val, pst);
                 // gradInterpolationConstantTet: g_d*cell + g_b*ptB + g_c*ptC + g_a*face (the record is dead afterwards)
                 const V3 ga = mk(T.g0, T.g1, T.g2), gb = mk(T.g3, T.g4, T.g5), gc = mk(T.g6, T.g7, T.g8);
                 const V3 gdv = -((ga + gb) + gc);
@@ -598,11 +623,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             }
             const double *aux = A.cellAux + (size_t)cell * A.auxStride;
             // the particle's scalars, read again (see reloadD)
-            const double etaOld = reloadD(A.in.eta + slot);
-            double Omega = reloadD(A.in.omega + slot), rho = reloadD(A.in.rho + slot);
+            const double etaOld = reloadInD(A.in.eta + slot);
+            double Omega = reloadInD(A.in.omega + slot), rho = reloadInD(A.in.rho + slot);
             double phi[NPHI];
 #pragma unroll
-            for (int k = 0; k < NPHI; ++k) phi[k] = (k < nPhi) ? reloadD(A.in.phi[k] + slot) : 0.0;
+            for (int k = 0; k < NPHI; ++k) phi[k] = (k < nPhi) ? reloadInD(A.in.phi[k] + slot) : 0.0;
             const uint32_t id = (uint32_t)reloadI(reinterpret_cast<const int *>(A.in.id) + slot);
             // mcRASOmegaModel::correct
             if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
@@ -654,7 +679,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             // the velocity before the half step ("Uold") and the velocity the half step ended with
             V3 Uold;
             if (MESH_AXISYM(M)) Uold = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
-            else Uold = mk(reloadD(A.in.ux + slot), reloadD(A.in.uy + slot), reloadD(A.in.uz + slot));
+            else Uold = mk(reloadInD(A.in.ux + slot), reloadInD(A.in.uy + slot), reloadInD(A.in.uz + slot));
             V3 U = Uold;
             if (reflected) U = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
             // mcSLMFullVelocityModel::correct
@@ -671,7 +696,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 U = U + (((deltaU + 0.5 * Acoef * deltaU * dTp) + diffUap * deltaT) + (Ubefore - UFap) * aux[0] * deltaT);
                 Co = fmax(Co, Omega);
             }
-            CoKeep = Co;
+            park[3 * K1_THREADS] = Co;
             // local time stepping
             double eta;
             if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
@@ -680,8 +705,8 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             A.out.eta[i] = eta;
 
             // ---- E9: mid-point rule from the old position ----
-            pos = mk(reloadD(A.in.px + slot), reloadD(A.in.py + slot), reloadD(A.in.pz + slot));
-            tet = reloadI(A.in.tet + slot);
+            pos = mk(reloadInD(A.in.px + slot), reloadInD(A.in.py + slot), reloadInD(A.in.pz + slot));
+            tet = tet0;
             loadTet(M, tet, T);
             cell = cell0;
             double hNum;   // numerical-diffusion length of the start cell (mcParticleCloud.C:1937-1971)
@@ -708,7 +733,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 if (k < A.lostCap) { LostRec r; r.idx = (uint32_t)i; r.cell = cell; r.m = m; A.lostList[k] = r; }
                 accS[ACC_N_LOST * K1_THREADS] += 1;
             } else accS[ACC_N_DELETED * K1_THREADS] += 1;
-            A.keyOut[i] = KEY_DEAD; A.out.cell[i] = -1;
+            A.out.cell[i] = -1;
             continue;
         }
         // ---- E11: mcOpenBoundary::correct(true) ----
@@ -723,11 +748,8 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         // ---- write back in sorted order (the scalars were written at the mid-point) ----
         A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
         A.out.cell[i] = cell; A.out.tet[i] = tet;
-        // key: rank of the cell in the processing order (tetBits == 0: nothing else; the stable sort keeps
-        // the previous order inside a cell), else followed by the local tet
-        const uint32_t rank = (uint32_t)__ldg(M.cellRank + cell);
-        A.keyOut[i] = (MESH_TETBITS(M) == 0) ? rank
-                                             : ((rank << MESH_TETBITS(M)) | (uint32_t)(tet - __ldg(M.cellTetStart + cell)));
+        // (the sort key — rank of the cell in the processing order — is formed by the sort kernels from out.cell and
+        // out.tet, so that this kernel does not end on a dependent look-up)
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {
@@ -742,7 +764,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
             accM[ACC_ETAMAX * K1_THREADS] = fmax(accM[ACC_ETAMAX * K1_THREADS], eta);
             accM[ACC_NEG_ETAMIN * K1_THREADS] = fmax(accM[ACC_NEG_ETAMIN * K1_THREADS], -eta);
-            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], CoKeep);
+            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], park[3 * K1_THREADS]);
         }
     }
 

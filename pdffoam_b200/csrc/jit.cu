@@ -34,7 +34,7 @@ std::string hexDouble(double v) {
 }
 
 // the constants the kernel may rely on: the parameters k_evolve reads and the mesh flags
-std::string prologue(const pdfb200_params &p, bool axisym, bool hasOpen, int tetBits, const int geoD[3], const int solD[3]) {
+std::string prologue(const pdfb200_params &p, bool axisym, bool hasOpen, int tetBits, int cellFaces, const int geoD[3], const int solD[3]) {
     std::ostringstream o;
     o << "#define K1_JIT 1\n";
     // CTAs per SM the specialised kernel is compiled for (profiles/README.md)
@@ -43,6 +43,7 @@ std::string prologue(const pdfb200_params &p, bool axisym, bool hasOpen, int tet
     o << "#define JIT_AXISYM " << (axisym ? 1 : 0) << "\n";
     o << "#define JIT_HAS_OPEN " << (hasOpen ? 1 : 0) << "\n";
     o << "#define JIT_TETBITS " << tetBits << "\n";
+    o << "#define JIT_CELLFACES " << cellFaces << "\n";
     o << "#define JIT_NGEOD " << ((geoD[0] > 0) + (geoD[1] > 0) + (geoD[2] > 0)) << "\n";
     for (int k = 0; k < 3; ++k) o << "#define JIT_GEOD" << k << " (" << geoD[k] << ")\n#define JIT_SOLD" << k << " (" << solD[k] << ")\n";
     o << "#include \"cloud.hpp\"\n";
@@ -134,7 +135,7 @@ void *Cloud::specialisedKernel() {
         std::fprintf(stderr, "pdfb200: kernel sources not found in %s; running the generic particle kernel\n", dir.c_str());
         return nullptr;
     }
-    const std::string pro = prologue(prm, axisym, hasOpen, tetBits, dm.geoD, dm.solD);
+    const std::string pro = prologue(prm, axisym, hasOpen, tetBits, dm.cellFacesUniform, dm.geoD, dm.solD);
     std::string flags = "-cubin -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false";
     if (const char *x = std::getenv("PDFB200_JIT_FLAGS")) flags += std::string(" ") + x;   // tuning experiments (-DK1_...)
     const uint64_t h = fnv1a(srcA, fnv1a(srcH, fnv1a(srcC, fnv1a(srcK, fnv1a(flags, fnv1a(pro))))));
@@ -181,10 +182,10 @@ void Cloud::dropSpecialisedKernel() {
 // The translation unit specialisedKernel() would compile for these parameters and mesh flags
 // (host only, no device needed): lets the CPU test-suite check that the kernel source builds
 // under K1_JIT. Returns the length of the text, or -1 when it does not fit.
-extern "C" long pdfb200_jit_source(const pdfb200_params *p, int axisym, int hasOpen, int tetBits, const int32_t geoD[3],
-                                   const int32_t solD[3], char *buf, long bufLen) {
+extern "C" long pdfb200_jit_source(const pdfb200_params *p, int axisym, int hasOpen, int tetBits, int cellFacesUniform,
+                                   const int32_t geoD[3], const int32_t solD[3], char *buf, long bufLen) {
     const int g[3] = {geoD[0], geoD[1], geoD[2]}, sd[3] = {solD[0], solD[1], solD[2]};
-    const std::string t = prologue(*p, axisym != 0, hasOpen != 0, tetBits, g, sd);
+    const std::string t = prologue(*p, axisym != 0, hasOpen != 0, tetBits, cellFacesUniform, g, sd);
     if ((long)t.size() + 1 > bufLen) return -1;
     std::memcpy(buf, t.c_str(), t.size() + 1);
     return (long)t.size();

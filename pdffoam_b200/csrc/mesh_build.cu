@@ -448,6 +448,11 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     // ---- fill the device mesh view ----
     dm.nCells = nCells; dm.nFaces = nFaces; dm.nInternalFaces = nInternalFaces; dm.nPoints = nPoints; dm.nBnd = nBnd;
     dm.nPatches = m.nPatches; dm.nTets = nTets; dm.tetBits = tetBits;
+    {
+        int nF = hCFS[1] - hCFS[0];
+        for (int c = 1; c < nCells && nF > 0; ++c) if (hCFS[c + 1] - hCFS[c] != nF) nF = 0;
+        dm.cellFacesUniform = nF;
+    }
     for (int k = 0; k < 3; ++k) { dm.geoD[k] = m.geometricD[k]; dm.solD[k] = m.solutionD[k]; dm.axis[k] = axis[k]; dm.centreNormal[k] = centreNormal[k]; }
     dm.nGeoD = nGeoD; dm.axisym = axisym; dm.openingAngle = openingAngle;
     dm.points = points.p; dm.faceStart = faceStart.p; dm.facePoints = facePoints.p; dm.owner = owner.p; dm.neighbour = neighbour.p;

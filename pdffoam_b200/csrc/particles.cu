@@ -148,9 +148,16 @@ __global__ void k_cell_bounds(int n, const uint32_t *keys, int tetBits, const in
 // stable sort by cell produces (what cub::DeviceRadixSort::SortPairs gave in three 8-bit passes
 // over 1 GB each), at one pass over the keys per kernel.
 // ---------------------------------------------------------------------------
-__global__ void k_cs_hist(int n, const uint32_t *keys, int *count) {
+// (forms the key — the rank of the particle's new cell in the processing order — from the state the particle
+// kernel has just written, and keeps it for the scatter)
+__global__ void k_cs_hist(int n, const int *cell, const int *cellRank, uint32_t *keys, int *count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t key = i < n ? keys[i] : KEY_DEAD;
+    uint32_t key = KEY_DEAD;
+    if (i < n) {
+        const int c = cell[i];
+        if (c >= 0) key = (uint32_t)__ldg(cellRank + c);
+        keys[i] = key;
+    }
     const unsigned m = __match_any_sync(0xffffffffu, key);
     if (key != KEY_DEAD && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(count + key, __popc(m));
 }
@@ -235,6 +242,19 @@ __global__ void k_cs_order(int nCells, const int *rankStart, const int *count, c
             __syncwarp();
         }
     }
+}
+
+// sort key of the radix path: (rank of the cell << tetBits) | local tet
+__global__ void k_make_keys(DMesh M, int n, const int *cell, const int *tet, uint32_t *keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell[i];
+    uint32_t key = KEY_DEAD;
+    if (c >= 0) {
+        key = (uint32_t)__ldg(M.cellRank + c);
+        if (M.tetBits > 0) key = (key << M.tetBits) | (uint32_t)(tet[i] - __ldg(M.cellTetStart + c));
+    }
+    keys[i] = key;
 }
 
 __global__ void k_cs_finish(const int *total, StepScalars *sc) {
@@ -1295,7 +1315,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         // ---- the fused particle kernel ----
         K1Args A;
         A.M = dm; A.P = prm; A.in = S[cur]; A.out = S[cur ^ 1];
-        A.perm = valsB.p; A.keyOut = keysA.p; A.sc = scal.p;
+        A.perm = valsB.p; A.sc = scal.p;
         A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride;
         A.Un = Un.p; A.lostShare = lostShare.p; A.lostList = lostList.p; A.lostCount = lostCount.p; A.lostCap = (unsigned)lostList.n;
         A.injPatchTail = injPatchTail.p;
@@ -1326,7 +1346,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             // counting sort by cell (see k_cs_*): same permutation as the stable radix sort
             CUDA_CHECK(cudaMemsetAsync(csCount.p, 0, nCells * sizeof(int), stream));
             CUDA_CHECK(cudaMemsetAsync(csCursor.p, 0, nCells * sizeof(int), stream));
-            if (total > 0) LAUNCH(this, k_cs_hist, gridFor(total, 256), 256, 0, total, keysA.p, csCount.p);
+            if (total > 0) LAUNCH(this, k_cs_hist, gridFor(total, 256), 256, 0, total, S[cur].cell, cellRank.p, keysA.p, csCount.p);
             scanInts(*this, nCells, csCount.p, csStart.p, scanTmp.p + 2);
             if (total > 0) LAUNCH(this, k_cs_scatter, gridFor(total, 256), 256, 0, total, keysA.p, csStart.p, csCursor.p, valsB.p);
             mark(3);
@@ -1336,8 +1356,10 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         } else {
             // radix sort by (cell, tet)
             size_t tempBytes = cubTemp.n;
-            if (total > 0)
+            if (total > 0) {
+                LAUNCH(this, k_make_keys, gridFor(total, 256), 256, 0, dm, total, S[cur].cell, S[cur].tet, keysA.p);
                 CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
+            }
             mark(3);
             CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
             CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
