@@ -202,6 +202,10 @@ typedef struct pdfb200_cell_fields {
 
 typedef struct pdfb200_cloud pdfb200_cloud;   /* opaque handle */
 
+/* (the types above are also read by the kernel source when the library specialises it at run time with
+ * NVRTC, which accepts no host function declarations: the entry points are hidden from that compiler) */
+#ifndef __CUDACC_RTC__
+
 /* Last error message of the calling thread ("" if none). Replaces
  * FatalErrorIn(...) << exit(FatalError) (process abort) in the reference.   */
 const char *pdfb200_last_error(void);
@@ -303,6 +307,15 @@ double pdfb200_last_evolve_ms(pdfb200_cloud *cloud);
  * (host only, no device needed; the CPU test-suite builds it); length of the text or -1. */
 long pdfb200_jit_source(const pdfb200_params *params, int axisym, int hasOpen, int tetBits, int cellFacesUniform,
                         const int32_t geometricD[3], const int32_t solutionD[3], char *buf, long bufLen);
+
+/* Compiles that translation unit exactly as the first evolve() does — kernel sources embedded in the
+ * library at build time, NVRTC in memory (libnvrtc is dlopen'ed), `nvcc -cubin` in a private temporary
+ * directory when NVRTC is missing — without needing a device. compiler: 0 = first available, 1 = NVRTC,
+ * 2 = nvcc. Returns the size of the cubin or -1; the compiler's messages go to log.                  */
+long pdfb200_jit_compile(const pdfb200_params *params, int axisym, int hasOpen, int tetBits, int cellFacesUniform,
+                         const int32_t geometricD[3], const int32_t solutionD[3], int compiler, char *log, long logLen);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

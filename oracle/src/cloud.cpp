@@ -175,15 +175,22 @@ static inline Vec3 reflectVec(const Vec3 &v, const Vec3 &n) {
 // mcParticle::hitPatch (mcParticle.C:211-235) -> mcParticleCloud::hitPatch
 // (mcParticleCloudI.H:211-230) -> mcSlipBoundary::hitPatch (.C:61-79) /
 // mcOpenBoundary::hitPatch (.C:159-205).
-void Cloud::hitPatch(Particle &p, int face) {
+bool Cloud::hitPatch(Particle &p, int face) {
     const int bf = face - mesh.nInternalFaces;
     const int patchI = mesh.facePatch[bf];
     const Patch &pp = mesh.patches[patchI];
+    if (pp.geom == PDFB200_PATCH_WEDGE && mesh.nGeometricD() < 3) {
+        // mcParticle.C:220-224: a wedge patch snaps the position back onto the centre plane and the track
+        // carries on from there; the tet of the snapped point is found with the shared locate rule.
+        mesh.constrainDirection(mesh.geometricD, p.position);
+        p.tet = mesh.locate(p.position, p.cell);
+        return true;
+    }
     if (pp.geom != PDFB200_PATCH_GENERIC || pp.handler == PDFB200_BC_EMPTY) {
-        // wedge/empty faces cannot be reached by a centre-plane track;
-        // mcEmptyBoundary aborts (.C:90-104). Treated as a lost particle.
+        // mcEmptyBoundary aborts the run (.C:61-104); a wedge patch of a 3-D mesh (nothing to snap) makes the
+        // reference spin until nSteps > 1000 and drop the particle (mcParticle.C:147-158). Both end as a lost particle.
         lostMass[p.cell] += p.m; ++nLost; p.keep = false;
-        return;
+        return false;
     }
     const Vec3 nw = mesh.faceAreas[face] / mesh.magSf[face];
     if (pp.handler == PDFB200_BC_SLIP) {
@@ -191,7 +198,7 @@ void Cloud::hitPatch(Particle &p, int face) {
         p.Ucorrection = reflectVec(p.Ucorrection, nw);
         p.Utracking = reflectVec(p.Utracking, nw);
         p.reflected = true;
-        return;
+        return false;
     }
     // open / inletOutlet
     if (Un[bf] < 0) {
@@ -199,14 +206,14 @@ void Cloud::hitPatch(Particle &p, int face) {
         patchMassIn[patchI][0] -= mpd;
         for (int cs = 0; cs < prm.nConserved; ++cs) patchMassIn[patchI][cs + 1] -= mpd * p.Phi[prm.conserved[cs]];
         p.keep = false; ++nDeleted;
-        return;
+        return false;
     }
     if (!pp.reflecting) {
         const double mpd = massPerDepth(p);
         patchMassOut[patchI][0] -= mpd;
         for (int cs = 0; cs < prm.nConserved; ++cs) patchMassOut[patchI][cs + 1] -= mpd * p.Phi[prm.conserved[cs]];
         p.keep = false; ++nDeleted;
-        return;
+        return false;
     }
     p.UParticle = reflectVec(p.UParticle, nw);
     p.Ucorrection = reflectVec(p.Ucorrection, nw);
@@ -214,6 +221,7 @@ void Cloud::hitPatch(Particle &p, int face) {
     p.reflected = true;
     p.reflectedAtOpenBoundary = true;
     p.reflectionBoundaryVelocity = nw * Un[bf];
+    return false;
 }
 
 // mcParticle::move (mcParticle.C:100-179). OpenFOAM's trackToFace is replaced
@@ -280,8 +288,7 @@ bool Cloud::move(Particle &p, double tdTrackTime) {
             s = std::min(1.0, std::max(0.0, s));
             p.position = x0 + s * dx;
             tf = s;
-            hitPatch(p, T.face);
-            entry = 3;
+            entry = hitPatch(p, T.face) ? -1 : 3;   // relocated on the centre plane: no entry face
             break;
         }
         if (!p.keep) break;
@@ -752,7 +759,8 @@ void Cloud::particleNumberControl() {
             if (nRanks > 1) n = (int)std::min<double>(nLocal[c], std::floor((double)n * nLocal[c] / npGlobal + 0.5));
             auto &lst = addr[c];
             std::sort(lst.begin(), lst.end(), [&](size_t a, size_t b) {
-                const double ma = particles[a].eta * particles[a].m, mb = particles[b].eta * particles[b].m;
+                // weights rounded to single precision, ties by id: see cloneWeight in pdffoam_b200/csrc/particles.cu
+                const float ma = (float)(particles[a].eta * particles[a].m), mb = (float)(particles[b].eta * particles[b].m);
                 if (ma != mb) return ma > mb;
                 return particles[a].id < particles[b].id;
             });

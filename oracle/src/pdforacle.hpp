@@ -350,7 +350,7 @@ struct Cloud {
     void constrainParticle(double dt, Particle &p) const; // mcParticleCloud.C:76-101
     void computeCourantNo(Particle &p) const;           // mcParticleCloud.C:2120-2148
     bool move(Particle &p, double trackTimeGlobal);     // mcParticle.C:100-179 on the tet walk
-    void hitPatch(Particle &p, int face);               // mcParticle.C:211-235 -> handlers
+    bool hitPatch(Particle &p, int face);               // mcParticle.C:211-235 -> handlers; true: snapped + relocated (wedge)
     void boundaryCorrectBefore();                       // mcOpenBoundary/mcInletOutletBoundary::correct(false)
     void injectPatch(int patchI);
     void cullPatch(int patchI);

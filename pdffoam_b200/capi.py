@@ -160,6 +160,16 @@ def _u32p(a: Optional[np.ndarray]):
     return a.ctypes.data_as(c_uint32_p)
 
 
+def jit_compile(lib: "Library", params: Params, axisym: bool, has_open: bool, tet_bits: int = 0,
+                geometric_d=(1, 1, 1), solution_d=(1, 1, 1), cell_faces: int = 6, compiler: int = 0):
+    """Compile the specialised kernel for these parameters the way the library does at the first step
+    (embedded sources; compiler 0 = first available, 1 = NVRTC, 2 = nvcc); host only. -> (cubin size or -1, log)"""
+    buf = C.create_string_buffer(1 << 16)
+    g = np.asarray(geometric_d, np.int32); sd = np.asarray(solution_d, np.int32)
+    n = lib.fn("jit_compile")(C.byref(params), int(axisym), int(has_open), int(tet_bits), int(cell_faces), _ip(g), _ip(sd), int(compiler), buf, len(buf))
+    return int(n), buf.value.decode(errors="replace")
+
+
 class PdfError(RuntimeError):
     """Raised when a C-ABI call returns a non-zero status (the reference would
     FatalErrorIn(...) << exit(FatalError))."""
@@ -171,7 +181,7 @@ API_SYMBOLS = [
     "upload_cloud_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
-    "kernel_launches", "last_evolve_ms", "profile", "jit_source", "rng_probe",
+    "kernel_launches", "last_evolve_ms", "profile", "jit_source", "jit_compile", "rng_probe",
 ]
 
 
@@ -226,6 +236,9 @@ class Library:
         if self.has("jit_source"):
             f("jit_source").argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_char_p, C.c_long]
             f("jit_source").restype = C.c_long
+        if self.has("jit_compile"):
+            f("jit_compile").argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, c_int32_p, c_int32_p, C.c_int, C.c_char_p, C.c_long]
+            f("jit_compile").restype = C.c_long
 
     def check(self, status: int, what: str):
         if status != 0:

@@ -110,6 +110,14 @@ void Cloud::create(const pdfb200_mesh &m, const pdfb200_params &p, int dev, int6
     buildMesh(m);
 }
 
+// mcSteadyFlamelet's constructor fails cleanly when its library is missing or too small (mcSteadyFlamelet.C:120-286);
+// the kernels index the tables without bounds checks, so the same is demanded before anything runs
+void Cloud::requireTables() const {
+    if (prm.reactionModel != PDFB200_REACTION_STEADY_FLAMELET) return;
+    if (nChi < 1 || nZ < 2) throw std::invalid_argument("SteadyFlamelet selected but no flamelet tables were set (pdfb200_set_flamelet_tables)");
+    if (nFlFields < 1 + prm.nAdded) throw std::invalid_argument("SteadyFlamelet: the flamelet library holds fewer tables than rho + the added scalars");
+}
+
 void Cloud::setTables(int nChi_, int nZ_, const double *chi, const double *z, int nFields, const double *const *fields) {
     // sanity checks of mcSteadyFlamelet's constructor (mcSteadyFlamelet.C:222-286)
     if (nZ_ < 2) throw std::invalid_argument("flamelet z must have at least 2 elements");
@@ -170,7 +178,9 @@ int pdfb200_set_delta_t(pdfb200_cloud *c, double dt) {
     USE_DEVICE(c);
     return guarded([&] {
         Cloud &C = c->c;
+        if (!(dt > 0)) throw std::invalid_argument("set_delta_t: the time step must be positive");
         C.deltaTHost = dt;
+        C.hScal->deltaT = dt;   // seed/upload push the whole mirror back to the device
         CUDA_CHECK(cudaMemcpy(&C.scal.p->deltaT, &dt, sizeof(double), cudaMemcpyHostToDevice));
     });
 }
@@ -195,11 +205,11 @@ int pdfb200_download_tets(pdfb200_cloud *c, double *gradN, int32_t *nbr, int32_t
         const size_t n = (size_t)C.nTets;
         std::vector<TetA> hA(n);
         std::vector<D4> hB(n), hC(n);
-        std::vector<int2> hP(n);
+        std::vector<D4> hP(n);
         CUDA_CHECK(cudaMemcpy(hA.data(), C.tetA.p, n * sizeof(TetA), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(hB.data(), C.tetB.p, n * sizeof(D4), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(hC.data(), C.tetC.p, n * sizeof(D4), cudaMemcpyDeviceToHost));
-        CUDA_CHECK(cudaMemcpy(hP.data(), C.tetPts.p, n * sizeof(int2), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(hP.data(), C.tetD.p, n * sizeof(D4), cudaMemcpyDeviceToHost));
         if (cell) CUDA_CHECK(cudaMemcpy(cell, C.tetCell.p, n * sizeof(int), cudaMemcpyDeviceToHost));
         for (size_t t = 0; t < n; ++t) {
             if (gradN) {
@@ -209,8 +219,8 @@ int pdfb200_download_tets(pdfb200_cloud *c, double *gradN, int32_t *nbr, int32_t
             }
             if (nbr) for (int k = 0; k < 4; ++k) nbr[4 * t + k] = hA[t].nbr[k];
             if (faceLabel) faceLabel[t] = hA[t].face;
-            if (ptB) ptB[t] = hP[t].x;
-            if (ptC) ptC[t] = hP[t].y;
+            if (ptB) ptB[t] = tetPtsOf(hP[t]).x;
+            if (ptC) ptC[t] = tetPtsOf(hP[t]).y;
         }
     });
 }

@@ -35,30 +35,7 @@ struct HostPatch { int start, size, geom, handler, reflecting; };
 // number of doubles in the trailing global section of the moment block
 #define BLOCK_TAIL 32
 
-// layout of the particle kernel's per-thread accumulators
-#ifndef K1_THREADS
-#define K1_THREADS 128
-#endif
-#define K1_JIT_MIN_BLOCKS 5   // CTAs per SM the run-time specialised kernel is compiled for (96 registers; measured best of 3..6)
-#ifndef K1_MAXCONS
-#define K1_MAXCONS 3
-#endif
-#define K1_NC1 (1 + K1_MAXCONS)
-// thread-private shared-memory accumulators
-#define ACC_DM_MINUS 0
-#define ACC_DM_PLUS (ACC_DM_MINUS + K1_NC1)
-#define ACC_MASS_IN (ACC_DM_PLUS + K1_NC1)
-#define ACC_MASS_OUT (ACC_MASS_IN + K1_NC1)
-#define ACC_N_DELETED (ACC_MASS_OUT + K1_NC1)
-#define ACC_N_LOST (ACC_N_DELETED + 1)
-#define ACC_N_ALIVE (ACC_N_LOST + 1)
-#define ACC_NSUM (ACC_N_ALIVE + 1)
-#define ACC_UMAX 0
-#define ACC_UCORRMAX 1
-#define ACC_ETAMAX 2
-#define ACC_NEG_ETAMIN 3
-#define ACC_COMAX 4
-#define ACC_NMAX 5
+#include "k1_layout.h"
 
 struct NcclApi;   // dlopen'ed NCCL entry points (comm.cu)
 
@@ -96,8 +73,7 @@ struct Cloud {
     DBuf<int> faceStart, facePoints, owner, neighbour, cellFaceStart, cellFaces, cellTetStart, faceTetStartOwn,
         faceTetStartNei, pointCellStart, pointCells, bfInfo, openCellStart, openCellFaces, cellRank, cellOfRank;
     DBuf<TetA> tetA;
-    DBuf<D4> tetB, tetC, cellCo4;
-    DBuf<int2> tetPts;
+    DBuf<D4> tetB, tetC, tetD, cellCo4;
     DBuf<int> tetCell;
 
     // ---- fields ----
@@ -132,7 +108,7 @@ struct Cloud {
     DBuf<int> injPatchTail;
     DBuf<unsigned char> cubTemp;
     DBuf<int> cellStart, cellEnd, ncFlag, ncCount, ncOffset, scanTmp, scanTileSums, scanTileOffs;
-    DBuf<int> injCount, injOffset, csCount, csCursor, csStart;
+    DBuf<int> injCount, injOffset, csCount, csCursor, csStart, ncCounts;
     DBuf<double> injSums;
     DBuf<double> k1PartSum, k1PartMax, cellPartSum, finalSums;   // deterministic reductions
     DBuf<double> ncDelta, cloneDelta;   // cloneDelta: [capacity][K1_NC1], axisymmetric cases only
@@ -161,6 +137,7 @@ struct Cloud {
     void buildMesh(const pdfb200_mesh &m);            // mesh_build.cu
     void chooseSortKey();                             // mesh_build.cu
     void setParams(const pdfb200_params &p);
+    void requireTables() const;
     void setTables(int nChi, int nZ, const double *chi, const double *z, int nFields, const double *const *fields);
     void uploadFv(const pdfb200_fv_fields &f);
     void uploadCloudFields(const pdfb200_cloud_fields &f);

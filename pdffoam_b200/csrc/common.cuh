@@ -10,8 +10,11 @@
 //   * per-cell moment block [nCells][nMom] (the buffer that is all-reduced).
 #pragma once
 
+// (also compiled by NVRTC at run time, jit.cu: the toolkit and C library headers are replaced by empty
+// stand-ins there, NVRTC has the device API built in)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/pdfb200.h"
 
@@ -41,8 +44,11 @@
 // cell's 24 chunks instead of one line per lane: the L1 cost of a record gather is the number of
 // distinct 128-byte lines per load instruction, and it was what bounded the particle kernel in
 // round 1 (one 128-byte record per tet: 4 loads x up to 32 lines).
-// Point labels of b and c (only needed by the interpolations) live in DMesh::tetPts, the centre of
-// the cell (vertex d) in DMesh::cellCentre4.
+// A fourth plane, D[t] = { gd.x, gd.y, gd.z, (ptB, ptC) }, is read once per particle at the mid-point: the
+// gradient of vertex d as richTetrahedron stores it (Sd/(-3V), richTetrahedronI.H:107-134 — not the
+// negated sum of the other three, which differs in the last bit and, multiplied by absolute pressures
+// of 1e5, showed up at 1e-9 in grad p*) and the global point labels of b and c that the interpolations
+// need. The centre of the cell (vertex d) is in DMesh::cellCentre4.
 struct __align__(32) TetA {
     int nbr[4];       // tet across the face opposite a, b, c, d (-1: boundary)
     int face;         // mesh face the tet stands on (tetFace_)
@@ -54,6 +60,12 @@ static_assert(sizeof(TetA) == 32, "TetA must be one 32-byte sector");
 // 256-bit read-only global load (SASS: LDG.E.ENL2.256.CONSTANT, new on sm_100): one instruction per
 // 32-byte chunk. The address must be 32-byte aligned.
 struct __align__(32) D4 { double x, y, z, w; };
+// point labels of b and c from plane D of the tet table
+__host__ __device__ inline int2 tetPtsOf(const D4 &d) {
+    long long bits;
+    memcpy(&bits, &d.w, sizeof(bits));
+    return make_int2((int)(bits & 0xffffffffll), (int)(bits >> 32));
+}
 __device__ __forceinline__ D4 ld256(const void *p) {
     D4 r;
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
@@ -135,7 +147,7 @@ struct DMesh {
     const int *pointCellStart, *pointCells; const double *pointWeights;
     const TetA *tetA;            // tet table, three planes of 32-byte chunks (see TetA)
     const D4 *tetB, *tetC;
-    const int2 *tetPts;          // global point labels of b and c
+    const D4 *tetD;              // gradN of d + global point labels of b and c (packed in .w)
     const int *tetCell;          // cell of each tet (the particle kernel tracks it instead)
     // boundary faces
     const int *bfInfo;           // handler | reflecting<<4 | geom<<8 | patch<<16
@@ -308,6 +320,7 @@ __device__ inline void blockReduce(double (&v)[N], double *smem /* [N*32] */) {
     __syncthreads();
 }
 
+#ifndef __CUDACC_RTC__
 #define CUDA_CHECK(expr)                                                              \
     do {                                                                              \
         cudaError_t _e = (expr);                                                      \
@@ -323,3 +336,4 @@ struct CudaError : std::runtime_error {
         : std::runtime_error(std::string(cudaGetErrorString(e)) + " in " + expr + " at " + file + ":" + std::to_string(line)), code(e) {}
 };
 #endif
+#endif   // !__CUDACC_RTC__

@@ -20,6 +20,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "k1_layout.h"
 
 // Compile-time knowledge of the run. The kernel is built twice from this one source: ahead of
 // time with the mesh flags and model parameters read at run time (k_evolve<NPHI>, below), and at
@@ -76,7 +77,8 @@ struct K1Args {
 struct TetL {
     int n0, n1, n2, n3;          // neighbours across the faces opposite a, b, c, d
     int face, nbrCell;           // mesh face of the tet, cell across it
-    int ptB, ptC;                // global point labels of b and c
+    int ptB, ptC;                // global point labels of b and c      } plane D, loaded where an
+    double gd0, gd1, gd2;        // gradN of d (richTetrahedron's own)  } interpolation needs it (loadPts)
     double g0, g1, g2, g3, g4, g5, g6, g7, g8;   // gradN of a, b, c
 };
 
@@ -90,8 +92,9 @@ __device__ __forceinline__ void loadTet(const DMesh &M, int t, TetL &T) {
 }
 
 __device__ __forceinline__ void loadPts(const DMesh &M, int t, TetL &T) {
-    const int2 pts = __ldg(M.tetPts + t);
-    T.ptB = pts.x; T.ptC = pts.y;
+    const D4 d = ld256(M.tetD + t);
+    T.gd0 = d.x; T.gd1 = d.y; T.gd2 = d.z;
+    T.ptB = __double2loint(d.w); T.ptC = __double2hiint(d.w);
 }
 
 // centre of a cell (vertex d of its tets) and its numerical-diffusion length: one 256-bit load
@@ -553,6 +556,17 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     const int bf = T.face - M.nInternalFaces;
                     const int info = __ldg(M.bfInfo + bf);
                     const int handler = BF_HANDLER(info);
+                    if (MESH_NGEOD(M) < 3 && BF_GEOM(info) == PDFB200_PATCH_WEDGE) {
+                        // mcParticle.C:220-224: a wedge patch snaps the position back onto the centre plane and the
+                        // track carries on from there, in the tet the shared locate rule gives for the snapped point
+                        constrainDir(MESH_GEOD3(M), pos);
+                        tet = locateTet(M, pos, cell);
+                        loadTet(M, tet, T);
+                        entry = -1;
+                        break;
+                    }
+                    // an empty patch aborts the reference (mcEmptyBoundary.C:61-104); a wedge patch of a 3-D mesh makes it
+                    // spin past 1000 sub-steps and drop the particle (mcParticle.C:147-158): both end as a lost particle
                     if (BF_GEOM(info) != PDFB200_PATCH_GENERIC || handler == PDFB200_BC_EMPTY) { status = 2; break; }
                     const double4 n4 = M.bfNormal[bf];
                     const V3 nw = mk(n4.x, n4.y, n4.z);
@@ -617,7 +631,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 interpMid(M, P, A.nodeMid, T.face, T.ptB, T.ptC, cell, w0, w1, w2, w3, val, pst);
                 // gradInterpolationConstantTet: g_d*cell + g_b*ptB + g_c*ptC + g_a*face (the record is dead afterwards)
                 const V3 ga = mk(T.g0, T.g1, T.g2), gb = mk(T.g3, T.g4, T.g5), gc = mk(T.g6, T.g7, T.g8);
-                const V3 gdv = -((ga + gb) + gc);
+                const V3 gdv = mk(T.gd0, T.gd1, T.gd2);
                 gradP = (gdv * pst[3] + gb * pst[1]) + gc * pst[2];
                 gradP = gradP + ga * pst[0];
             }

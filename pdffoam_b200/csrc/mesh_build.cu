@@ -95,7 +95,7 @@ __global__ void k_build_tets(int nCells, int nInternalFaces, const int *cellFace
                              const int *cellTetStart, const int *faceTetStartOwn, const int *faceTetStartNei,
                              const int *owner, const int *faceStart, const int *facePoints, const double *points,
                              const int *neighbour, const double *faceCentres, const double4 *cellCentre4, TetA *tetA, D4 *tetB, D4 *tetC,
-                             int2 *tetPts, int *tetCell) {
+                             D4 *tetD, int *tetCell) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCells) return;
     const double4 cc = cellCentre4[c];
@@ -116,11 +116,14 @@ __global__ void k_build_tets(int nCells, int nInternalFaces, const int *cellFace
             const V3 Sa = 0.5 * cross3(cpt - b, d - b);
             const V3 Sb = 0.5 * cross3(d - a, cpt - a);
             const V3 Sc = 0.5 * cross3(b - a, d - a);
+            const V3 Sd = 0.5 * cross3(cpt - a, b - a);
             const double vol = (1.0 / 6.0) * dot3(cross3(b - a, cpt - a), d - a);
             double g[9];
+            D4 d4; d4.x = d4.y = d4.z = 0;
             if (vol > 0) {
                 const double den = -3. * vol;
-                const V3 ga = Sa / den, gb = Sb / den, gc = Sc / den;
+                const V3 ga = Sa / den, gb = Sb / den, gc = Sc / den, gd = Sd / den;
+                d4.x = gd.x; d4.y = gd.y; d4.z = gd.z;
                 g[0] = ga.x; g[1] = ga.y; g[2] = ga.z;
                 g[3] = gb.x; g[4] = gb.y; g[5] = gb.z;
                 g[6] = gc.x; g[7] = gc.y; g[8] = gc.z;
@@ -140,17 +143,18 @@ __global__ void k_build_tets(int nCells, int nInternalFaces, const int *cellFace
             b4.x = g[1]; b4.y = g[2]; b4.z = g[3]; b4.w = g[4];
             c4.x = g[5]; c4.y = g[6]; c4.z = g[7]; c4.w = g[8];
             tetB[t] = b4; tetC[t] = c4;
-            tetPts[t] = make_int2(ptBI, ptCI);
+            d4.w = __hiloint2double(ptCI, ptBI);
+            tetD[t] = d4;
             tetCell[t] = c;
         }
     }
     // the other face of this cell sharing mesh edge (b,c)
     for (int t1 = tBegin; t1 < tEnd; ++t1) {
-        const int2 p1 = tetPts[t1];
+        const int2 p1 = tetPtsOf(tetD[t1]);
         const int lo1 = min(p1.x, p1.y), hi1 = max(p1.x, p1.y);
         for (int t2 = tBegin; t2 < tEnd; ++t2) {
             if (t2 == t1) continue;
-            const int2 p2 = tetPts[t2];
+            const int2 p2 = tetPtsOf(tetD[t2]);
             if (min(p2.x, p2.y) == lo1 && max(p2.x, p2.y) == hi1) { tetA[t1].nbr[0] = t2; break; }
         }
     }
@@ -342,7 +346,7 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     courantCoeffs.alloc((size_t)nFaces * 3); cellCo4.alloc(hCF.size());
     linWeights.alloc(std::max(nInternalFaces, 1)); pointWeights.alloc(hPC.size());
     bfNormal.alloc(nBnd);
-    tetA.alloc((size_t)nTets); tetB.alloc((size_t)nTets); tetC.alloc((size_t)nTets); tetPts.alloc((size_t)nTets); tetCell.alloc((size_t)nTets);
+    tetA.alloc((size_t)nTets); tetB.alloc((size_t)nTets); tetC.alloc((size_t)nTets); tetD.alloc((size_t)nTets); tetCell.alloc((size_t)nTets);
 
     const int B = 128;
     LAUNCH(this, k_face_geom, gridFor(nFaces, B), B, 0, nFaces, faceStart.p, facePoints.p, points.p, faceCentres.p, faceAreas.p, magSf.p);
@@ -350,7 +354,7 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
            points.p, faceCentres.p, faceAreas.p, cellCentre4.p, cellVolumes.p, bbMin.p, bbMax.p, m.geometricD[0], m.geometricD[1], m.geometricD[2]);
     LAUNCH(this, k_build_tets, gridFor(nCells, 64), 64, 0, nCells, nInternalFaces, cellFaceStart.p, cellFaces.p, cellTetStart.p,
            faceTetStartOwn.p, faceTetStartNei.p, owner.p, faceStart.p, facePoints.p, points.p, neighbour.p, faceCentres.p, cellCentre4.p,
-           tetA.p, tetB.p, tetC.p, tetPts.p, tetCell.p);
+           tetA.p, tetB.p, tetC.p, tetD.p, tetCell.p);
     LAUNCH(this, k_point_weights, gridFor(nPoints, B), B, 0, nPoints, pointCellStart.p, pointCells.p, points.p, cellCentre4.p, pointWeights.p);
     LAUNCH(this, k_face_tables, gridFor(nFaces, B), B, 0, nFaces, nInternalFaces, owner.p, neighbour.p, faceCentres.p, faceAreas.p,
            magSf.p, cellCentre4.p, bfInfo.p, linWeights.p, courantCoeffs.p, bfNormal.p);
@@ -463,7 +467,7 @@ void Cloud::buildMesh(const pdfb200_mesh &m) {
     dm.cellVolumes = cellVolumes.p; dm.volumeOrArea = volumeOrArea.p; dm.bbMin = bbMin.p; dm.bbMax = bbMax.p;
     dm.courantCoeffs = courantCoeffs.p; dm.cellCo4 = cellCo4.p; dm.linWeights = linWeights.p;
     dm.pointCellStart = pointCellStart.p; dm.pointCells = pointCells.p; dm.pointWeights = pointWeights.p;
-    dm.tetA = tetA.p; dm.tetB = tetB.p; dm.tetC = tetC.p; dm.tetPts = tetPts.p; dm.tetCell = tetCell.p; dm.bfInfo = bfInfo.p; dm.bfNormal = bfNormal.p;
+    dm.tetA = tetA.p; dm.tetB = tetB.p; dm.tetC = tetC.p; dm.tetD = tetD.p; dm.tetCell = tetCell.p; dm.bfInfo = bfInfo.p; dm.bfNormal = bfNormal.p;
     dm.openCellStart = openCellStart.p; dm.openCellFaces = openCellFaces.p; dm.patchFaceT = patchFaceT.p;
     CUDA_CHECK(cudaStreamSynchronize(s));
 }

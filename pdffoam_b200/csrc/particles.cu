@@ -477,7 +477,7 @@ __global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const 
     double w0, w1, w2, w3;
     baryAt(T, pos - cellCentre(M, cell), w0, w1, w2, w3);
     double val[NODE_MID_STRIDE], pst[4];
-    const int2 pts = M.tetPts[tet];
+    const int2 pts = tetPtsOf(M.tetD[tet]);
     interpMid(M, P, nodeMid, T.face, pts.x, pts.y, cell, w0, w1, w2, w3, val, pst);
     double eta = 1.0;
     if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
@@ -659,7 +659,7 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
                     loadTet(M, tet, TL);
                     double w0, w1, w2, w3, val[NODE_MID_STRIDE], pst[4];
                     baryAt(TL, pos - cellCentre(M, cellI), w0, w1, w2, w3);
-                    const int2 pts = M.tetPts[tet];
+                    const int2 pts = tetPtsOf(M.tetD[tet]);
                     interpMid(M, P, nodeMid, TL.face, pts.x, pts.y, cellI, w0, w1, w2, w3, val, pst);
                     eta = val[NM_ETA];
                 } else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) {
@@ -722,12 +722,20 @@ __global__ void k_inject_finish(int nBnd, const int *total, StepScalars *sc, lon
     int t = *total;
     if ((long long)sc->nSlots + sc->nTail + t > capacity) { sc->overflow = 1; t = max(0, (int)(capacity - sc->nSlots - sc->nTail)); }
     sc->nTail += t;
+    // ids are 32 bits wide: running out of them must stop the run, not hand two particles one random stream
+    if ((unsigned long long)sc->nextId + (unsigned long long)t * (unsigned long long)nRanks > 0xffffffffull) sc->overflow = 3;
     sc->nextId += (uint32_t)t * (uint32_t)nRanks;
 }
 
 // ---------------------------------------------------------------------------
 // particle-number control (mcParticleCloud.C:1014-1221)
 // ---------------------------------------------------------------------------
+// The weight the clone selection ranks by: eta*m rounded to single precision. The reference sorts by the
+// double product and leaves the order of equal weights to std::sort; freshly seeded or injected particles of a
+// cell carry m = rho V / (Npc eta), i.e. products that agree to the last bit or two, so that order would hang on
+// the round-off of the moment sums. Weights that agree to 2^-24 count as equal here and the id decides
+// (same rule in oracle/src/cloud.cpp).
+__device__ __forceinline__ double cloneWeight(double eta, double m) { return (double)__double2float_rn(eta * m); }
 __global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, const int *cellStart, const int *cellEnd,
                               int *flag, int *nClone, int nRanks, int *list, int *nList) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -772,7 +780,7 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
         // re-read global memory
         const bool inRegs = cnt <= 128;
         if (fl == 1) {
-            // cloneParticles (:1107-1139): the n heaviest by eta*m (ties by id) are split
+            // cloneParticles (:1107-1139): the n heaviest by eta*m (see cloneWeight; ties by id) are split
             const int n = nClone[c];
             // the clones themselves are created by k_nc_clone, one thread per task
             auto makeClone = [&](int slot, int rk, uint32_t) { cloneSrc[cloneOffset[c] + rk] = (uint32_t)slot; };
@@ -784,7 +792,7 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
                     const bool valid = j < e;
                     const int slot = valid ? (int)perm[j] : 0;
                     slotv[it] = slot;
-                    keyv[it] = valid ? S.eta[slot] * S.m[slot] : -PDF_VGREAT;
+                    keyv[it] = valid ? cloneWeight(S.eta[slot], S.m[slot]) : -PDF_VGREAT;
                     idv[it] = valid ? S.id[slot] : 0xffffffffu;
                     rkv[it] = 0;
                 }
@@ -811,12 +819,12 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
                 int it = 0;
                 for (int j = s + lane; j < e; j += 32, ++it) {
                     const int slot = (int)perm[j];
-                    const double key_i = S.eta[slot] * S.m[slot];
+                    const double key_i = cloneWeight(S.eta[slot], S.m[slot]);
                     const uint32_t id_i = S.id[slot];
                     int rk = 0;
                     for (int q = s; q < e; ++q) {
                         const int sq = (int)perm[q];
-                        const double kq = S.eta[sq] * S.m[sq];
+                        const double kq = cloneWeight(S.eta[sq], S.m[sq]);
                         if (kq > key_i || (kq == key_i && S.id[sq] < id_i)) ++rk;
                     }
                     if (rk < n && it < 256) {
@@ -950,8 +958,8 @@ struct DevReport {
 #define RP_CELLMAX (RP_CELLSUM + 3)      // 2: -rhoErrMin, rhoErrMax
 #define RP_NCDELTA (RP_CELLMAX + 2)      // K1_NC1
 #define RP_INJ (RP_NCDELTA + K1_NC1)     // K1_NC1
-#define RP_LOSTSUM (RP_INJ + K1_NC1)     // 1: total lost mass re-spread
-#define RP_CLONEDELTA (RP_LOSTSUM + 1)   // K1_NC1: axisymmetric mass-per-depth change of the clones
+#define RP_LOSTSUM (RP_INJ + K1_NC1)     // K1_NC1: lost mass re-spread, per depth, x {1, conserved scalars}
+#define RP_CLONEDELTA (RP_LOSTSUM + K1_NC1)   // K1_NC1: axisymmetric mass-per-depth change of the clones
 #define RP_END (RP_CLONEDELTA + K1_NC1)
 static_assert(RP_END <= 64, "DevReport too small");
 
@@ -984,23 +992,46 @@ __global__ void k_lost_reduce(const LostRec *list, LostRec *sorted, const unsign
     }
 }
 
-// lostMass_/max(PaNIC,1) (mcParticleCloud.C:1363-1369); partial sums of what is re-spread.
+// lostMass_/max(PaNIC,1) (mcParticleCloud.C:1363-1369).
 // The mass a rank lost is shared among the particles this rank holds in the cell after number
 // control: nLocal = (segment length) + (PaNIC - N), where N is the all-reduced count of the moment
 // block and PaNIC has since been updated by this rank's clones and eliminations. With one rank that
 // is PaNIC itself (the reference's expression); with several it conserves the mass rank by rank.
 __global__ void k_lost_share(int nCells, const double *lostMass, const double *PaNIC, const int *cellStart,
-                             const int *cellEnd, const double *block, int nMom, double *lostShare, double *partial) {
-    __shared__ double sm[32];
-    double v[1] = {0.0};
+                             const int *cellEnd, const double *block, int nMom, double *lostShare) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += gridDim.x * blockDim.x) {
         const double nLocal = (double)(cellEnd[c] - cellStart[c]) + (PaNIC[c] - block[(size_t)c * nMom]);
-        const double sh = lostMass[c] / fmax(nLocal, 1.);
-        lostShare[c] = sh;
-        v[0] += sh * nLocal;
+        lostShare[c] = lostMass[c] / fmax(nLocal, 1.);
     }
-    blockReduce<1, false>(v, sm);
-    if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
+}
+
+// What the re-spread adds to the step's mass balance (mcParticleCloud.C:1363-1369 runs before the sums of
+// :1432-1444, so the reference's deltaMassInst sees the masses with their shares): the sum over the particles
+// alive after number control of massPerDepth(share) x {1, conserved scalars}. The shares themselves are added to
+// the masses by the next step's particle kernel. Nothing was lost in almost every step: the kernel then only
+// writes zeros. Per-CTA partial rows, folded by k_fold_rows.
+__global__ void k_lost_balance(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const StepScalars *sc, const unsigned *lostCount,
+                               const double *lostShare, double *partial) {
+    __shared__ double sm[K1_NC1 * 32];
+    double v[K1_NC1];
+#pragma unroll
+    for (int k = 0; k < K1_NC1; ++k) v[k] = 0;
+    if (*lostCount != 0) {
+        const int nSorted = sc->nSorted, n = nSorted + sc->nTail, nSlots = sc->nSlots;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int slot = i < nSorted ? (int)perm[i] : nSlots + (i - nSorted);
+            const int c = S.cell[slot];
+            if (c < 0) continue;
+            const double sh = lostShare[c];
+            if (sh == 0.0) continue;
+            const double mpd = massPerDepth(M, mk(S.px[slot], S.py[slot], S.pz[slot]), sh);
+            v[0] += mpd;
+            for (int cs = 0; cs < P.nConserved; ++cs) v[1 + cs] += mpd * S.phi[P.conserved[cs]][slot];
+        }
+    }
+    blockReduce<K1_NC1, false>(v, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < K1_NC1; ++k) partial[blockIdx.x * K1_NC1 + k] = v[k];
 }
 
 // column sums of an [n][K1_NC1] array: per-CTA partial rows (folded by k_fold_rows)
@@ -1032,6 +1063,7 @@ __global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int
     const int nCl = ncCounts ? ncCounts[0] : 0;
     sc->nTail = nCl;
     sc->nInjStart = nCl;
+    if ((unsigned long long)sc->nextId + (unsigned long long)nCl * (unsigned long long)nRanksForId > 0xffffffffull) sc->overflow = 3;
     sc->nextId += (uint32_t)nCl * (uint32_t)nRanksForId;
     sc->anyLost = rp->v[RP_K1SUM + ACC_N_LOST] > 0 ? 1 : 0;
     sc->nLostTotal += (long long)rp->v[RP_K1SUM + ACC_N_LOST];
@@ -1112,7 +1144,7 @@ void Cloud::allocParticles() {
     cubTemp.alloc(tempBytes + 256);
     cellStart.alloc(nCells); cellEnd.alloc(nCells); ncFlag.alloc(nCells); ncCount.alloc(nCells + 1); ncOffset.alloc(nCells + 1);
     scanTmp.alloc(8);
-    csCount.alloc(nCells); csCursor.alloc(nCells); csStart.alloc(nCells);
+    csCount.alloc(nCells); csCursor.alloc(nCells); csStart.alloc(nCells); ncCounts.alloc(2);
     injCount.alloc(std::max(nBnd, 1)); injOffset.alloc(std::max(nBnd, 1) + 1); injSums.alloc((size_t)std::max(nBnd, 1) * K1_NC1);
     ncDelta.alloc((size_t)nCells * K1_NC1);
     if (axisym) cloneDelta.alloc((size_t)capacity * K1_NC1);
@@ -1129,6 +1161,7 @@ void Cloud::allocParticles() {
 
 void Cloud::seedParticles() {
     if (!haveMoments) throw std::logic_error("seed_particles: init_moments first");
+    requireTables();
     allocParticles();
     const int Npc = prm.particlesPerCell;
     const int nLoc = (Npc - rank + nRanks - 1) / nRanks;
@@ -1145,6 +1178,21 @@ void Cloud::seedParticles() {
     CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     nParticlesHost = n; nSlotsHost = 0; sortedValid = false;
+}
+
+// labels handed in by the caller index the mesh tables without bounds checks in every kernel
+__global__ void k_check_labels(DMesh M, int n, const int *cell, const int *tet, int *bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell[i];
+    bool ok = c >= 0 && c < M.nCells;
+    if (ok && tet) { const int t = tet[i]; ok = t >= M.cellTetStart[c] && t < M.cellTetStart[c + 1]; }
+    if (!ok) atomicAdd(bad, 1);
+}
+// ids when the caller gives none: running index, interleaved over the ranks so that no two ranks share one
+__global__ void k_default_ids(int n, uint32_t *id, int rank, int nRanks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) id[i] = (uint32_t)i * (uint32_t)nRanks + (uint32_t)rank;
 }
 
 void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
@@ -1164,13 +1212,31 @@ void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
     up(s.m, p.m); up(s.omega, p.Omega); up(s.rho, p.rho); up(s.eta, p.eta);
     for (int k = 0; k < prm.nPhi; ++k) { if (!p.Phi[k]) throw std::invalid_argument("upload_particles: null scalar column"); up(s.phi[k], p.Phi[k]); }
     CUDA_CHECK(cudaMemcpy(s.cell, p.cell, n * sizeof(int), cudaMemcpyHostToDevice));
-    if (p.id) CUDA_CHECK(cudaMemcpy(s.id, p.id, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    else CUDA_CHECK(cudaMemcpy(s.id, iota.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    // the next free id: above every id in use and congruent to the rank (ids advance in steps of nRanks)
+    uint64_t idEnd = 0;
+    if (p.id) {
+        CUDA_CHECK(cudaMemcpy(s.id, p.id, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        for (int64_t i = 0; i < n; ++i) idEnd = std::max<uint64_t>(idEnd, (uint64_t)p.id[i] + 1);
+    } else {
+        if (n > 0) LAUNCH(this, k_default_ids, gridFor(n, 256), 256, 0, (int)n, s.id, rank, nRanks);
+        idEnd = (uint64_t)n * (uint64_t)nRanks;
+    }
+    const uint64_t nextId64 = (idEnd + (uint64_t)nRanks - 1) / (uint64_t)nRanks * (uint64_t)nRanks + (uint64_t)rank;
+    if (nextId64 > 0xffffffffull) throw std::invalid_argument("upload_particles: particle ids exhaust the 32-bit id space");
     if (p.tet) CUDA_CHECK(cudaMemcpy(s.tet, p.tet, n * sizeof(int), cudaMemcpyHostToDevice));
-    else LAUNCH(this, k_locate, gridFor(n, 128), 128, 0, dm, (int)n, s);
+    if (n > 0) {
+        // labels are validated before any kernel indexes a mesh table with them (cell first: the locate kernel needs it)
+        DBuf<int> bad; bad.alloc(1); bad.zero(stream);
+        LAUNCH(this, k_check_labels, gridFor(n, 256), 256, 0, dm, (int)n, s.cell, p.tet ? s.tet : nullptr, bad.p);
+        int hBad = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&hBad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (hBad) throw std::invalid_argument("upload_particles: " + std::to_string(hBad) + " particles carry a cell label outside the mesh or a tet label outside their cell");
+        if (!p.tet) LAUNCH(this, k_locate, gridFor(n, 128), 128, 0, dm, (int)n, s);
+    }
     StepScalars h = *hScal;
     h.nSorted = 0; h.nTail = (int)n; h.nInjStart = (int)n; h.nSlots = 0; h.anyLost = 0;
-    h.nextId = (uint32_t)n + (uint32_t)rank;
+    h.nextId = (uint32_t)nextId64;
     *hScal = h;
     CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1259,9 +1325,9 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     if (!haveMoments) throw std::logic_error("evolve: fields/moments not initialised");
     if (stateAllocs.empty()) throw std::logic_error("evolve: no particles (seed_particles or upload_particles first)");
     if (prm.nConserved > K1_MAXCONS) throw std::invalid_argument("evolve: at most 3 conserved scalars are supported");
+    requireTables();
     const RngKey key = makeKey(prm.seed);
     DevReport *dRep = reinterpret_cast<DevReport *>(finalSums.p + 128);
-    DBuf<int> ncCounts; ncCounts.alloc(2);
     CUDA_CHECK(cudaEventRecord(evStart, stream));
     int k1Blocks = 0;
     // the scalars live in registers: instantiate the kernel for nPhi <= 1, 2, 3 and the general bound
@@ -1305,6 +1371,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         // the host needs the entry count to size the sort
         CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (hScal->overflow == 3) throw std::runtime_error("evolve: the 32-bit particle id space is exhausted");
         if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
         const int nSorted = hScal->nSorted, nTail = hScal->nTail;
         const int total = nSorted + nTail;
@@ -1427,10 +1494,15 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         // ---- lost mass shares ----
         {
             const int gL = std::min(gridFor(nCells, 256), numSMs * 4);
-            LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, momentBlock.p, nMom, lostShare.p, k1PartMax.p);
-            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gL, 1, k1PartMax.p, dRep->v + RP_LOSTSUM, 0);
+            LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, momentBlock.p, nMom, lostShare.p);
         }
         LAUNCH(this, k_step_end, 1, 32, 0, scal.p, dRep, prm, 0, nc ? ncCounts.p : nullptr, total, nRanks);
+        {
+            // after k_step_end: nSorted / nTail / nSlots describe the particles the next step starts from
+            const int gB = numSMs * 4;
+            LAUNCH(this, k_lost_balance, gB, 256, 0, dm, prm, S[cur], valsB.p, scal.p, lostCount.p, lostShare.p, k1PartSum.p);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gB, K1_NC1, k1PartSum.p, dRep->v + RP_LOSTSUM, 0);
+        }
 
         // ---- report ----
         CUDA_CHECK(cudaMemcpyAsync(hFinal, dRep, sizeof(DevReport), cudaMemcpyDeviceToHost, stream));
@@ -1449,6 +1521,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         profParticleSteps += (double)total;
         ++profSteps;
         if (hScal->overflow == 2) throw std::runtime_error("evolve: more than " + std::to_string(lostList.n) + " particles lost in one step");
+        if (hScal->overflow == 3) throw std::runtime_error("evolve: the 32-bit particle id space is exhausted");
         if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
         const double *v = hFinal;
         if (v[RP_K1SUM + ACC_N_LOST] > 0) lostDirty = true;
@@ -1467,11 +1540,10 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             r.etaMax = std::max(0.0, v[RP_K1MAX + ACC_ETAMAX]); r.etaMin = -v[RP_K1MAX + ACC_NEG_ETAMIN];
             r.CoMax = std::max(0.0, v[RP_K1MAX + ACC_COMAX]);
             for (int k = 0; k <= prm.nConserved; ++k) {
-                r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + (v[RP_NCDELTA + k] + v[RP_CLONEDELTA + k]);
+                r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + (v[RP_NCDELTA + k] + v[RP_CLONEDELTA + k]) + v[RP_LOSTSUM + k];
                 r.massInInst[k] = v[RP_K1SUM + ACC_MASS_IN + k] + v[RP_INJ + k];
                 r.massOutInst[k] = v[RP_K1SUM + ACC_MASS_OUT + k];
             }
-            r.deltaMassInst[0] += v[RP_LOSTSUM];
             r.nParticles = nParticlesHost;
             r.nInjected = nInjected; r.nDeleted = (int64_t)v[RP_K1SUM + ACC_N_DELETED];
             r.nCloned = hNc[0]; r.nEliminated = hNc[1]; r.nLost = (int64_t)v[RP_K1SUM + ACC_N_LOST];

@@ -39,7 +39,7 @@ def test_device_library_exports_every_declared_symbol():
     from oracle.oracle import OracleLib
     ol = OracleLib()
     for s in capi.API_SYMBOLS:
-        if s in ("comm_unique_id", "comm_init", "kernel_launches", "last_evolve_ms", "profile", "jit_source"):
+        if s in ("comm_unique_id", "comm_init", "kernel_launches", "last_evolve_ms", "profile", "jit_source", "jit_compile"):
             continue
         assert ol.has(s), f"oracle does not export pdforacle_{s}"
 
@@ -141,11 +141,13 @@ def _jit_cases():
     yield "BurkeSchumann wedge", cases.with_scalars(cases.wedge_jet(nx=4, nr_jet=2, nr_co=2, ppc=8), ["z", "T"], "BurkeSchumann"), True, True
 
 
+@pytest.mark.parametrize("compiler", [1, 2])
 @pytest.mark.parametrize("idx", [0, 1, 2])
-def test_specialised_kernel_source_compiles_for_sm100a(tmp_path, idx):
-    """The translation unit the library builds at run time (jit.cu) for three model
-    selections: nvcc must compile it for sm_100a and the cubin must hold k_evolve_jit.
-    (Running it needs a GPU: tests/test_gpu_jit.py.)"""
+def test_specialised_kernel_compiles_for_sm100a(idx, compiler):
+    """The translation unit the library builds at run time (jit.cu) for three model selections, through the
+    library's own compile path — kernel sources embedded in the .so, NVRTC in memory (compiler 1) and the
+    nvcc route used when NVRTC is missing (compiler 2): both must produce a cubin for sm_100a that holds
+    k_evolve_jit. (Running it needs a GPU: tests/test_gpu_jit.py.)"""
     name, case, axisym, has_open = list(_jit_cases())[idx]
     lib = C.CDLL(capi.device_library_path())
     holder = capi.Library.__new__(capi.Library)
@@ -154,12 +156,32 @@ def test_specialised_kernel_source_compiles_for_sm100a(tmp_path, idx):
     gd = case.mesh.geometric_d
     src = capi.jit_source(holder, case.params, axisym, has_open, 0, gd, case.mesh.solution_d)
     assert "struct JitP" in src and f"JIT_AXISYM {int(axisym)}" in src
-    cu = tmp_path / "k.cu"
-    cu.write_text(src)
-    out = tmp_path / "k.cubin"
-    csrc = os.path.join(ROOT, "pdffoam_b200", "csrc")
-    r = subprocess.run(["nvcc", "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-                        "-fmad=false", "-I" + csrc, "-o", str(out), str(cu)], capture_output=True, text=True)
-    assert r.returncode == 0, f"{name}: {r.stderr[-3000:]}"
-    sym = subprocess.run(["cuobjdump", "-elf", str(out)], capture_output=True, text=True).stdout
-    assert "k_evolve_jit" in sym
+    n, log = capi.jit_compile(holder, case.params, axisym, has_open, 0, gd, case.mesh.solution_d, compiler=compiler)
+    assert n > 10000, f"{name}: {log[-3000:]}"
+
+
+def test_jit_cache_directory_must_be_private(tmp_path, monkeypatch):
+    """a cache directory that others can write to is not used (the cubin found there would run on the
+    caller's data); the library then compiles in memory without caching. Checked through the exported symbol by
+    pointing PDFB200_JIT_CACHE at a world-writable directory and at a symlink."""
+    import stat
+    lib = C.CDLL(capi.device_library_path())
+    if not hasattr(lib, "pdfb200_jit_cache_dir"):
+        pytest.skip("no cache introspection")
+    lib.pdfb200_jit_cache_dir.restype = C.c_long
+    lib.pdfb200_jit_cache_dir.argtypes = [C.c_char_p, C.c_long]
+    buf = C.create_string_buffer(4096)
+
+    def cache_dir():
+        n = lib.pdfb200_jit_cache_dir(buf, len(buf))
+        return buf.value.decode() if n > 0 else ""
+
+    good = tmp_path / "good"
+    monkeypatch.setenv("PDFB200_JIT_CACHE", str(good))
+    assert cache_dir() == str(good) and stat.S_IMODE(os.stat(good).st_mode) == 0o700
+    bad = tmp_path / "bad"; bad.mkdir(); os.chmod(bad, 0o777)
+    monkeypatch.setenv("PDFB200_JIT_CACHE", str(bad))
+    assert cache_dir() == ""
+    link = tmp_path / "link"; os.symlink(good, link)
+    monkeypatch.setenv("PDFB200_JIT_CACHE", str(link))
+    assert cache_dir() == ""

@@ -69,6 +69,6 @@ def test_gpu_curl_matches_oracle(device_lib, oracle_lib, ppc, mesh):
     rng = np.random.default_rng(5)
     P["Phi"][0] = rng.uniform(0.0, 1.0, size=P["m"].shape[0])
     P["m"] = P["m"] * rng.uniform(0.8, 1.25, size=P["m"].shape[0])
-    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=6, rtol=1e-9, atol=1e-11)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=6, rtol=1e-10, atol=1e-12)
     Q = dev.download_particles()
     assert np.std(Q["Phi"][0]) < np.std(P["Phi"][0]), "no mixing happened"

@@ -1,0 +1,91 @@
+"""Error behaviour of the C ABI on a device: misuse must come back as a status with a message
+(the reference aborts with FatalError), never as an out-of-bounds access that kills the CUDA
+context."""
+import os
+
+import numpy as np
+import pytest
+
+from pdffoam_b200 import capi, cases
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_steady_flamelet_without_tables_is_refused(device_lib):
+    """mcSteadyFlamelet's constructor fails when its library is missing (mcSteadyFlamelet.C:120-286)."""
+    tab = cases.load_flamelet_tables(os.path.join(ROOT, "tests", "golden", "flamelet_sandiaD.npz"))
+    case = cases.with_scalars(cases.synthetic_box(4, 3, 2, ppc=8, closed=True), ["z", "chi", "T"], "SteadyFlamelet", tab)
+    case.tables = None                                   # "forgot" pdfb200_set_flamelet_tables
+    h = case.make_cloud(device_lib)
+    with pytest.raises(capi.PdfError, match="flamelet tables"):
+        h.seed_particles()
+    h.upload_particles(case.random_particles(8, seed=1))
+    with pytest.raises(capi.PdfError, match="flamelet tables"):
+        h.evolve(1)
+    # a library with rho only, but one added scalar selected
+    h.set_flamelet_tables(tab["chi"], tab["z"], tab["fields"][:1])
+    with pytest.raises(capi.PdfError, match="fewer tables"):
+        h.evolve(1)
+    # the context is alive: with the full library the step runs
+    h.set_flamelet_tables(tab["chi"], tab["z"], tab["fields"])
+    assert h.evolve(1)[0].nParticles == case.mesh.n_cells * 8
+
+
+@pytest.mark.parametrize("order", ["set_then_upload", "upload_then_set"])
+def test_set_delta_t_survives_upload_and_seed(device_lib, oracle_lib, order):
+    case = cases.synthetic_box(4, 3, 2, ppc=8, closed=True)
+    P = case.random_particles(8, seed=2)
+    for lib in (device_lib, oracle_lib):
+        h = case.make_cloud(lib)
+        if order == "set_then_upload":
+            h.set_delta_t(3e-3); h.upload_particles(P)
+        else:
+            h.upload_particles(P); h.set_delta_t(3e-3)
+        assert h.delta_t() == 3e-3
+        assert h.evolve(1)[0].deltaT == 3e-3
+    h = case.make_cloud(device_lib)
+    h.set_delta_t(2e-3); h.seed_particles()
+    assert h.evolve(1)[0].deltaT == 2e-3
+
+
+def test_upload_with_bad_labels_is_refused_and_context_survives(device_lib):
+    case = cases.synthetic_box(4, 3, 2, ppc=8, closed=True)
+    h = case.make_cloud(device_lib)
+    P = case.random_particles(8, seed=3)
+    bad = dict(P); bad["cell"] = P["cell"].copy(); bad["cell"][5] = case.mesh.n_cells + 7
+    with pytest.raises(capi.PdfError, match="cell label"):
+        h.upload_particles(bad)
+    bad["cell"][5] = -3
+    with pytest.raises(capi.PdfError, match="cell label"):
+        h.upload_particles(bad)
+    bad = dict(P); bad["tet"] = np.zeros_like(P["cell"])         # tet 0 belongs to cell 0 only
+    with pytest.raises(capi.PdfError, match="tet label"):
+        h.upload_particles(bad)
+    h.upload_particles(P)
+    assert h.evolve(2)[-1].nParticles == P["m"].size
+
+
+def test_default_ids_and_next_id(device_lib):
+    """ids given on upload need not be 0..n-1 (a restart after number control): clones must not reuse one"""
+    case = cases.synthetic_box(4, 3, 2, ppc=10, closed=True, number_control=True)
+    case.params.deltaT0 = 2e-3
+    P = case.random_particles(10, seed=4)
+    P["id"] = (np.arange(P["m"].size, dtype=np.uint32) * 7 + 1000).astype(np.uint32)
+    # thin out a few cells so that number control clones
+    keep = ~np.isin(P["cell"], [1, 2, 3]) | (np.arange(P["m"].size) % 3 == 0)
+    Q = {k: (v[keep] if k != "Phi" else [a[keep] for a in v]) for k, v in P.items()}
+    h = case.make_cloud(device_lib)
+    h.upload_particles(Q)
+    reps = h.evolve(3)
+    assert sum(r.nCloned for r in reps) > 0
+    ids = h.download_particles()["id"]
+    assert np.unique(ids).size == ids.size
+    new = np.setdiff1d(ids, Q["id"])
+    assert new.size > 0 and new.min() > Q["id"].max()
+    # no ids given: running index
+    R = dict(Q); R.pop("id")
+    h2 = case.make_cloud(device_lib)
+    h2.upload_particles(R)
+    assert np.array_equal(np.sort(h2.download_particles()["id"]), np.arange(Q["m"].size, dtype=np.uint32))

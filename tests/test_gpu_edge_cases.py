@@ -34,7 +34,7 @@ def test_warped_hex_mesh_deterministic_and_stochastic(device_lib, oracle_lib):
     case = cases.synthetic_box(7, 5, 4, ppc=20, closed=False, number_control=True)
     _perturb_interior_points(case.mesh, 0.15)
     case.params.deltaT0 = 2e-3
-    dev, ora, reps = run_both(case, device_lib, oracle_lib, None, n_steps=6, seed_on_device=True, rtol=1e-9, atol=1e-11)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, None, n_steps=6, seed_on_device=True, rtol=1e-10, atol=1e-12)
     assert sum(r[0].nInjected for r in reps) > 0 and sum(r[0].nLost for r in reps) == 0
 
 
@@ -43,7 +43,7 @@ def test_six_scalars(device_lib, oracle_lib):
     case = cases.synthetic_box(6, 4, 3, ppc=16, closed=False, n_phi=6)
     case.params.deltaT0 = 2e-3
     P = case.random_particles(16, seed=12)
-    run_both(case, device_lib, oracle_lib, P, n_steps=5, rtol=1e-9, atol=1e-11)
+    run_both(case, device_lib, oracle_lib, P, n_steps=5, rtol=1e-10, atol=1e-12)
 
 
 def test_crowded_cell(device_lib, oracle_lib):
@@ -61,7 +61,7 @@ def test_crowded_cell(device_lib, oracle_lib):
     Q["pos"] = Q["pos"].copy()
     Q["pos"][-dup.size:] = lo + rng.uniform(0.05, 0.95, size=(dup.size, 3)) * (hi - lo)
     Q["m"] = Q["m"] * rng.uniform(0.5, 1.5, size=Q["m"].shape[0])
-    dev, ora, reps = run_both(case, device_lib, oracle_lib, Q, n_steps=4, rtol=1e-9, atol=1e-11)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, Q, n_steps=4, rtol=1e-10, atol=1e-12)
     assert sum(r[0].nEliminated for r in reps) > 0
 
 
@@ -72,4 +72,4 @@ def test_cell_interpolation_scheme_everywhere(device_lib, oracle_lib):
         setattr(case.params, name, 0)
     case.params.deltaT0 = 2e-3
     P = case.random_particles(18, seed=4)
-    run_both(case, device_lib, oracle_lib, P, n_steps=5, rtol=1e-9, atol=1e-11)
+    run_both(case, device_lib, oracle_lib, P, n_steps=5, rtol=1e-10, atol=1e-12)

@@ -13,7 +13,7 @@ from parity_util import compare_cell_fields, compare_particles, run_both, sort_b
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RTOL, ATOL = 1e-9, 1e-11
+RTOL, ATOL = 1e-10, 1e-12
 
 
 @pytest.mark.parametrize("table", ["flamelet_sandiaD", "flamelet_bluffbody"])
@@ -65,9 +65,15 @@ def test_flamelet_lookup_matches_golden_vectors(device_lib):
 def test_burke_schumann(device_lib, oracle_lib):
     case = cases.with_scalars(cases.synthetic_box(6, 4, 4, ppc=18, closed=False), ["z", "T"], "BurkeSchumann")
     case.params.deltaT0 = 1e-3
-    # grad p* is formed from absolute pressures (1e5) times shape gradients (~1e2) that sum to zero:
-    # round-off of that cancellation is ~1e-9 in the gradient, ~1e-11 in U after one step
-    run_both(case, device_lib, oracle_lib, None, n_steps=4, seed_on_device=True, rtol=1e-8, atol=1e-9)
+    # The kernel evaluates the reference's expression for grad p* with richTetrahedron's own gradN[3] (plane D of the tet
+    # table) and divides by rho (mcSLMFullVelocityModel.C:174), so everything is held to 1e-10 relative. What remains is
+    # the granularity of an absolute pressure in fp64: p* = p - 2/3 rho k ~ 1e5 has ulp 1.46e-11, and when the cloud
+    # density behind it differs in its last bit (the moment sums run in another order) p* at a node flips by one ulp in
+    # a few cells. One flip moves a velocity by ulp(p) |grad N| eta dt / rho = 1.46e-11 x 16/m x 2e-2 s / 0.17 kg/m3 =
+    # 2.7e-11 m/s (eta <= 20 from local time stepping, rho = p/(R T) at T_stoi = 2000 K); a handful of particles out
+    # of 6000 show it, on components that are ~1e-2 m/s. Hence the absolute floor of 1e-10 m/s; the reference's own
+    # result has the same granularity.
+    run_both(case, device_lib, oracle_lib, None, n_steps=4, seed_on_device=True, rtol=1e-10, atol=1e-10)
 
 
 def test_particle_local_time_stepping_and_cell_scheme(device_lib, oracle_lib):

@@ -54,7 +54,7 @@ def test_stochastic_closed_box_same_streams(device_lib, oracle_lib):
     time stepping, limitedSimple position correction, numerical diffusion)."""
     case = cases.synthetic_box(8, 5, 4, ppc=25, closed=True)
     P = case.random_particles(25, seed=5)
-    run_both(case, device_lib, oracle_lib, P, n_steps=8, rtol=1e-9, atol=1e-11)
+    run_both(case, device_lib, oracle_lib, P, n_steps=8, rtol=1e-10, atol=1e-12)
 
 
 def test_open_box_injection_and_outflow(device_lib, oracle_lib):
@@ -62,7 +62,7 @@ def test_open_box_injection_and_outflow(device_lib, oracle_lib):
     deletion at inflow faces, open-boundary reflection."""
     case = cases.synthetic_box(8, 4, 4, ppc=20, closed=False)
     P = case.random_particles(20, seed=3)
-    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=8, rtol=1e-9, atol=1e-11)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=8, rtol=1e-10, atol=1e-12)
     assert sum(r[0].nInjected for r in reps) > 0
     assert sum(r[0].nDeleted for r in reps) > 0
 
@@ -95,7 +95,7 @@ def test_particle_number_control(device_lib, oracle_lib):
     R["pos"] = R["pos"].copy()
     R["pos"][-dup.size:] += 1e-4 * (rng.random((dup.size, 3)) - 0.5)
     R["m"] = R["m"] * rng.uniform(0.5, 1.5, size=R["m"].shape[0])
-    dev, ora, reps = run_both(case, device_lib, oracle_lib, R, n_steps=5, rtol=1e-9, atol=1e-11)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, R, n_steps=5, rtol=1e-10, atol=1e-12)
     assert sum(r[0].nCloned for r in reps) > 0
     assert sum(r[0].nEliminated for r in reps) > 0
 
@@ -108,13 +108,13 @@ def test_dense_cells_sorted_by_cell_and_tet(device_lib, oracle_lib):
     P = case.random_particles(256, seed=21)
     rng = np.random.default_rng(4)
     P["m"] = P["m"] * rng.uniform(0.5, 1.5, size=P["m"].shape[0])
-    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=4, rtol=1e-9, atol=1e-11)
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, P, n_steps=4, rtol=1e-10, atol=1e-12)
     assert sum(r[0].nInjected for r in reps) > 0
 
 
 def test_seed_on_device_matches_oracle(device_lib, oracle_lib):
     case = cases.synthetic_box(6, 4, 3, ppc=16, closed=True)
-    run_both(case, device_lib, oracle_lib, None, n_steps=3, seed_on_device=True, rtol=1e-9, atol=1e-11)
+    run_both(case, device_lib, oracle_lib, None, n_steps=3, seed_on_device=True, rtol=1e-10, atol=1e-12)
 
 
 def test_product_does_not_load_oracle(device_lib):
@@ -129,3 +129,14 @@ def test_product_does_not_load_oracle(device_lib):
             "m = open('/proc/self/maps').read(); assert 'libpdfb200.so' in m; assert 'pdforacle' not in m; print('ok')" % root)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_midsize_open_box_jit_kernel_and_counting_sort(device_lib, oracle_lib):
+    """40 x 20 x 20 cells x 64 particles (1.0e6): cells >> CTAs, so the run-time specialised kernel, the counting
+    sort by cell, the Morton processing order, injection, outflow and number control are all compared with the
+    oracle at a size where a CTA no longer sees a whole cell row (VERDICT r01, weak #5)."""
+    case = cases.synthetic_box(40, 20, 20, ppc=64, closed=False, number_control=True)
+    case.params.deltaT0 = 1e-3
+    dev, ora, reps = run_both(case, device_lib, oracle_lib, None, n_steps=3, seed_on_device=True, rtol=1e-10, atol=1e-12)
+    assert sum(r[0].nInjected for r in reps) > 0 and sum(r[0].nDeleted for r in reps) > 0
+    assert sum(r[0].nCloned + r[0].nEliminated for r in reps) > 0
