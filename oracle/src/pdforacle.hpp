@@ -5,15 +5,18 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
 // legs may load this library; the product (pdffoam_b200/csrc) never does.
 //
-// PARITY STATUS: "parity unpinned" against the reference binary — pdfFoam needs
-// OpenFOAM 1.7.x/2.1.x which is not available here and the reference ships no
-// golden vectors. What pins this oracle instead:
-//   * closed-form known answers derived from the cited reference lines
-//     (tests/test_oracle_known_answers.py),
-//   * the reference's own flamelet tables and the analytic inlet PDF/CDF used
-//     by tests/mcInletRandom,
-//   * a literal restatement of richTetrahedron::inside / find() used to check
-//     the tet walk's end state.
+// PARITY STATUS: pinned in part by the reference's own code compiled here, unpinned for the rest.
+//   * PINNED (oracle/_ref/libpdfref.so, built by oracle/ref/Makefile from the unmodified sources under
+//     /root/reference against a stand-in for the OpenFOAM headers; compared bit for bit by
+//     tests/test_oracle_vs_ref.py): findCoeffs/binterp (mcSteadyFlamelet.C:44-93), mcInletRandom::
+//     updateCoeffs/PDF/CDF + mcInversionInletRandom::newton/value, richTetrahedron::update/inside,
+//     tetFacePointCellDecomposition (order, face, point pair of every tet, cellTetrahedra, find).
+//   * UNPINNED ("parity unpinned"): evolve() as a whole. pdfFoam needs OpenFOAM 1.7.x/2.1.x and its wmake
+//     build, neither of which exists here, and the reference ships no golden vectors.
+//     What holds that part instead: closed-form known answers derived from the cited reference lines
+//     (tests/test_oracle_known_answers.py, test_oracle_evolve.py), the reference's own flamelet tables and
+//     the analytic inlet PDF/CDF used by tests/mcInletRandom, independent numpy restatements
+//     (tests/golden/make_golden.py).
 // OpenFOAM primitives (trackToFace, interpolationCellPointFace,
 // volPointInterpolation, linearInterpolate, fvc::grad, Random) are *defined*
 // here per SURVEY.md Appendix B.
