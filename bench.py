@@ -4,6 +4,9 @@ synthetic 3-D box of BASELINE.json configs[4] / SURVEY.md §8(d).
 
   python bench.py --gpus N --steps K --warmup W            (N>1: under torchrun)
   python bench.py --impl reference ...                      CPU arm (the oracle on all host cores)
+  python bench.py --config SandiaD|SydneyBluffBodyFlame|SydneyBluffBodyFlow|SandiaPropaneJet4x
+                                                            the tutorial-shaped configs of BASELINE.json configs[0..3]
+  python bench.py --scaling strong --gpus N                 fixed total of 2.5e8 particles split over N GPUs
 
 Workload (weak scaling): 200x100x100 hexes = 2.0e6 cells (4.8e7 tets), 64
 particles per cell PER GPU (1.28e8 particles per GPU, 1.02e9 at 8 GPUs),
@@ -26,6 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+TRAFFIC_PROFILE = "r02_k_evolve_v3_metrics.csv"   # ncu --set full capture of the shipped k_evolve_jit (profiles/README.md)
 METRIC = "particle-steps/sec"
 UNIT = "particle-steps/s"
 
@@ -107,61 +111,111 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ppc_per_gpu(args, n_ranks):
+    """particles per cell on each GPU: fixed (weak scaling) or the fixed total split over the ranks (strong)"""
+    if args.scaling == "strong":
+        return max(1, int(round(args.ppc_total / n_ranks)))
+    if args.config != "synthetic" and args.ppc_per_gpu <= 0:
+        return 0                       # the tutorial's own particlesPerCell
+    return args.ppc_per_gpu if args.ppc_per_gpu > 0 else 64
+
+
 def build_case(args, n_ranks):
+    """The case at full size: every rank holds the whole mesh and its share of each cell's particles."""
     from pdffoam_b200 import cases
-    nx, ny, nz = args.cells
-    case = cases.synthetic_box(nx, ny, nz, ppc=args.ppc_per_gpu * n_ranks, closed=False, number_control=True,
-                               reaction="cold", lts="cell", poscorr="limitedSimple")
+    ppc = ppc_per_gpu(args, n_ranks)
+    if args.config == "synthetic":
+        nx, ny, nz = args.cells
+        return cases.synthetic_box(nx, ny, nz, ppc=ppc * n_ranks, closed=False, number_control=True,
+                                   reaction="cold", lts="cell", poscorr="limitedSimple")
+    case = cases.tutorial_case(args.config)
+    if ppc > 0 or n_ranks > 1:
+        case.params.particlesPerCell = (ppc if ppc > 0 else case.params.particlesPerCell) * n_ranks
     return case
 
 
-def cpu_baseline(args, sample_cells=(40, 20, 20), steps=10):
+def workload_text(args, case, n_ranks, per_gpu):
+    P = case.params
+    names = {v: k for k, v in __import__("pdffoam_b200.cases", fromlist=["x"]).REACTION_MODELS.items()}
+    mix = {0: "none", 1: "IEM", 2: "modifiedCurl"}[P.mixingModel]
+    models = f"SLMFull+{mix}+RAS+{names[P.reactionModel]}, cell LTS, limitedSimple, number control"
+    if args.config == "synthetic":
+        nx, ny, nz = args.cells
+        return (f"synthetic 3D hex-to-tet box {nx}x{ny}x{nz} = {case.mesh.n_cells} cells, {P.particlesPerCell // n_ranks} particles/cell/GPU "
+                f"({per_gpu} particles per GPU), {models}, inletOutlet x-faces (BASELINE.json configs[4])")
+    idx = {"SydneyBluffBodyFlow": 0, "SandiaD": 1, "SydneyBluffBodyFlame": 2, "SandiaPropaneJet4x": 3}[args.config]
+    return (f"tutorial-shaped {args.config}: axisymmetric wedge, {case.mesh.n_cells} cells x {P.particlesPerCell // n_ranks} particles/cell/GPU "
+            f"({per_gpu} particles per GPU), scalars {P.nPhi}, {models}, synthetic frozen FV fields (BASELINE.json configs[{idx}])")
+
+
+def cpu_case(config, cells, ppc):
+    """The bounded sample of the workload the CPU legs run: same fields, models and particles per cell, fewer
+    cells (synthetic box) or the unrefined mesh (SandiaPropaneJet4x); the other tutorial shapes run at full size."""
+    from pdffoam_b200 import cases
+    if config == "synthetic":
+        return cases.synthetic_box(*cells, ppc=ppc, closed=False, number_control=True)
+    if config == "SandiaPropaneJet4x":
+        return _propane_unrefined(ppc if ppc > 0 else 400)   # the tutorial's own resolution, same particles per cell
+    return cases.tutorial_case(config, ppc=ppc if ppc > 0 else None)
+
+
+def _propane_unrefined(ppc):
+    from pdffoam_b200 import cases, meshgen
+    IO, SLIP = meshgen.BC_INLET_OUTLET, meshgen.BC_SLIP
+    return cases._streams_case(
+        "SandiaPropaneJet", meshgen.graded(54, 0.0, 0.3, 6.0), [(7, 1.0e-4, 2.6e-3, 1.0), (5, 2.6e-3, 4.5e-3, 1.0), (24, 4.5e-3, 0.04, 6.0)], 2.5,
+        [("jet", 2.6e-3, 69.0, 1.0, 1.8, IO), ("bluffBody", 4.5e-3, 0.0, 0.0, 1.2, SLIP), ("coflow", 1e30, 9.2, 0.0, 1.2, IO)],
+        None, ("z", "T"), "BurkeSchumann",
+        dict(CFL=0.1, averagingCoeff=5e3, particlesPerCell=ppc, ltsUpperBound=20.0, pcC=0.2, Cmix=2.0, mixingModel="IEM"))
+
+
+def cpu_baseline(args, ppc, sample_cells=(40, 20, 20), budget_s=15.0):
     """The oracle ("port" of the reference's evolve) timed single-threaded on a
     bounded sample of the same workload (same ppc, same fields, fewer cells)."""
-    from pdffoam_b200 import cases
     from oracle.oracle import OracleLib
     lib = OracleLib()
-    nx, ny, nz = sample_cells
-    case = cases.synthetic_box(nx, ny, nz, ppc=args.ppc_per_gpu, closed=False, number_control=True)
+    case = cpu_case(args.config, sample_cells, ppc)
     h = case.make_cloud(lib)
     h.seed_particles()
     h.evolve(4)
     n0 = h.num_particles()
     t0 = time.perf_counter()
-    reps = h.evolve(steps)
+    psteps, steps = 0, 0
+    while steps < 3 or (time.perf_counter() - t0 < budget_s and steps < 200):
+        psteps += h.evolve(1)[0].nParticles
+        steps += 1
     dt = time.perf_counter() - t0
-    psteps = sum(r.nParticles for r in reps)
     return {"value": psteps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle evolve, {nx}x{ny}x{nz} cells x {args.ppc_per_gpu} ppc = {n0} particles, {steps} steps, 1 thread"}
+            "sample": f"oracle evolve, {case.name}: {case.mesh.n_cells} cells x {case.params.particlesPerCell} ppc = {n0} particles, {steps} steps, 1 thread"}
 
 
 # ---------------------------------------------------------------------------
 # reference arm: the oracle on all host cores (particle-sharded processes, the
 # per-cell moment block summed between evolve_begin / evolve_end)
 # ---------------------------------------------------------------------------
-def _ref_worker(conn, cells, ppc, n_ranks, rank):
+def _ref_worker(conn, config, cells, ppc, n_ranks, rank, shared_blocks, shared_total, nblk):
     import ctypes as C
-    from pdffoam_b200 import cases
     from pdffoam_b200.capi import StepReport
     from oracle.oracle import OracleLib, dp
     lib = OracleLib()
-    case = cases.synthetic_box(*cells, ppc=ppc, closed=False, number_control=True)
+    case = cpu_case(config, cells, ppc)
     h = case.make_cloud(lib)
     lib.fn("set_rank")(h.h, n_ranks, rank)
     h.seed_particles()
-    nblk = int(lib.fn("moment_block_size")(h.h))
-    block = np.zeros(nblk)
+    assert int(lib.fn("moment_block_size")(h.h)) == nblk
+    # the per-cell moment blocks live in shared memory (inherited through fork): nothing big crosses the pipes
+    mine = np.frombuffer(shared_blocks, dtype=np.float64)[rank * nblk:(rank + 1) * nblk]
+    total = np.frombuffer(shared_total, dtype=np.float64)
     rep = StepReport()
     conn.send(("ready", h.num_particles()))
     while True:
         msg = conn.recv()
         if msg[0] == "begin":
-            lib.check(lib.fn("evolve_begin")(h.h, C.byref(rep), dp(block)), "evolve_begin")
-            conn.send((block.copy(), rep.CoMax, rep.UMax))
+            lib.check(lib.fn("evolve_begin")(h.h, C.byref(rep), dp(mine)), "evolve_begin")
+            conn.send((rep.CoMax, rep.UMax))
         elif msg[0] == "end":
-            block[:] = msg[1]
-            rep.CoMax = msg[2]
-            lib.check(lib.fn("evolve_end")(h.h, C.byref(rep), dp(block)), "evolve_end")
+            rep.CoMax = msg[1]
+            lib.check(lib.fn("evolve_end")(h.h, C.byref(rep), dp(total)), "evolve_end")
             conn.send(int(rep.nParticles))
         else:
             break
@@ -172,14 +226,26 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
+    from oracle.oracle import OracleLib
     cores = os.cpu_count() or 1
     n_proc = max(1, min(cores, 64))
     cells = tuple(args.ref_cells)
+    ppc = ppc_per_gpu(args, 1)
+    case0 = cpu_case(args.config, cells, ppc)
+    ppc_total = case0.params.particlesPerCell
+    n_proc = min(n_proc, ppc_total)                     # every process holds at least one particle per cell
+    h0 = case0.make_cloud(OracleLib())
+    nblk = int(OracleLib().fn("moment_block_size")(h0.h))
+    del h0
     ctx = mp.get_context("fork")
+    shared_blocks = ctx.RawArray("d", n_proc * nblk)
+    shared_total = ctx.RawArray("d", nblk)
+    blocks = np.frombuffer(shared_blocks, dtype=np.float64).reshape(n_proc, nblk)
+    total = np.frombuffer(shared_total, dtype=np.float64)
     conns, procs = [], []
     for r in range(n_proc):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(b, cells, args.ppc_per_gpu, n_proc, r), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(b, args.config, cells, ppc, n_proc, r, shared_blocks, shared_total, nblk), daemon=True)
         p.start()
         conns.append(a); procs.append(p)
     n0 = sum(c.recv()[1] for c in conns)
@@ -188,10 +254,10 @@ def run_reference(args):
         for c in conns:
             c.send(("begin",))
         outs = [c.recv() for c in conns]
-        block = np.sum([o[0] for o in outs], axis=0)
-        comax = max(o[1] for o in outs)
+        np.sum(blocks, axis=0, out=total)
+        comax = max(o[0] for o in outs)
         for c in conns:
-            c.send(("end", block, comax))
+            c.send(("end", comax))
         return sum(c.recv() for c in conns)
 
     for _ in range(min(args.spinup, 4) + args.warmup):
@@ -205,13 +271,13 @@ def run_reference(args):
         c.send(("quit",))
     value = psteps / dt
     sample = (f"oracle evolve (CPU restatement of mcParticleCloud::evolve; pdfFoam itself needs OpenFOAM and cannot be built here), "
-              f"{cells[0]}x{cells[1]}x{cells[2]} cells x {args.ppc_per_gpu} ppc = {n0} particles per step, "
-              f"{n_proc} particle-sharded processes")
+              f"{case0.name}: {case0.mesh.n_cells} cells x {ppc_total} ppc = {n0} particles per step, "
+              f"{n_proc} particle-sharded processes, moment blocks summed in shared memory")
+    full = build_case(args, 1)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic 3D hex-to-tet box {args.cells[0]}x{args.cells[1]}x{args.cells[2]} cells, "
-                                   f"{args.ppc_per_gpu} particles/cell/GPU (BASELINE.json configs[4])", "sample": sample},
+            "config": {"workload": workload_text(args, full, 1, full.mesh.n_cells * full.params.particlesPerCell), "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_proc, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -222,10 +288,10 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 def ncu_traffic_bytes(args, n_phi):
     """DRAM bytes of one k_evolve launch as captured by ncu for the default workload
-    (profiles/r01_k_evolve_jit_metrics.csv); None when the bench runs another workload."""
-    if list(args.cells) != [200, 100, 100] or args.ppc_per_gpu != 64 or n_phi != 1:
+    (profiles/TRAFFIC_PROFILE); None when the bench runs another workload."""
+    if args.config != "synthetic" or args.scaling != "weak" or list(args.cells) != [200, 100, 100] or args.ppc_per_gpu != 64 or n_phi != 1:
         return None
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_k_evolve_jit_metrics.csv")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", TRAFFIC_PROFILE)
     try:
         tot = 0.0
         with open(path) as f:
@@ -256,7 +322,8 @@ def run_ours(args):
     lib = DeviceLibrary()
     case = build_case(args, world)
     n_phi = case.params.nPhi
-    per_gpu = case.mesh.n_cells * args.ppc_per_gpu
+    ppc_gpu = case.params.particlesPerCell // world
+    per_gpu = case.mesh.n_cells * ppc_gpu
     h = case.make_cloud(lib, device=local_rank, capacity=int(per_gpu * 1.2) + 65536)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -284,13 +351,26 @@ def run_ours(args):
     launches0 = h.kernel_launches()
 
     # ---- device-resident timing: K steps, CUDA events on the library's stream ----
+    # inputs larger than L2 (the default workload: 12 GB of particle state) need no flush; the small tutorial shapes
+    # fit the 126 MB L2, so there every timed step is preceded by a write of a 512 MB buffer (not timed)
+    state_bytes = per_gpu * (algorithmic_bytes_per_particle_step(n_phi) // 2)
+    flush = state_bytes < 1e9
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if flush else None
     barrier()
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
-        reps = h.evolve(args.steps)
+        if not flush:
+            reps = h.evolve(args.steps)
+            dev_ms = h.last_evolve_ms()
+        else:
+            reps, dev_ms = [], 0.0
+            for _ in range(args.steps):
+                flush_buf.fill_(1)
+                torch.cuda.synchronize()
+                reps += h.evolve(1)
+                dev_ms += h.last_evolve_ms()
         barrier()
         wall = time.perf_counter() - t0
-    dev_ms = h.last_evolve_ms()
     prof = h.profile(reset=True)
     launches = h.kernel_launches() - launches0
     psteps_local = float(sum(r.nParticles for r in reps))
@@ -342,13 +422,12 @@ def run_ours(args):
         achieved = bpp * k_particles / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic 3D hex-to-tet box {args.cells[0]}x{args.cells[1]}x{args.cells[2]} = {nc} cells, "
-                                   f"{args.ppc_per_gpu} particles/cell/GPU ({per_gpu} particles per GPU), SLMFull+IEM+RAS+cold, "
-                                   f"cell LTS, limitedSimple, number control, inletOutlet x-faces (BASELINE.json configs[4])",
+            "config": {"workload": workload_text(args, case, world, per_gpu),
                        "parallelism": f"particle-sharded x{world}, moment all-reduce", "n_phi": n_phi,
-                       "l2_policy": "inputs >> L2 (particle state %.1f GB per GPU)" % (per_gpu * (bpp / 2) / 1e9)},
+                       "l2_policy": ("inputs >> L2 (particle state %.1f GB per GPU)" % (state_bytes / 1e9)) if not flush
+                       else ("L2 flushed before every timed step (512 MB written); particle state %.3f GB per GPU" % (state_bytes / 1e9))},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "allreduce_ms_per_step": ar_ms / args.steps,
             "hbm_GBps_whole_step": bpp * psteps / world / (dev_ms * 1e-3) / 1e9,
@@ -356,7 +435,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_evolve", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(args, n_phi), "peak_source": peak_src,
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one k_evolve "
-                                           "launch of this workload (profiles/r01_k_evolve_jit_metrics.csv); null for other workloads",
+                                           f"launch of this workload (profiles/{TRAFFIC_PROFILE}); null for other workloads",
                          "algorithmic_bytes_per_launch": bpp * k_particles,
                          "algorithmic_bytes_per_particle_step": bpp},
             "e2e": {"value": e2e_psteps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -365,7 +444,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args)
+                line["cpu_baseline"] = cpu_baseline(args, ppc_per_gpu(args, 1))
             except Exception as e:  # the baseline must never hide the GPU number
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
@@ -381,11 +460,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, nargs=3, default=[200, 100, 100])
-    ap.add_argument("--ppc-per-gpu", type=int, default=64)
+    ap.add_argument("--ppc-per-gpu", type=int, default=-1, help="particles per cell and GPU (default: 64 for the synthetic box, the tutorial's own value otherwise)")
+    ap.add_argument("--config", default="synthetic", choices=["synthetic", "SydneyBluffBodyFlow", "SandiaD", "SydneyBluffBodyFlame", "SandiaPropaneJet4x"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--ppc-total", type=int, default=125, help="--scaling strong: particles per cell in total (125 x 2e6 cells = 2.5e8)")
     ap.add_argument("--ref-cells", type=int, nargs=3, default=[48, 24, 24])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spinup", type=int, default=10, help="set-up steps before the warm-up (not timed)")
     args = ap.parse_args()
+    if args.config == "synthetic" and args.ppc_per_gpu <= 0:
+        args.ppc_per_gpu = 64
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -194,10 +194,14 @@ typedef struct pdfb200_cell_fields {
     double *k;          /* kCloudPDF                                          */
     double *Phi[PDFB200_MAX_PHI];
     double *Cov[PDFB200_MAX_COV];
+    /* velocity-scalar flux <u'' phi''> = UPhiMom/mMom - U Phi, [nCells*3] per scalar. Not in the reference
+     * (its moments stop at mcParticleCloud.C:933-956); BASELINE north_star asks for "scalar fluxes".        */
+    double *UPhi[PDFB200_MAX_PHI];
     double *PaNIC;      /* particles per cell                                 */
     /* time-averaged moments (mMoment, VMoment, UMoment, <Phi>Moment, ...)    */
     double *mMom, *VMom, *UMom, *UUMom;
     double *PhiMom[PDFB200_MAX_PHI]; double *PhiPhiMom[PDFB200_MAX_COV];
+    double *UPhiMom[PDFB200_MAX_PHI];   /* time-averaged sum of eta m U phi, [nCells*3] per scalar */
 } pdfb200_cell_fields;
 
 typedef struct pdfb200_cloud pdfb200_cloud;   /* opaque handle */
@@ -255,6 +259,25 @@ int pdfb200_evolve(pdfb200_cloud *cloud, int32_t nSteps, pdfb200_step_report *re
 
 /* Cell fields of updateCloudPDF (mcParticleCloud.C:824-1009) back to the host. */
 int pdfb200_download_cell_fields(pdfb200_cloud *cloud, pdfb200_cell_fields *out);
+/* Restart: the time-averaged moment fields of a previous run instead of init_moments — the mMoment, VMoment,
+ * UMoment, UUMoment, <Phi>Moment and <Phi><Phi>Moment fields that mcParticleCloud's constructor reads with
+ * READ_IF_PRESENT (mcParticleCloud.C:339-517) and checkMoments() accepts only as a complete set (:739-820:
+ * "Moments are missing. Forced re-initialization."): any of them NULL -> PDFB200_ERR_INVALID and the caller
+ * falls back to pdfb200_init_moments. UPhiMom and PaNIC may be NULL (flux moments restart from the means,
+ * counts from zero). The mean fields (rho, U, Tau, k, Phi, Cov, pnd) are re-derived from the moments exactly
+ * as updateCloudPDF derives them (:958-1008). Call after upload_fv_fields / upload_cloud_fields.            */
+int pdfb200_upload_moments(pdfb200_cloud *cloud, const pdfb200_cell_fields *moments);
+/* The step counter: third word of every random-number counter (the keyed generator replaces
+ * OpenFOAM's Random, whose state the reference does not checkpoint). A restarted run that sets it to the value of
+ * the run it continues draws the same numbers that run would have drawn.                                     */
+int64_t pdfb200_step_counter(pdfb200_cloud *cloud);
+int pdfb200_set_step_counter(pdfb200_cloud *cloud, int64_t step);
+/* The id the next injected or cloned particle receives (ids key the random streams; Particle<>::origId in the
+ * reference). upload_particles sets it just above the largest id handed in; a restarted run that wants the
+ * particles it creates to carry the ids (and so the streams) the continued run would have given them restores
+ * the counter of that run. It must stay congruent to the rank modulo the number of ranks.                   */
+int64_t pdfb200_id_counter(pdfb200_cloud *cloud);
+int pdfb200_set_id_counter(pdfb200_cloud *cloud, int64_t nextId);
 
 /* current particle time step (mcParticleCloud::deltaT()) */
 double pdfb200_delta_t(pdfb200_cloud *cloud);

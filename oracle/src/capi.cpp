@@ -190,8 +190,48 @@ int pdforacle_download_cell_fields(pdforacle_cloud *h, pdfb200_cell_fields *o) {
     }
     for (int k = 0; k < c.prm.nPhi; ++k) { cp(o->Phi[k], c.PhicPdf[k].c); cp(o->PhiMom[k], c.PhiMom[k]); }
     for (int k = 0; k < c.nCov(); ++k) { cp(o->Cov[k], c.PhiPhicPdf[k].c); cp(o->PhiPhiMom[k], c.PhiPhiMom[k]); }
+    for (int k = 0; k < c.prm.nPhi; ++k)
+        for (int i = 0; i < nc; ++i) {
+            if (o->UPhi[k]) { const Vec3 &v = c.UPhiFlux[k][i]; o->UPhi[k][3 * i] = v.x; o->UPhi[k][3 * i + 1] = v.y; o->UPhi[k][3 * i + 2] = v.z; }
+            if (o->UPhiMom[k]) { const Vec3 &v = c.UPhiMom[k][i]; o->UPhiMom[k][3 * i] = v.x; o->UPhiMom[k][3 * i + 1] = v.y; o->UPhiMom[k][3 * i + 2] = v.z; }
+        }
     return PDFB200_OK;
 }
+
+// restart from the moment fields of a previous run (mcParticleCloud.C:339-517, checkMoments :739-820)
+int pdforacle_upload_moments(pdforacle_cloud *h, const pdfb200_cell_fields *m) {
+    ORACLE_TRY
+    Cloud &c = h->c;
+    const int nc = c.mesh.nCells;
+    bool complete = m->mMom && m->VMom && m->UMom && m->UUMom;
+    for (int k = 0; k < c.prm.nPhi; ++k) complete = complete && m->PhiMom[k];
+    for (int k = 0; k < c.nCov(); ++k) complete = complete && m->PhiPhiMom[k];
+    if (!complete) throw std::invalid_argument("upload_moments: Moments are missing (use init_moments)");
+    c.initMoments();   // sizes, boundary types of the derived fields
+    c.mMom.assign(m->mMom, m->mMom + nc); c.VMom.assign(m->VMom, m->VMom + nc);
+    for (int i = 0; i < nc; ++i) {
+        c.UMom[i] = Vec3(m->UMom[3 * i], m->UMom[3 * i + 1], m->UMom[3 * i + 2]);
+        const double *d = m->UUMom + 6 * i;
+        SymmTensor t; t.xx = d[0]; t.xy = d[1]; t.xz = d[2]; t.yy = d[3]; t.yz = d[4]; t.zz = d[5];
+        c.UUMom[i] = t;
+    }
+    for (int k = 0; k < c.prm.nPhi; ++k) c.PhiMom[k].assign(m->PhiMom[k], m->PhiMom[k] + nc);
+    for (int k = 0; k < c.nCov(); ++k) c.PhiPhiMom[k].assign(m->PhiPhiMom[k], m->PhiPhiMom[k] + nc);
+    for (int k = 0; k < c.prm.nPhi; ++k)
+        for (int i = 0; i < nc; ++i)
+            c.UPhiMom[k][i] = m->UPhiMom[k] ? Vec3(m->UPhiMom[k][3 * i], m->UPhiMom[k][3 * i + 1], m->UPhiMom[k][3 * i + 2])
+                                            : (c.PhiMom[k][i] / std::max(c.mMom[i], SMALL)) * c.UMom[i];
+    // the mean fields follow from the moments as in updateCloudPDF (:958-1008): existing weight 1, nothing new
+    const std::vector<double> none(c.momentBlockSize(), 0.0);
+    c.finaliseMoments(none, 1.0);
+    c.rhocPdfInst.c = c.rhocPdf.c; c.pndcPdfInst.c = c.pndcPdf.c;
+    if (m->PaNIC) c.PaNIC.assign(m->PaNIC, m->PaNIC + nc);
+    ORACLE_CATCH
+}
+int64_t pdforacle_id_counter(pdforacle_cloud *h) { return (int64_t)h->c.nextId; }
+int pdforacle_set_id_counter(pdforacle_cloud *h, int64_t id) { h->c.nextId = (uint32_t)id; return PDFB200_OK; }
+int64_t pdforacle_step_counter(pdforacle_cloud *h) { return (int64_t)h->c.step; }
+int pdforacle_set_step_counter(pdforacle_cloud *h, int64_t step) { h->c.step = (uint32_t)step; return PDFB200_OK; }
 
 double pdforacle_delta_t(pdforacle_cloud *h) { return h->c.deltaT; }
 int pdforacle_set_delta_t(pdforacle_cloud *h, double dt) { h->c.deltaT = dt; return PDFB200_OK; }

@@ -623,10 +623,11 @@ void Cloud::adjustAxiSymmetricMass(std::vector<Particle *> &ps) const {
 // updateCloudPDF (mcParticleCloud.C:824-1009), split into the particle loop
 // (:933-956) and the time-averaging / derived fields (:958-1008) so that a
 // particle-sharded run can sum the instantaneous block across ranks in between.
-// Block layout per cell: N, M, V, MU(3), MPhi(nPhi), MPhiPhi(nCov), MUU(6).
+// Block layout per cell: N, M, V, MU(3), MPhi(nPhi), MPhiPhi(nCov), MUU(6), MUPhi(3 nPhi)
+// (the last group is the velocity-scalar flux moment, new: not in the reference).
 // ---------------------------------------------------------------------------
 void Cloud::accumulateInstantMoments(std::vector<double> &block) const {
-    const int nM = 12 + prm.nPhi + nCov();
+    const int nM = nMoments();
     block.assign(momentBlockSize(), 0.0);
     for (const Particle &p : particles) {
         double *b = &block[(size_t)p.cell * nM];
@@ -644,11 +645,16 @@ void Cloud::accumulateInstantMoments(std::vector<double> &block) const {
         double *uu = b + 6 + prm.nPhi + nCov();
         uu[0] += mpd * (Up.x * Up.x); uu[1] += mpd * (Up.x * Up.y); uu[2] += mpd * (Up.x * Up.z);
         uu[3] += mpd * (Up.y * Up.y); uu[4] += mpd * (Up.y * Up.z); uu[5] += mpd * (Up.z * Up.z);
+        double *up = uu + 6;
+        for (int i = 0; i < prm.nPhi; ++i) {
+            const double mp = mpd * p.Phi[i];
+            up[3 * i] += mp * Up.x; up[3 * i + 1] += mp * Up.y; up[3 * i + 2] += mp * Up.z;
+        }
     }
 }
 
 void Cloud::finaliseMoments(const std::vector<double> &block, double existWt) {
-    const int nc = mesh.nCells, nM = 12 + prm.nPhi + nCov();
+    const int nc = mesh.nCells, nM = nMoments();
     const double newWt = 1.0 - existWt;
     const double SMALL_MASS = SMALL, SMALL_VOLUME = SMALL;
     for (int c = 0; c < nc; ++c) {
@@ -684,6 +690,12 @@ void Cloud::finaliseMoments(const std::vector<double> &block, double existWt) {
         T.xx = M.xx / mB - u.x * u.x; T.xy = M.xy / mB - u.x * u.y; T.xz = M.xz / mB - u.x * u.z;
         T.yy = M.yy / mB - u.y * u.y; T.yz = M.yz / mB - u.y * u.z; T.zz = M.zz / mB - u.z * u.z;
         kcPdf.c[c] = 0.5 * (T.xx + T.yy + T.zz);
+        const double *up = uu + 6;
+        for (int i = 0; i < prm.nPhi; ++i) {
+            Vec3 &F = UPhiMom[i][c];
+            F = existWt * F + newWt * Vec3(up[3 * i], up[3 * i + 1], up[3 * i + 2]);
+            UPhiFlux[i][c] = F / mB - PhicPdf[i].c[c] * u;
+        }
     }
     applyBC(pndcPdfInst); applyBC(pndcPdf); applyBC(rhocPdfInst); applyBC(rhocPdf);
     applyBC(UcPdf);

@@ -260,6 +260,7 @@ void Cloud::initMoments() {
     const int nc = mesh.nCells, nb = nBnd();
     mMom.resize(nc); VMom.resize(nc); UMom.resize(nc); UUMom.resize(nc);
     PhiMom.assign(prm.nPhi, std::vector<double>(nc)); PhiPhiMom.assign(nCov(), std::vector<double>(nc));
+    UPhiMom.assign(prm.nPhi, std::vector<Vec3>(nc)); UPhiFlux.assign(prm.nPhi, std::vector<Vec3>(nc));
     rhocPdfInst = rhocPdf; pndcPdf = rhocPdf; pndcPdfInst = rhocPdf;
     UcPdf.c = Ufv.c; UcPdf.b = Ufv.b; UcPdf.fixed = Ufv.fixed;
     applyBC(UcPdf);
@@ -280,6 +281,8 @@ void Cloud::initMoments() {
         int pp = 0;
         for (int i = 0; i < prm.nPhi; ++i) {
             PhiMom[i][c] = mMom[c] * PhicPdf[i].c[c];
+            UPhiMom[i][c] = (mMom[c] * PhicPdf[i].c[c]) * u;   // zero flux to start with
+            UPhiFlux[i][c] = Vec3();
             for (int j = i; j < prm.nPhi; ++j, ++pp)
                 PhiPhiMom[pp][c] = mMom[c] * (PhiPhicPdf[pp].c[c] + PhicPdf[i].c[c] * PhicPdf[j].c[c]);
         }

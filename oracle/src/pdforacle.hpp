@@ -296,6 +296,7 @@ struct Cloud {
     std::vector<double> PaNIC, lostMass;
     // moments
     std::vector<double> mMom, VMom; std::vector<Vec3> UMom; std::vector<SymmTensor> UUMom;
+    std::vector<std::vector<Vec3>> UPhiMom, UPhiFlux;   // [nPhi][nCells]: time-averaged sum of eta m U phi, and <u'' phi''>
     std::vector<std::vector<double>> PhiMom, PhiPhiMom;
 
     // flamelet tables
@@ -366,7 +367,8 @@ struct Cloud {
     // split step for particle-sharded multi-rank runs
     void evolveBegin(pdfb200_step_report *rep, std::vector<double> &momentBlock);
     void evolveEnd(pdfb200_step_report *rep, const std::vector<double> &momentBlock);
-    int momentBlockSize() const { return mesh.nCells * (12 + prm.nPhi + nCov()) + 32; }
+    int nMoments() const { return 12 + prm.nPhi + nCov() + 3 * prm.nPhi; }   // N, M, V, MU, MPhi, MPhiPhi, MUU, MUPhi
+    int momentBlockSize() const { return mesh.nCells * nMoments() + 32; }
 
     // models on one particle (mcModel::correct(mcParticle&))
     void omegaCorrect(Particle &p) const;               // mcRASOmegaModel.C:125-147

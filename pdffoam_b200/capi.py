@@ -118,10 +118,10 @@ class CellFieldsStruct(C.Structure):
     _fields_ = [
         ("rho", c_double_p), ("rhoInst", c_double_p), ("pnd", c_double_p), ("pndInst", c_double_p),
         ("U", c_double_p), ("Tau", c_double_p), ("k", c_double_p),
-        ("Phi", c_double_p * MAX_PHI), ("Cov", c_double_p * MAX_COV),
+        ("Phi", c_double_p * MAX_PHI), ("Cov", c_double_p * MAX_COV), ("UPhi", c_double_p * MAX_PHI),
         ("PaNIC", c_double_p),
         ("mMom", c_double_p), ("VMom", c_double_p), ("UMom", c_double_p), ("UUMom", c_double_p),
-        ("PhiMom", c_double_p * MAX_PHI), ("PhiPhiMom", c_double_p * MAX_COV),
+        ("PhiMom", c_double_p * MAX_PHI), ("PhiPhiMom", c_double_p * MAX_COV), ("UPhiMom", c_double_p * MAX_PHI),
     ]
 
 
@@ -179,7 +179,7 @@ class PdfError(RuntimeError):
 API_SYMBOLS = [
     "last_error", "create", "destroy", "set_params", "set_flamelet_tables", "upload_fv_fields",
     "upload_cloud_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
-    "download_particles", "evolve", "download_cell_fields", "delta_t", "set_delta_t",
+    "download_particles", "evolve", "download_cell_fields", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
     "kernel_launches", "last_evolve_ms", "profile", "jit_source", "jit_compile", "rng_probe",
 ]
@@ -219,6 +219,11 @@ class Library:
         f("download_particles").argtypes = [vp, C.c_int64, C.POINTER(ParticlesStruct), C.POINTER(C.c_int64)]
         f("evolve").argtypes = [vp, C.c_int32, C.POINTER(StepReport)]
         f("download_cell_fields").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("upload_moments").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("step_counter").argtypes = [vp]; f("step_counter").restype = C.c_int64
+        f("set_step_counter").argtypes = [vp, C.c_int64]
+        f("id_counter").argtypes = [vp]; f("id_counter").restype = C.c_int64
+        f("set_id_counter").argtypes = [vp, C.c_int64]
         f("delta_t").argtypes = [vp]; f("delta_t").restype = C.c_double
         f("set_delta_t").argtypes = [vp, C.c_double]
         f("mesh_info_get").argtypes = [vp, C.POINTER(MeshInfo)]
@@ -445,15 +450,18 @@ class CloudHandle:
         nc = self.mesh.n_cells
         out = dict(rho=np.zeros(nc), rhoInst=np.zeros(nc), pnd=np.zeros(nc), pndInst=np.zeros(nc), U=np.zeros((nc, 3)),
                    Tau=np.zeros((nc, 6)), k=np.zeros(nc), Phi=[np.zeros(nc) for _ in range(self.n_phi)],
-                   Cov=[np.zeros(nc) for _ in range(self.n_cov)], PaNIC=np.zeros(nc))
+                   Cov=[np.zeros(nc) for _ in range(self.n_cov)], PaNIC=np.zeros(nc),
+                   UPhi=[np.zeros((nc, 3)) for _ in range(self.n_phi)])
         if moments:
             out.update(mMom=np.zeros(nc), VMom=np.zeros(nc), UMom=np.zeros((nc, 3)), UUMom=np.zeros((nc, 6)),
-                       PhiMom=[np.zeros(nc) for _ in range(self.n_phi)], PhiPhiMom=[np.zeros(nc) for _ in range(self.n_cov)])
+                       PhiMom=[np.zeros(nc) for _ in range(self.n_phi)], PhiPhiMom=[np.zeros(nc) for _ in range(self.n_cov)],
+                       UPhiMom=[np.zeros((nc, 3)) for _ in range(self.n_phi)])
         s = CellFieldsStruct()
         for k in ("rho", "rhoInst", "pnd", "pndInst", "U", "Tau", "k", "PaNIC"):
             setattr(s, k, _dp(out[k]))
         for i in range(self.n_phi):
             s.Phi[i] = _dp(out["Phi"][i])
+            s.UPhi[i] = _dp(out["UPhi"][i])
         for i in range(self.n_cov):
             s.Cov[i] = _dp(out["Cov"][i])
         if moments:
@@ -461,10 +469,40 @@ class CloudHandle:
                 setattr(s, k, _dp(out[k]))
             for i in range(self.n_phi):
                 s.PhiMom[i] = _dp(out["PhiMom"][i])
+                s.UPhiMom[i] = _dp(out["UPhiMom"][i])
             for i in range(self.n_cov):
                 s.PhiPhiMom[i] = _dp(out["PhiPhiMom"][i])
         self.lib.check(self.lib.fn("download_cell_fields")(self.h, C.byref(s)), "download_cell_fields")
         return out
+
+    def upload_moments(self, cf: Dict[str, np.ndarray]):
+        """Restart from the moment fields of a previous run (pdfb200_upload_moments); cf as returned by
+        download_cell_fields(moments=True). Missing keys are passed as NULL."""
+        s = CellFieldsStruct()
+        keep = []
+
+        def d(a):
+            a = np.ascontiguousarray(a, np.float64); keep.append(a); return _dp(a)
+        for k in ("mMom", "VMom", "UMom", "UUMom", "PaNIC"):
+            if cf.get(k) is not None:
+                setattr(s, k, d(cf[k]))
+        for name, n in (("PhiMom", self.n_phi), ("PhiPhiMom", self.n_cov), ("UPhiMom", self.n_phi)):
+            if cf.get(name) is not None:
+                for i in range(n):
+                    getattr(s, name)[i] = d(cf[name][i])
+        self.lib.check(self.lib.fn("upload_moments")(self.h, C.byref(s)), "upload_moments")
+
+    def step_counter(self) -> int:
+        return int(self.lib.fn("step_counter")(self.h))
+
+    def id_counter(self) -> int:
+        return int(self.lib.fn("id_counter")(self.h))
+
+    def set_id_counter(self, next_id: int):
+        self.lib.check(self.lib.fn("set_id_counter")(self.h, int(next_id)), "set_id_counter")
+
+    def set_step_counter(self, step: int):
+        self.lib.check(self.lib.fn("set_step_counter")(self.h, int(step)), "set_step_counter")
 
     # ---- introspection ----
     def mesh_info(self) -> MeshInfo:

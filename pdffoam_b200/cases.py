@@ -354,3 +354,163 @@ def wedge_jet(nx=24, nr_jet=4, nr_co=10, length=0.3, r_min=2e-4, r_jet=3.6e-3, r
                          relaxTimeU=1e-5, relaxTimek=1e-5)
     # cell volumes of the wedge hexes: (r2^2 - r1^2)/2 * 2*theta ... computed by the library; keep the case light
     return Case(name=f"wedgeJet{nx}x{nr_jet + nr_co}", mesh=mesh, params=prm, fv=fv, cf=cf, info=dict(theta=th))
+
+
+# ---------------------------------------------------------------------------
+# The four tutorial configurations of BASELINE.json configs[0..3]:
+# mesh shape, patch set, scalar set, model selection and numerics follow the cited tutorial
+# files; the frozen FV fields are synthetic jet profiles (OpenFOAM's RAS solution is not
+# available here), which is what "synthetic data of that shape" means for these cases.
+# ---------------------------------------------------------------------------
+def _streams_case(name: str, xs, r_blocks, half_angle_deg, streams, tables_path: Optional[str], scalars: Sequence[str],
+                  reaction: str, numerics: Dict, golden_dir: Optional[str] = None) -> Case:
+    """streams: [(patch name, r_upper, U, z, rho, handler)] from the axis outwards;
+    r_blocks: [(n cells, r_lo, r_hi, grading)] (blockMesh blocks in r)."""
+    rs = np.concatenate([meshgen.graded(n, lo, hi, g)[(1 if i else 0):] for i, (n, lo, hi, g) in enumerate(r_blocks)])
+    mesh = meshgen.wedge_mesh(xs, rs, half_angle_deg, inlet_split=[(s[0], s[1], s[5]) for s in streams])
+    th = np.deg2rad(half_angle_deg)
+    cc = mesh.cell_centres_simple()
+    fcb = mesh.face_centres_simple()[mesh.n_internal_faces:]
+    own = _bnd_owner(mesh)
+    nc, nb = mesh.n_cells, mesh.n_boundary_faces
+    length = float(xs[-1])
+    inflow = [s for s in streams if s[5] == meshgen.BC_INLET_OUTLET]
+    r_jet, U_jet, U_co = inflow[0][1], inflow[0][2], inflow[-1][2]
+
+    def radius(x):
+        return np.hypot(x[:, 1], x[:, 2])
+
+    def stream_of(r):
+        idx = np.searchsorted(np.array([s[1] for s in streams]), r, side="left")
+        return np.minimum(idx, len(streams) - 1)
+
+    def Ufun(x):
+        r = radius(x)
+        spread = r_jet * (1 + 8.0 * x[:, 0] / length)
+        ux = U_co + (U_jet - U_co) * (r_jet / spread) * np.exp(-(r / spread) ** 2)
+        for s in inflow[1:-1]:                                   # pilot-like annular streams decay into the coflow
+            w = s[1] * (1 + 3.0 * x[:, 0] / length)
+            ux = ux + (s[2] - U_co) * np.exp(-(r / w) ** 4) * np.exp(-6.0 * x[:, 0] / length) * (r > r_jet)
+        ur = 0.02 * ux * r / spread
+        return np.stack([ux, ur, np.zeros_like(ux)], axis=1)
+
+    def kfun(x):
+        return 0.01 * Ufun(x)[:, 0] ** 2 + 0.05
+
+    def zfun(x):
+        r = radius(x)
+        spread = r_jet * (1 + 8.0 * x[:, 0] / length)
+        return np.clip((r_jet / spread) * np.exp(-(r / spread) ** 2), 0.0, 1.0)
+
+    lt = 0.5 * r_jet * 10
+    U = Ufun(cc); k = kfun(cc); eps = 0.09 ** 0.75 * k ** 1.5 / lt
+    p = np.zeros(nc)
+    R = np.zeros((nc, 6)); R[:, 0] = R[:, 3] = R[:, 5] = 2.0 / 3.0 * k
+    Ub = U[own].copy(); kb = k[own].copy(); epsb = eps[own].copy(); pb = p[own].copy(); Rb = R[own].copy()
+    fixed = [s[0] for s in inflow]
+    z = zfun(cc); zb = z[own].copy()
+    rho_in = np.ones(nb)
+    for s in streams:
+        sl = mesh.boundary_slice(s[0])
+        if s[5] == meshgen.BC_INLET_OUTLET:
+            Ub[sl] = 0.0; Ub[sl, 0] = s[2]
+            kb[sl] = 0.01 * s[2] ** 2 + 0.05; epsb[sl] = 0.09 ** 0.75 * kb[sl] ** 1.5 / lt
+            Rb[sl] = 0; Rb[sl, 0] = Rb[sl, 3] = Rb[sl, 5] = 2.0 / 3.0 * kb[sl]
+            zb[sl] = s[3]; rho_in[sl] = s[4]
+        else:                                                    # bluff-body face: slip wall
+            Ub[sl, 0] = 0.0
+    for pname in ("axis", "outerWall"):
+        Ub[mesh.boundary_slice(pname), 1] = 0.0
+    for pname, sign in (("back", -1.0), ("front", 1.0)):
+        sl = mesh.boundary_slice(pname)
+        n = np.array([0.0, -np.sin(th), np.cos(th)]) if sign > 0 else np.array([0.0, -np.sin(th), -np.cos(th)])
+        cn = np.array([0.0, 0.0, 1.0]) if sign > 0 else np.array([0.0, 0.0, -1.0])
+        Ub[sl] = U[own][sl] @ _rotation_tensor(cn, n).T
+    fv = dict(U=U, Ub=Ub, UbFixed=_flags(mesh, fixed), p=p, pb=pb, k=k, kb=kb, kbFixed=_flags(mesh, fixed),
+              epsilon=eps, epsilonb=epsb, R=R, Rb=Rb)
+    tables = None
+    rho = np.ones(nc)
+    if reaction == "SteadyFlamelet":
+        tables = load_flamelet_tables(tables_path)
+        rho = np.interp(z, tables["z"], tables["fields"][0][0])
+    elif reaction == "cold":
+        rho = np.full(nc, inflow[-1][4])
+    rhob = rho[own].copy()
+    for s in inflow:
+        rhob[mesh.boundary_slice(s[0])] = s[4]
+    n_phi = len(scalars)
+    Phi, Phib, PhibFixed = [z], [zb], [_flags(mesh, fixed)]
+    for _ in scalars[1:]:
+        Phi.append(np.zeros(nc)); Phib.append(np.zeros(nb)); PhibFixed.append(np.zeros(nb, np.uint8))
+    n_cov = n_phi * (n_phi + 1) // 2
+    cov = [np.zeros(nc) for _ in range(n_cov)]
+    cov[0] = 0.05 * z * (1 - z)
+    cf = dict(rho=rho, rhob=rhob, rhobFixed=_flags(mesh, fixed), Phi=Phi, Phib=Phib, PhibFixed=PhibFixed,
+              Cov=cov, Covb=[c[own].copy() for c in cov], CovbFixed=[np.zeros(nb, np.uint8)] * n_cov)
+    kw = dict(mixed=[0], conserved=[0], reactionModel=reaction, zIdx=0, kMin=1e-8, DNum=0.05, Omega0=1e5,
+              particleNumberControl=1, cloneAt=0.8, eliminateAt=1.2, localTimeStepping="cell", positionCorrection="limitedSimple",
+              relaxTimeU=1e-5, relaxTimek=1e-5)
+    if reaction == "SteadyFlamelet":
+        kw.update(chiIdx=list(scalars).index("chi"), addedIdx=[list(scalars).index("T")], Cchi=2.0)
+    elif reaction == "BurkeSchumann":
+        # tutorials/SandiaPropaneJet/constant/thermophysicalProperties:22-31
+        kw.update(TIdx=list(scalars).index("T"), bsRox=287.007, bsRfuel=188.554, bsRstoi=237.780, bsTox=294.0, bsTfuel=294.0,
+                  bsTstoi=294.0, bsZstoi=0.5)
+        fv["p"] = fv["p"] + 1.0e5; fv["pb"] = fv["pb"] + 1.0e5
+        cf["rho"] = 1.0e5 / (287.007 * 294.0) * np.ones(nc); cf["rhob"] = cf["rho"][own].copy()
+    kw.update(numerics)
+    prm = default_params(n_phi, **kw)
+    return Case(name=name, mesh=mesh, params=prm, fv=fv, cf=cf, tables=tables, info=dict(theta=th, r_jet=r_jet, streams=streams))
+
+
+TUTORIALS = ("SydneyBluffBodyFlow", "SandiaD", "SydneyBluffBodyFlame", "SandiaPropaneJet4x")
+
+
+def tutorial_case(name: str, ppc: Optional[int] = None, refine: int = 1, golden_dir: Optional[str] = None) -> Case:
+    """The four tutorial-shaped configurations of BASELINE.json (configs[0..3]); `refine` multiplies the cell
+    counts of the blockMesh blocks in x and r, `ppc` overrides the particles per cell."""
+    import os
+    IO, SLIP = meshgen.BC_INLET_OUTLET, meshgen.BC_SLIP
+    if golden_dir is None:
+        golden_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    f = refine
+    if name == "SandiaD":
+        # tutorials/SandiaD/constant/polyMesh/blockMeshDict:22-48: blocks (1 54 8)(1 54 6)(1 54 20), grading x 15, r 2/2/8;
+        # D = 7.2 mm, pilot to 18.2 mm; inlet z and rho from 0.org/z, 0.org/rho; system/mcThermoCloudSolution:11-53
+        return _streams_case(
+            "SandiaD", meshgen.graded(54 * f, 0.0, 0.8, 15.0),
+            [(8 * f, 1.5e-4, 3.6e-3, 2.0), (6 * f, 3.6e-3, 9.1e-3, 2.0), (20 * f, 9.1e-3, 0.15, 8.0)], 5.0,
+            [("jet", 3.6e-3, 49.6, 1.0, 1.08147, IO), ("pilot", 9.1e-3, 11.4, 0.268692, 0.178466, IO), ("coflow", 1e30, 0.9, 0.0, 1.21731, IO)],
+            os.path.join(golden_dir, "flamelet_sandiaD.npz"), ("z", "chi", "T"), "SteadyFlamelet",
+            dict(CFL=0.3, averagingCoeff=2e4, particlesPerCell=ppc or 40, ltsUpperBound=50.0, pcC=5e-2, Cmix=2.0, mixingModel="IEM"))
+    if name == "SydneyBluffBodyFlame":
+        # tutorials/SydneyBluffBodyFlame/constant/polyMesh/blockMeshDict:22-48: blocks (1 80 6)(1 80 40)(1 80 34);
+        # jet r = 1.8 mm, bluff body r = 25 mm (slip), coflow to 150 mm; BASELINE configs[2]: modified-Curl mixing
+        return _streams_case(
+            "SydneyBluffBodyFlame", meshgen.graded(80 * f, 0.0, 0.3, 4.0),
+            [(6 * f, 1.5e-4, 1.8e-3, 1.0), (40 * f, 1.8e-3, 25e-3, 1.0), (34 * f, 25e-3, 0.15, 6.0)], 5.0,
+            [("jet", 1.8e-3, 108.0, 1.0, 0.84, IO), ("bluffBody", 25e-3, 0.0, 0.0, 1.0, SLIP), ("coflow", 1e30, 35.0, 0.0, 1.2, IO)],
+            os.path.join(golden_dir, "flamelet_bluffbody.npz"), ("z", "chi", "T"), "SteadyFlamelet",
+            dict(CFL=0.1, averagingCoeff=5e3, particlesPerCell=ppc or 40, ltsUpperBound=20.0, pcC=0.2, Cmix=2.0,
+                 mixingModel="modifiedCurl", relaxTimeU=5e-5, relaxTimek=5e-5))
+    if name == "SydneyBluffBodyFlow":
+        # tutorials/SydneyBluffBodyFlow/flow/constant/polyMesh/blockMeshDict:46-48: blocks (1 64 6)(1 64 24)(1 64 34);
+        # scalars case: (z), cold, IEM, ~100 particles per cell (BASELINE configs[0])
+        return _streams_case(
+            "SydneyBluffBodyFlow", meshgen.graded(64 * f, 0.0, 0.3, 4.0),
+            [(6 * f, 1.5e-4, 1.8e-3, 1.0), (24 * f, 1.8e-3, 25e-3, 1.0), (34 * f, 25e-3, 0.15, 6.0)], 5.0,
+            [("jet", 1.8e-3, 61.0, 1.0, 1.2, IO), ("bluffBody", 25e-3, 0.0, 0.0, 1.2, SLIP), ("coflow", 1e30, 20.0, 0.0, 1.2, IO)],
+            None, ("z",), "cold",
+            dict(CFL=0.1, averagingCoeff=1e3, particlesPerCell=ppc or 100, ltsUpperBound=20.0, pcC=0.2, Cmix=2.0, mixingModel="IEM",
+                 coldDensity=1.2))
+    if name == "SandiaPropaneJet4x":
+        # tutorials/SandiaPropaneJet/constant/polyMesh/blockMeshDict:9-36: blocks (54 7 1)(54 5 1)(54 24 1), grading x 6,
+        # half-angle 2.5 deg; BASELINE configs[3]: mesh refined 4x, 400 particles per cell
+        g = 4 * f
+        return _streams_case(
+            "SandiaPropaneJet4x", meshgen.graded(54 * g, 0.0, 0.3, 6.0),
+            [(7 * g, 1.0e-4, 2.6e-3, 1.0), (5 * g, 2.6e-3, 4.5e-3, 1.0), (24 * g, 4.5e-3, 0.04, 6.0)], 2.5,
+            [("jet", 2.6e-3, 69.0, 1.0, 1.8, IO), ("bluffBody", 4.5e-3, 0.0, 0.0, 1.2, SLIP), ("coflow", 1e30, 9.2, 0.0, 1.2, IO)],
+            None, ("z", "T"), "BurkeSchumann",
+            dict(CFL=0.1, averagingCoeff=5e3, particlesPerCell=ppc or 400, ltsUpperBound=20.0, pcC=0.2, Cmix=2.0, mixingModel="IEM"))
+    raise KeyError(f"unknown tutorial case {name}; valid: {TUTORIALS}")

@@ -75,7 +75,7 @@ void Cloud::setParams(const pdfb200_params &p) {
     prm.C0 = fmax(0.0, prm.C0);                    // mcSLMFullVelocityModel.C:97-98
     prm.C1 = fmax(0.0, fmin(1.0, prm.C1));
     nCov = prm.nPhi * (prm.nPhi + 1) / 2;
-    nMom = 12 + prm.nPhi + nCov;
+    nMom = 12 + prm.nPhi + nCov + 3 * prm.nPhi;   // N, M, V, MU(3), MPhi, MPhiPhi, MUU(6), MUPhi(3 nPhi)
     cellAuxStride = 2 + prm.nPhi;
 }
 
@@ -172,6 +172,40 @@ int pdfb200_download_particles(pdfb200_cloud *c, int64_t maxn, pdfb200_particles
 }
 int pdfb200_evolve(pdfb200_cloud *c, int32_t nSteps, pdfb200_step_report *reports) { USE_DEVICE(c); return guarded([&] { H(c)->evolve(nSteps, reports); }); }
 int pdfb200_download_cell_fields(pdfb200_cloud *c, pdfb200_cell_fields *o) { USE_DEVICE(c); return guarded([&] { H(c)->downloadCellFields(*o); }); }
+int pdfb200_upload_moments(pdfb200_cloud *c, const pdfb200_cell_fields *m) {
+    if (!m) { g_err = "upload_moments: null argument"; return PDFB200_ERR_INVALID; }
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->uploadMoments(*m); });
+}
+int64_t pdfb200_id_counter(pdfb200_cloud *c) {
+    USE_DEVICE(c);
+    uint32_t v = 0;
+    if (cudaMemcpy(&v, &c->c.scal.p->nextId, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+int pdfb200_set_id_counter(pdfb200_cloud *c, int64_t id) {
+    USE_DEVICE(c);
+    return guarded([&] {
+        Cloud &C = c->c;
+        if (id < 0 || id > 0xffffffffLL) throw std::invalid_argument("set_id_counter: out of range");
+        if (id % C.nRanks != C.rank) throw std::invalid_argument("set_id_counter: the id must be congruent to the rank modulo the number of ranks");
+        const uint32_t v = (uint32_t)id;
+        C.hScal->nextId = v;
+        CUDA_CHECK(cudaMemcpy(&C.scal.p->nextId, &v, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    });
+}
+int64_t pdfb200_step_counter(pdfb200_cloud *c) { return (int64_t)c->c.stepHost; }
+int pdfb200_set_step_counter(pdfb200_cloud *c, int64_t step) {
+    USE_DEVICE(c);
+    return guarded([&] {
+        Cloud &C = c->c;
+        if (step < 0 || step > 0xffffffffLL) throw std::invalid_argument("set_step_counter: out of range");
+        const uint32_t s32 = (uint32_t)step;
+        C.stepHost = s32;
+        C.hScal->step = s32;   // seed/upload push the whole mirror back to the device
+        CUDA_CHECK(cudaMemcpy(&C.scal.p->step, &s32, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    });
+}
 
 double pdfb200_delta_t(pdfb200_cloud *c) { return c->c.deltaTHost; }
 int pdfb200_set_delta_t(pdfb200_cloud *c, double dt) {

@@ -89,7 +89,7 @@ struct Cloud {
     DBuf<unsigned> lostCount;
     bool lostDirty = false;                        // lostMass holds non-zero entries from the last step
     // time-averaged moments
-    DBuf<double> mMom, VMom, UMom, UUMom, PhiMom, PhiPhiMom;
+    DBuf<double> mMom, VMom, UMom, UUMom, PhiMom, PhiPhiMom, UPhiMom, UPhi_c;
     DBuf<double> momentBlock;                      // [nCells*nMom + BLOCK_TAIL]
     // step work arrays
     DBuf<double> phiPC, UPC_c, OmegaRaw_c, etaRaw_c;
@@ -142,6 +142,7 @@ struct Cloud {
     void uploadFv(const pdfb200_fv_fields &f);
     void uploadCloudFields(const pdfb200_cloud_fields &f);
     void initMoments();
+    void uploadMoments(const pdfb200_cell_fields &m);
     void allocParticles();
     void seedParticles();
     void uploadParticles(int64_t n, const pdfb200_particles &p);

@@ -21,7 +21,7 @@ struct FieldPtrs {
     double *Phi_c, *Phi_b, *Cov_c, *Cov_b;
     const uint8_t *rhoFixed, *kbFixed, *PhiFixed, *CovFixed;
     double *PaNIC, *lostMass, *lostShare;
-    double *mMom, *VMom, *UMom, *UUMom, *PhiMom, *PhiPhiMom;
+    double *mMom, *VMom, *UMom, *UUMom, *PhiMom, *PhiPhiMom, *UPhiMom, *UPhi_c;   // UPhi*: [nPhi][nCells][3]
     // work
     double *phiPC, *UPC_c, *OmegaRaw_c, *etaRaw_c;
     double *nodeMid, *nodePC, *cellAux;
@@ -36,7 +36,7 @@ static FieldPtrs fieldPtrs(Cloud &c) {
     f.Phi_c = c.Phi_c.p; f.Phi_b = c.Phi_b.p; f.Cov_c = c.Cov_c.p; f.Cov_b = c.Cov_b.p;
     f.rhoFixed = c.rhoFixed.p; f.kbFixed = c.kbFixed.p; f.PhiFixed = c.PhiFixed.p; f.CovFixed = c.CovFixed.p;
     f.PaNIC = c.PaNIC.p; f.lostMass = c.lostMass.p; f.lostShare = c.lostShare.p;
-    f.mMom = c.mMom.p; f.VMom = c.VMom.p; f.UMom = c.UMom.p; f.UUMom = c.UUMom.p; f.PhiMom = c.PhiMom.p; f.PhiPhiMom = c.PhiPhiMom.p;
+    f.mMom = c.mMom.p; f.VMom = c.VMom.p; f.UMom = c.UMom.p; f.UUMom = c.UUMom.p; f.PhiMom = c.PhiMom.p; f.PhiPhiMom = c.PhiPhiMom.p; f.UPhiMom = c.UPhiMom.p; f.UPhi_c = c.UPhi_c.p;
     f.phiPC = c.phiPC.p; f.UPC_c = c.UPC_c.p; f.OmegaRaw_c = c.OmegaRaw_c.p; f.etaRaw_c = c.etaRaw_c.p;
     f.nodeMid = c.nodeMid.p; f.nodePC = c.nodePC.p; f.cellAux = c.cellAux.p;
     return f;
@@ -309,6 +309,8 @@ __global__ void k_init_moments(DMesh M, FieldPtrs F, int nPhi) {
     for (int i = 0; i < nPhi; ++i) {
         const double pi = F.Phi_c[(size_t)i * M.nCells + c];
         F.PhiMom[(size_t)i * M.nCells + c] = mM * pi;
+        st3(F.UPhiMom, (size_t)i * M.nCells + c, (mM * pi) * u);   // zero flux to start with
+        st3(F.UPhi_c, (size_t)i * M.nCells + c, mk(0, 0, 0));
         for (int j = i; j < nPhi; ++j, ++pp)
             F.PhiPhiMom[(size_t)pp * M.nCells + c] = mM * (F.Cov_c[(size_t)pp * M.nCells + c] + pi * F.Phi_c[(size_t)j * M.nCells + c]);
     }
@@ -321,14 +323,17 @@ __global__ void k_init_moments(DMesh M, FieldPtrs F, int nPhi) {
 // sums of E15 (:1376-1381,1432-1433). Partial row: sums [ |rhoErr|, totalMass,
 // totalParticleMass ], maxima [ -rhoErrMin, rhoErrMax ].
 // ---------------------------------------------------------------------------
+// deriveOnly: restart from uploaded moments (pdfb200_upload_moments): existing weight 1, the block is not read.
 __global__ void k_finalise(DMesh M, FieldPtrs F, pdfb200_params P, const double *block, int nMom, int nCov,
-                           double *partSum, double *partMax) {
+                           double *partSum, double *partMax, int deriveOnly) {
     __shared__ double sm[3 * 32];
     double s[3] = {0, 0, 0}, mx[2] = {-PDF_VGREAT, -PDF_VGREAT};
-    const double existWt = (P.averagingCoeff - 1.) / P.averagingCoeff, newWt = 1.0 - existWt;
+    const double existWt = deriveOnly ? 1.0 : (P.averagingCoeff - 1.) / P.averagingCoeff, newWt = 1.0 - existWt;
     const int nPhi = P.nPhi;
+    double zeros[12 + 2 * PDFB200_MAX_PHI + PDFB200_MAX_COV + 3 * PDFB200_MAX_PHI];
+    if (deriveOnly) for (int k = 0; k < nMom; ++k) zeros[k] = 0.0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < M.nCells; c += gridDim.x * blockDim.x) {
-        const double *b = block + (size_t)c * nMom;
+        const double *b = deriveOnly ? zeros : block + (size_t)c * nMom;
         F.PaNIC[c] = b[0];
         const double mI = b[1], VI = b[2];
         const double voa = M.volumeOrArea[c];
@@ -368,6 +373,13 @@ __global__ void k_finalise(DMesh M, FieldPtrs F, pdfb200_params P, const double 
         tau[3] = uu[3] / mB - u.y * u.y; tau[4] = uu[4] / mB - u.y * u.z; tau[5] = uu[5] / mB - u.z * u.z;
         // bound(kcPdf_, kMin) restated as a floor
         F.kpdf_c[c] = fmax(0.5 * (tau[0] + tau[3] + tau[5]), P.kMin);
+        const double *upI = uuI + 6;
+        for (int i = 0; i < nPhi; ++i) {
+            const size_t o = (size_t)i * M.nCells + c;
+            const V3 fm = existWt * ld3(F.UPhiMom, o) + newWt * mk(upI[3 * i], upI[3 * i + 1], upI[3 * i + 2]);
+            st3(F.UPhiMom, o, fm);
+            st3(F.UPhi_c, o, fm / mB - phi[i] * u);
+        }
         const double e = (pnd - rho) / rho;
         s[0] += fabs(e);
         const double V = M.cellVolumes[c];
@@ -445,6 +457,7 @@ void Cloud::initMoments() {
     rhoInst_c.alloc(nc); pnd_c.alloc(nc); pndInst_c.alloc(nc); Updf_c.alloc(nc * 3); Tau_c.alloc(nc * 6); Tau_b.alloc(nb * 6);
     kpdf_c.alloc(nc); PaNIC.alloc(nc); lostMass.alloc(nc); lostShare.alloc(nc);
     mMom.alloc(nc); VMom.alloc(nc); UMom.alloc(nc * 3); UUMom.alloc(nc * 6); PhiMom.alloc(nc * nPhi); PhiPhiMom.alloc(nc * nC);
+    UPhiMom.alloc(nc * nPhi * 3); UPhi_c.alloc(nc * nPhi * 3);
     momentBlock.alloc(nc * nMom + BLOCK_TAIL); momentBlock.zero(stream);
     phiPC.alloc(nc); UPC_c.alloc(nc * 3); OmegaRaw_c.alloc(nc); etaRaw_c.alloc(nc);
     const size_t nNodes = nc + nPoints + nFaces;
@@ -490,7 +503,7 @@ void Cloud::prepareFields() {
 // called by Cloud::finaliseStep (particles.cu) once the moment block is complete
 void fieldsFinalise(Cloud &c, double *partSum, double *partMax, int grid) {
     FieldPtrs F = fieldPtrs(c);
-    LAUNCH(&c, k_finalise, grid, 256, 0, c.dm, F, c.prm, c.momentBlock.p, c.nMom, c.nCov, partSum, partMax);
+    LAUNCH(&c, k_finalise, grid, 256, 0, c.dm, F, c.prm, c.momentBlock.p, c.nMom, c.nCov, partSum, partMax, 0);
     LAUNCH(&c, k_bnd_apply, gridFor(c.nBnd, 128), 128, 0, c.dm, F, c.prm.nPhi, c.nCov);
 }
 
@@ -504,5 +517,41 @@ void Cloud::downloadCellFields(pdfb200_cell_fields &o) {
     dl(o.mMom, mMom.p, nc); dl(o.VMom, VMom.p, nc); dl(o.UMom, UMom.p, nc * 3); dl(o.UUMom, UUMom.p, nc * 6);
     for (int i = 0; i < prm.nPhi; ++i) { dl(o.Phi[i], Phi_c.p + i * nc, nc); dl(o.PhiMom[i], PhiMom.p + i * nc, nc); }
     for (int i = 0; i < nCov; ++i) { dl(o.Cov[i], Cov_c.p + i * nc, nc); dl(o.PhiPhiMom[i], PhiPhiMom.p + i * nc, nc); }
+    for (int i = 0; i < prm.nPhi; ++i) { dl(o.UPhi[i], UPhi_c.p + i * nc * 3, nc * 3); dl(o.UPhiMom[i], UPhiMom.p + i * nc * 3, nc * 3); }
     CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// the moment fields of a previous run instead of initMoments (mcParticleCloud.C:339-517, checkMoments :739-820)
+__global__ void k_flux_from_means(int n, int nCells, const double *PhiMom, const double *mMom, const double *UMom, double *UPhiMom) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int c = j % nCells;
+    st3(UPhiMom, j, (PhiMom[j] / fmax(mMom[c], PDF_SMALL)) * ld3(UMom, c));
+}
+void Cloud::uploadMoments(const pdfb200_cell_fields &m) {
+    if (!haveFv || !haveCloudFields) throw std::logic_error("upload_moments: upload the FV and cloud fields first");
+    bool complete = m.mMom && m.VMom && m.UMom && m.UUMom;
+    for (int i = 0; i < prm.nPhi; ++i) complete = complete && m.PhiMom[i];
+    for (int i = 0; i < nCov; ++i) complete = complete && m.PhiPhiMom[i];
+    if (!complete) throw std::invalid_argument("upload_moments: Moments are missing (use init_moments)");
+    initMoments();   // allocations, boundary values of the derived fields
+    const size_t nc = nCells;
+    auto ul = [&](double *dst, const double *src, size_t n) { CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, stream)); };
+    ul(mMom.p, m.mMom, nc); ul(VMom.p, m.VMom, nc); ul(UMom.p, m.UMom, nc * 3); ul(UUMom.p, m.UUMom, nc * 6);
+    for (int i = 0; i < prm.nPhi; ++i) ul(PhiMom.p + i * nc, m.PhiMom[i], nc);
+    for (int i = 0; i < nCov; ++i) ul(PhiPhiMom.p + i * nc, m.PhiPhiMom[i], nc);
+    bool haveFlux = prm.nPhi > 0;
+    for (int i = 0; i < prm.nPhi; ++i) haveFlux = haveFlux && m.UPhiMom[i];
+    if (haveFlux) for (int i = 0; i < prm.nPhi; ++i) ul(UPhiMom.p + i * nc * 3, m.UPhiMom[i], nc * 3);
+    else if (prm.nPhi > 0) LAUNCH(this, k_flux_from_means, gridFor((long long)nc * prm.nPhi, 256), 256, 0, (int)(nc * prm.nPhi), nCells, PhiMom.p, mMom.p, UMom.p, UPhiMom.p);
+    FieldPtrs F = fieldPtrs(*this);
+    const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
+    if (cellPartSum.n < (size_t)gF * 8) cellPartSum.alloc((size_t)std::max(gF, numSMs * 16) * 8);
+    LAUNCH(this, k_finalise, gF, 256, 0, dm, F, prm, momentBlock.p, nMom, nCov, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, 1);
+    LAUNCH(this, k_bnd_apply, gridFor(nBnd, 128), 128, 0, dm, F, prm.nPhi, nCov);
+    // the instantaneous fields are diagnostics of the last step: they restart from the averaged ones
+    CUDA_CHECK(cudaMemcpyAsync(rhoInst_c.p, rho_c.p, nc * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(pndInst_c.p, pnd_c.p, nc * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if (m.PaNIC) ul(PaNIC.p, m.PaNIC, nc);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
 }

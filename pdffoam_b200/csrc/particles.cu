@@ -264,15 +264,15 @@ __global__ void k_cs_finish(const int *total, StepScalars *sc) {
 // updateCloudPDF first half (mcParticleCloud.C:929-956): one warp per cell,
 // lanes stride over the cell's segment of the sorted order, butterfly reduction
 // in a fixed order -> deterministic sums without atomics.
-// Block layout per cell: N, M, V, MU(3), MPhi(nPhi), MPhiPhi(nCov), MUU(6).
-#ifndef MOM_MIN_BLOCKS
-#define MOM_MIN_BLOCKS 4
-#endif
+// Block layout per cell: N, M, V, MU(3), MPhi(nPhi), MPhiPhi(nCov), MUU(6), MUPhi(3 nPhi); the last group is the
+// velocity-scalar flux moment (BASELINE north_star "scalar fluxes"; the reference's moments stop at MUU).
+// Compiled for 4 CTAs per SM (64 registers) up to one scalar, where the kernel is latency-bound; the wider
+// instantiations hold 20 + 6 nPhi + nCov accumulators and would spill at that limit.
 template <int NPHI>
-__global__ void __launch_bounds__(256, MOM_MIN_BLOCKS) k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
+__global__ void __launch_bounds__(256, (NPHI <= 1 ? 4 : NPHI <= 3 ? 2 : 1)) k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
                           double *block, int nMom) {
     constexpr int NCOV = NPHI * (NPHI + 1) / 2;
-    constexpr int NACC = 11 + NPHI + NCOV;   // all but the count
+    constexpr int NACC = 11 + NPHI + NCOV + 3 * NPHI;   // all but the count
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
     for (int r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < M.nCells; r += gridDim.x * warpsPerBlock) {
@@ -301,6 +301,11 @@ __global__ void __launch_bounds__(256, MOM_MIN_BLOCKS) k_moments(DMesh M, PState
             double *uu = a + 5 + NPHI + NCOV;
             uu[0] += mpd * (U.x * U.x); uu[1] += mpd * (U.x * U.y); uu[2] += mpd * (U.x * U.z);
             uu[3] += mpd * (U.y * U.y); uu[4] += mpd * (U.y * U.z); uu[5] += mpd * (U.z * U.z);
+#pragma unroll
+            for (int k = 0; k < NPHI; ++k) {
+                const double mp = mpd * ph[k];
+                uu[6 + 3 * k] += mp * U.x; uu[7 + 3 * k] += mp * U.y; uu[8 + 3 * k] += mp * U.z;
+            }
         }
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
@@ -330,9 +335,15 @@ __global__ void __launch_bounds__(256, MOM_MIN_BLOCKS) k_moments(DMesh M, PState
 #define MIX_WARPS 8
 __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
                                                               const int *cellEnd, const StepScalars *sc, RngKey key, uint32_t *hashScratch,
-                                                              uint32_t *rankSlot) {
+                                                              uint32_t *rankSlot, double *balancePartial) {
     __shared__ int slotByRank[MIX_WARPS][128];
+    __shared__ double balSm[K1_MAXCONS * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // what the mixing adds to the step's balance of the conserved scalars, sum of massPerDepth x (phi_new - phi_old):
+    // a pair conserves its eta*m-weighted mean, the balance (mcParticleCloud.C:1432-1444) weighs with m per depth
+    double bal[K1_MAXCONS];
+#pragma unroll
+    for (int k = 0; k < K1_MAXCONS; ++k) bal[k] = 0.0;
     const uint32_t step = sc->step;
     const double deltaT = sc->deltaT;
     for (int c = blockIdx.x * MIX_WARPS + warp; c < M.nCells; c += gridDim.x * MIX_WARPS) {
@@ -366,8 +377,17 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
                 double *col = S.phi[P.mixed[mI]];
                 const double fp = col[p], fq = col[q];
                 const double mean = (wp * fp + wq * fq) / (wp + wq);
-                col[p] = fp + a * (mean - fp);
-                col[q] = fq + a * (mean - fq);
+                const double np_ = fp + a * (mean - fp), nq = fq + a * (mean - fq);
+                col[p] = np_;
+                col[q] = nq;
+                for (int cs = 0; cs < P.nConserved; ++cs)
+                    if (P.conserved[cs] == P.mixed[mI]) {
+                        const double mpdP = massPerDepth(M, mk(S.px[p], S.py[p], S.pz[p]), S.m[p]);
+                        const double mpdQ = massPerDepth(M, mk(S.px[q], S.py[q], S.pz[q]), S.m[q]);
+                        const double d = mpdP * (np_ - fp) + mpdQ * (nq - fq);
+#pragma unroll
+                        for (int k = 0; k < K1_MAXCONS; ++k) if (k == cs) bal[k] += d;
+                    }
             }
         };
         auto hashOf = [&](uint32_t id, int r) {
@@ -424,6 +444,10 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
             }
         }
     }
+    __syncthreads();
+    blockReduce<K1_MAXCONS, false>(bal, balSm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < K1_MAXCONS; ++k) balancePartial[blockIdx.x * K1_MAXCONS + k] = bal[k];
 }
 
 // ---------------------------------------------------------------------------
@@ -960,7 +984,8 @@ struct DevReport {
 #define RP_INJ (RP_NCDELTA + K1_NC1)     // K1_NC1
 #define RP_LOSTSUM (RP_INJ + K1_NC1)     // K1_NC1: lost mass re-spread, per depth, x {1, conserved scalars}
 #define RP_CLONEDELTA (RP_LOSTSUM + K1_NC1)   // K1_NC1: axisymmetric mass-per-depth change of the clones
-#define RP_END (RP_CLONEDELTA + K1_NC1)
+#define RP_MIXDELTA (RP_CLONEDELTA + K1_NC1)   // K1_MAXCONS: change of the conserved-scalar balance by pair mixing
+#define RP_END (RP_MIXDELTA + K1_MAXCONS)
 static_assert(RP_END <= 64, "DevReport too small");
 
 // Lost particles (mcParticleCloud.C:1257-1260,1346-1351, notifyLostParticle :2088-2092): the particle
@@ -1436,8 +1461,12 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         // "modifiedCurl" pair mixing on the sorted order, before the moments are taken
         if (prm.mixingModel == PDFB200_MIXING_MODCURL && prm.nMixed > 0 && total > 0) {
             if (valsA.n < (size_t)capacity) valsA.alloc(capacity);
-            LAUNCH(this, k_mix_curl, std::min(gridFor(nCells, MIX_WARPS), numSMs * 8), MIX_WARPS * 32, 0, dm, prm, S[cur], valsB.p,
-                   cellStart.p, cellEnd.p, scal.p, key, keysA.p, valsA.p);
+            const int gM = std::min(gridFor(nCells, MIX_WARPS), numSMs * 8);
+            LAUNCH(this, k_mix_curl, gM, MIX_WARPS * 32, 0, dm, prm, S[cur], valsB.p,
+                   cellStart.p, cellEnd.p, scal.p, key, keysA.p, valsA.p, cellPartSum.p);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gM, K1_MAXCONS, cellPartSum.p, dRep->v + RP_MIXDELTA, 0);
+        } else {
+            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_MIXDELTA, 0, K1_MAXCONS * sizeof(double), stream));
         }
         switch (prm.nPhi) {
         case 0: launchMoments<0>(*this, S[cur], valsB.p); break;
@@ -1544,6 +1573,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
                 r.massInInst[k] = v[RP_K1SUM + ACC_MASS_IN + k] + v[RP_INJ + k];
                 r.massOutInst[k] = v[RP_K1SUM + ACC_MASS_OUT + k];
             }
+            for (int k = 1; k <= prm.nConserved; ++k) r.deltaMassInst[k] += v[RP_MIXDELTA + k - 1];
             r.nParticles = nParticlesHost;
             r.nInjected = nInjected; r.nDeleted = (int64_t)v[RP_K1SUM + ACC_N_DELETED];
             r.nCloned = hNc[0]; r.nEliminated = hNc[1]; r.nLost = (int64_t)v[RP_K1SUM + ACC_N_LOST];

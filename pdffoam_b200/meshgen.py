@@ -240,9 +240,9 @@ def wedge_mesh(xs: np.ndarray, rs: np.ndarray, half_angle_deg: float = 5.0,
     """Axisymmetric wedge, one cell thick (all four tutorial configs, SURVEY
     Appendix E): x stream-wise, y ~ r, the wedge spans +-z.
 
-    inlet_split: [(name, r_upper), ...] splits the x-min side by radius
-    (e.g. jet / pilot / coflow). Patches: inlet(s), "outflow", "axis",
-    "outerWall", "back", "front".
+    inlet_split: [(name, r_upper[, handler]), ...] splits the x-min side by radius
+    (e.g. jet / pilot / coflow, or jet / bluffBody (slip) / coflow). Patches:
+    inlet(s), "outflow", "axis", "outerWall", "back", "front".
     """
     th = np.deg2rad(half_angle_deg)
 
@@ -255,9 +255,9 @@ def wedge_mesh(xs: np.ndarray, rs: np.ndarray, half_angle_deg: float = 5.0,
 
     if inlet_split is None:
         inlet_split = [("inlet", float("inf"))]
-    bounds = np.array([b for _, b in inlet_split])
+    bounds = np.array([it[1] for it in inlet_split])
     sp = {
-        "xmin": [(n, PATCH_GENERIC, inlet_handler, 1) for n, _ in inlet_split],
+        "xmin": [(it[0], PATCH_GENERIC, it[2] if len(it) > 2 else inlet_handler, 1) for it in inlet_split],
         "xmax": [("outflow", PATCH_GENERIC, outlet_handler, 1)],
         "ymin": [("axis", PATCH_GENERIC, BC_SLIP, 1)], "ymax": [("outerWall", PATCH_GENERIC, BC_SLIP, 1)],
         "zmin": [("back", PATCH_WEDGE, BC_EMPTY, 1)], "zmax": [("front", PATCH_WEDGE, BC_EMPTY, 1)],

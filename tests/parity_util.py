@@ -37,7 +37,7 @@ def compare_particles(pd_: Dict, po: Dict, rtol=1e-10, atol=1e-12, exact_index=T
 def compare_cell_fields(cd: Dict, co: Dict, rtol=1e-10, atol=1e-12, what=""):
     for k in ("rho", "rhoInst", "pnd", "pndInst", "U", "Tau", "k", "PaNIC", "mMom", "VMom", "UMom", "UUMom"):
         np.testing.assert_allclose(cd[k], co[k], rtol=rtol, atol=atol, err_msg=f"{what}: cell field {k}")
-    for name in ("Phi", "Cov", "PhiMom", "PhiPhiMom"):
+    for name in ("Phi", "Cov", "PhiMom", "PhiPhiMom", "UPhi", "UPhiMom"):
         for i, (a, b) in enumerate(zip(cd[name], co[name])):
             np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=f"{what}: cell field {name}[{i}]")
 
