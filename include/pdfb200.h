@@ -69,10 +69,18 @@ enum {
     PDFB200_REACTION_STEADY_FLAMELET = 3, /* "SteadyFlamelet" */
     PDFB200_REACTION_NAIVE_FLAMELET = 4   /* "naiveFlamelet" (mcNaiveFlameletModel.C:64-69): rho = 1 - 3.2 z (1 - z), T = 1e5 / rho */
 };
-enum { PDFB200_POSCORR_NONE = 0, PDFB200_POSCORR_LIMITED_SIMPLE = 1 }; /* "limitedSimple" */
+/* mcPositionCorrection run-time selection (mcPositionCorrection/mcPositionCorrection.C): "limitedSimple" and
+ * "simple" (mcSimplePositionCorrection.C:127-163) are algebraic and run entirely on the device. "external" is the
+ * boundary for the three variants whose updateInternals() solves a PDE with OpenFOAM's linear solvers
+ * ("ellipticRelaxation", "Muradoglu", "integrated"): the OpenFOAM side keeps solving, uploads the resulting cell
+ * fields with pdfb200_upload_poscorr_fields and the device does the per-particle part (their correct(mcParticle&)). */
+enum { PDFB200_POSCORR_NONE = 0, PDFB200_POSCORR_LIMITED_SIMPLE = 1, PDFB200_POSCORR_SIMPLE = 2, PDFB200_POSCORR_EXTERNAL = 3 };
 enum { PDFB200_LTS_NONE = 0, PDFB200_LTS_CELL = 1, PDFB200_LTS_PARTICLE = 2 }; /* "cell","particle" */
 enum { PDFB200_INTERP_CELL = 0, PDFB200_INTERP_CELL_POINT_FACE = 1 };  /* "cell","cellPointFace" */
-enum { PDFB200_INLET_RANDOM_INVERSION = 0 };                           /* "inversion" */
+/* mcInletRandom run-time selection (mcInletRandom.C:66-90): "inversion" (Newton inversion of the CDF,
+ * mcInversionInletRandom.C:63-119) and "sampling" (acceptance-rejection, mcSamplingInletRandom.C:37-102: normal
+ * deviates U+u'N accepted with probability proportional to their value). Both draw from x exp(-(x-U)^2 b^2)/Q. */
+enum { PDFB200_INLET_RANDOM_INVERSION = 0, PDFB200_INLET_RANDOM_SAMPLING = 1 };
 
 /* ---- mesh: the polyMesh the cloud borrows (mcParticleCloud.C:301-310) ---- */
 typedef struct pdfb200_mesh {
@@ -129,7 +137,7 @@ typedef struct pdfb200_params {
     int32_t  rngMode;        /* oracle only: 0 = keyed Philox (same streams as the device),
                                 1 = one sequential stream consumed in list order like
                                 OpenFOAM's Random (the reference's behaviour)           */
-    int32_t  reserved;
+    int32_t  inletRandom;    /* PDFB200_INLET_RANDOM_* ("randomGenerator { type ...; }" of an inletOutlet handler) */
 } pdfb200_params;
 
 /* ---- FV-owned fields the cloud borrows (mcParticleCloud.C:319-331, .H:206):
@@ -204,6 +212,24 @@ typedef struct pdfb200_cell_fields {
     double *UPhiMom[PDFB200_MAX_PHI];   /* time-averaged sum of eta m U phi, [nCells*3] per scalar */
 } pdfb200_cell_fields;
 
+/* ---- fields of an externally solved position correction (PDFB200_POSCORR_EXTERNAL). Per particle
+ *        Ucorrection -= interp(G0) + scale * interp(l) * (interp(zeta) != 0 ? interp(G1) : interp(G2))
+ *      with the interpolation scheme interpUPosCorr, which is
+ *        mcMuradogluPositionCorrection::correct (.C:158-169): G0 = grad(phi), G1 = grad(Q), G2 = grad(QInst),
+ *            l = L, zeta, scale = a*U0;
+ *        mcEllipticRelaxationPositionCorrection::correct (.C:238-248): the same without G0 (NULL);
+ *        mcIntegratedPositionCorrection::correct (.C:132-138, Ucorrection += UPosCorr): G0 = -UPosCorr, scale = 0.
+ *      Cell values [nCells*3] / [nCells] and boundary-face values [nBnd*3] / [nBnd] after
+ *      correctBoundaryConditions(); a NULL pair counts as zero.                                         ---- */
+typedef struct pdfb200_poscorr_fields {
+    const double *G0, *G0b;
+    const double *G1, *G1b;
+    const double *G2, *G2b;
+    const double *l, *lb;
+    const double *zeta, *zetab;
+    double scale;
+} pdfb200_poscorr_fields;
+
 typedef struct pdfb200_cloud pdfb200_cloud;   /* opaque handle */
 
 /* (the types above are also read by the kernel source when the library specialises it at run time with
@@ -238,6 +264,8 @@ int pdfb200_set_flamelet_tables(pdfb200_cloud *cloud, int32_t nChi, int32_t nZ,
 int pdfb200_upload_fv_fields(pdfb200_cloud *cloud, const pdfb200_fv_fields *f);
 /* Upload rho / scalar / covariance fields and their boundary conditions. */
 int pdfb200_upload_cloud_fields(pdfb200_cloud *cloud, const pdfb200_cloud_fields *f);
+/* Upload the fields of an externally solved position correction (see pdfb200_poscorr_fields); once per solve. */
+int pdfb200_upload_poscorr_fields(pdfb200_cloud *cloud, const pdfb200_poscorr_fields *f);
 /* mcParticleCloud::initMoments (mcParticleCloud.C:1633-1701). */
 int pdfb200_init_moments(pdfb200_cloud *cloud);
 

@@ -46,6 +46,7 @@ class OracleLibrary(Library):
         f("binterp").restype = C.c_double
         f("inlet_random").argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, c_double_p]
         f("inlet_random_sample").argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_int64, c_double_p]
+        f("inlet_sampling").argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, c_double_p, c_double_p]
         f("rng_probe").argtypes = [C.c_uint64, C.c_int64, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, c_double_p]
         f("philox").argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         f("rotation_tensor").argtypes = [c_double_p, c_double_p, c_double_p]
@@ -97,6 +98,7 @@ class RefLibrary:
         L.pdfref_binterp.restype = C.c_double
         L.pdfref_inlet_random.argtypes = [C.c_double, C.c_double, C.c_double, c_double_p, C.c_int64, c_double_p, c_double_p, C.POINTER(C.c_int32)]
         L.pdfref_inlet_random_select.argtypes = [C.c_char_p]
+        L.pdfref_inlet_sampling.argtypes = [C.c_double, C.c_double, C.c_int32, C.c_int64, c_double_p]
         L.pdfref_decomp_create.argtypes = [C.c_int32, c_double_p, C.c_int32, c_int32_p, c_int32_p, c_int32_p, C.c_int32, c_int32_p, C.c_int32,
                                            c_double_p, c_double_p]
         L.pdfref_decomp_create.restype = vp

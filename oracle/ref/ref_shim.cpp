@@ -5,7 +5,8 @@
 //   pdfref_find_coeffs / pdfref_binterp  -> mcSteadyFlamelet.C:36-95 (anonymous-namespace templates; the Makefile
 //                                           cuts that block out of the file into _ref/gen/steadyFlameletHelpers.inc)
 //   pdfref_inlet_*                       -> mcInletRandom.C:92-108, mcInletRandomI.H:28-39,
-//                                           mcInversionInletRandom.C:63-119 through mcInletRandom::New("inversion")
+//                                           mcInversionInletRandom.C:63-119 through mcInletRandom::New("inversion"),
+//                                           mcSamplingInletRandom.C through New("sampling")
 //   pdfref_decomp_*                      -> tetFacePointCellDecomposition{.H,I.H,.C}<richTetPointRef>,
 //                                           richTetrahedron{.H,I.H,.C}
 #include "foamStub.H"
@@ -18,6 +19,7 @@ const Foam::Vector Foam::Vector::zero(0, 0, 0);
 #include "tetFacePointCellDecomposition.H"
 #include "mcInletRandom.C"
 #include "mcInversionInletRandom.C"
+#include "mcSamplingInletRandom.C"
 #include "steadyFlameletHelpers.inc"
 
 #include <cstdint>
@@ -79,6 +81,18 @@ int pdfref_inlet_random(double UMean, double uRms, double x, double* out3, int64
         rnd.queue(u, (size_t)n);
         for (int64_t k = 0; k < n; ++k) values[k] = r().value();
         if (warnings) *warnings = messageStream::warnings() - w0;
+    });
+}
+// n values of the "sampling" generator (mcSamplingInletRandom.C:37-102) on a free-running Random
+int pdfref_inlet_sampling(double UMean, double uRms, int32_t seed, int64_t n, double* values)
+{
+    return guarded([&] {
+        Random rnd(seed);
+        rnd.freeRunning();
+        dictionary d;
+        d.add("type", "sampling");
+        autoPtr<mcInletRandom> r = mcInletRandom::New(rnd, UMean, uRms, d);
+        for (int64_t k = 0; k < n; ++k) values[k] = r().value();
     });
 }
 // unknown generator types fail like the reference (mcInletRandom.C:76-88)

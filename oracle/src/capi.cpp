@@ -98,6 +98,32 @@ int pdforacle_upload_cloud_fields(pdforacle_cloud *h, const pdfb200_cloud_fields
     ORACLE_CATCH
 }
 
+int pdforacle_upload_poscorr_fields(pdforacle_cloud *h, const pdfb200_poscorr_fields *f) {
+    ORACLE_TRY
+    Cloud &c = h->c;
+    const int nc = c.mesh.nCells, nb = c.nBnd();
+    auto vec = [&](VectorField &F, const double *cv, const double *bv) {
+        F.fixed.assign(nb, 1);   // boundary values are taken as uploaded
+        F.resize(nc, nb);
+        if (!cv) return;
+        if (!bv) throw std::invalid_argument("upload_poscorr_fields: cell values without boundary values");
+        for (int i = 0; i < nc; ++i) F.c[i] = Vec3(cv[3 * i], cv[3 * i + 1], cv[3 * i + 2]);
+        for (int i = 0; i < nb; ++i) F.b[i] = Vec3(bv[3 * i], bv[3 * i + 1], bv[3 * i + 2]);
+    };
+    auto sca = [&](ScalarField &F, const double *cv, const double *bv) {
+        F.fixed.assign(nb, 1);
+        F.resize(nc, nb);
+        if (!cv) return;
+        if (!bv) throw std::invalid_argument("upload_poscorr_fields: cell values without boundary values");
+        F.c.assign(cv, cv + nc); F.b.assign(bv, bv + nb);
+    };
+    vec(c.pcG0, f->G0, f->G0b); vec(c.pcG1, f->G1, f->G1b); vec(c.pcG2, f->G2, f->G2b);
+    sca(c.pcL, f->l, f->lb); sca(c.pcZeta, f->zeta, f->zetab);
+    c.pcScale = f->scale;
+    c.havePcExt = true;
+    ORACLE_CATCH
+}
+
 int pdforacle_init_moments(pdforacle_cloud *h) {
     if (!h->c.haveFv || !h->c.haveCloudFields) { g_err = "init_moments: upload fields first"; return PDFB200_ERR_STATE; }
     h->c.initMoments();
@@ -328,6 +354,17 @@ double pdforacle_binterp(const double *v, int32_t nRows, int32_t nCols, int32_t 
 int pdforacle_inlet_random(double UMean, double uRms, double x, double u, double *out) {
     InletRandom r; r.updateCoeffs(UMean, uRms);
     out[0] = r.Q; out[1] = r.m; out[2] = r.PDF(x); out[3] = r.CDF(x); out[4] = r.value(u);
+    return PDFB200_OK;
+}
+// "sampling" generator probes: keyed (face bf, draws 0..n-1 of step `step`) and sequential
+int pdforacle_inlet_sampling(double UMean, double uRms, uint64_t seed, uint32_t bf, uint32_t step, int64_t n, double *keyed, double *sequential) {
+    InletRandom r; r.updateCoeffs(UMean, uRms);
+    KeyedRng k; k.setSeed(seed);
+    SeqRandom s; s.seed(seed);
+    for (int64_t i = 0; i < n; ++i) {
+        if (keyed) keyed[i] = r.sample(k, bf, step, (uint32_t)i);
+        if (sequential) sequential[i] = r.sample(s);
+    }
     return PDFB200_OK;
 }
 int pdforacle_inlet_random_sample(double UMean, double uRms, uint64_t seed, int64_t n, double *out) {

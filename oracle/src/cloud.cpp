@@ -304,6 +304,21 @@ bool Cloud::move(Particle &p, double tdTrackTime) {
 // ---------------------------------------------------------------------------
 void Cloud::positionCorrectionCorrect(Particle &p) const {
     if (prm.positionCorrection == PDFB200_POSCORR_NONE) return;
+    if (prm.positionCorrection == PDFB200_POSCORR_SIMPLE) {
+        // mcSimplePositionCorrection::correct (.C:156-163): Ucorrection -= cmptMultiply(Ainv[cell], interp(gradPhi)) with
+        // Ainv = (1./dy*dz, 1./dx*dz, 1./dx*dy) of the cell's bounding box (.C:127) - operator precedence as written
+        const Vec3 d = mesh.bbMax[p.cell] - mesh.bbMin[p.cell];
+        const Vec3 Ainv(1. / d.y * d.z, 1. / d.x * d.z, 1. / d.x * d.y);
+        const Vec3 g = interp(UPosCorrN, p);
+        p.Ucorrection -= Vec3(Ainv.x * g.x, Ainv.y * g.y, Ainv.z * g.z);
+        return;
+    }
+    if (prm.positionCorrection == PDFB200_POSCORR_EXTERNAL) {
+        // mcMuradogluPositionCorrection::correct (.C:158-169) / mcEllipticRelaxation... (.C:238-248) / mcIntegrated... (.C:132-138)
+        const double z = interp(pcZetaN, p), l = interp(pcLN, p);
+        p.Ucorrection -= interp(UPosCorrN, p) + (pcScale * l) * (z != 0 ? interp(pcG1N, p) : interp(pcG2N, p));
+        return;
+    }
     p.Ucorrection += interp(UPosCorrN, p);
 }
 
@@ -524,7 +539,9 @@ void Cloud::injectPatch(int patchI) {
             ++kDraw;
             // randomVelocity (.C:215-229)
             const Vec3 &U = inletU[bf]; const SymmTensor &R = inletR[bf];
-            const Vec3 UpLocal(inrnd.value(uVal), U.y + std::sqrt(R.yy) * n1, U.z + std::sqrt(R.zz) * n2);
+            const double uIn = prm.inletRandom != PDFB200_INLET_RANDOM_SAMPLING ? inrnd.value(uVal)
+                             : (prm.rngMode == 1 ? inrnd.sample(srng) : inrnd.sample(krng, (uint32_t)bf, step, kDraw - 1));
+            const Vec3 UpLocal(uIn, U.y + std::sqrt(R.yy) * n1, U.z + std::sqrt(R.zz) * n2);
             const Vec3 Up = transform(revTrans[bf], UpLocal);
             // randomPoint (.C:179-212)
             const std::vector<double> &w = probVec[bf];

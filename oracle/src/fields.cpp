@@ -328,7 +328,28 @@ void Cloud::updateModelInternals() {
             UPC.fixed = rhocPdf.fixed;
             applyBC(UPC);
         }
-        makeNodes(UPC, UPosCorrN, prm.interpUPosCorr);
+        if (prm.positionCorrection == PDFB200_POSCORR_SIMPLE) {
+            // mcSimplePositionCorrection::updateInternals (.C:135-163): phi = pnd/rho - 1 (zeroGradient),
+            // gradPhi = C |Ufv| grad(phi). Boundary values of gradPhi: zeroGradient (its declared patch type, .C:92-109;
+            // OpenFOAM's assignment copies fvc::grad's patch values instead, which differ by the normal component -
+            // an OpenFOAM primitive that is defined here).
+            ScalarField phi; phi.resize(nc, nb);
+            for (int c = 0; c < nc; ++c) phi.c[c] = pndcPdf.c[c] / rhocPdf.c[c] - 1.;
+            applyBC(phi);
+            std::vector<Vec3> g;
+            gaussGrad(phi, g);
+            for (int c = 0; c < nc; ++c) UPC.c[c] = (prm.pcC * mag(Ufv.c[c])) * g[c];
+            UPC.fixed.assign(nb, 0);
+            applyBC(UPC);
+        }
+        if (prm.positionCorrection == PDFB200_POSCORR_EXTERNAL) {
+            if (!havePcExt) throw std::logic_error("evolve: positionCorrection external selected but no fields uploaded (upload_poscorr_fields)");
+            makeNodes(pcG0, UPosCorrN, prm.interpUPosCorr);
+            makeNodes(pcG1, pcG1N, prm.interpUPosCorr); makeNodes(pcG2, pcG2N, prm.interpUPosCorr);
+            makeNodes(pcL, pcLN, prm.interpUPosCorr); makeNodes(pcZeta, pcZetaN, prm.interpUPosCorr);
+        } else {
+            makeNodes(UPC, UPosCorrN, prm.interpUPosCorr);
+        }
     }
 
     // --- mcRASOmegaModel::updateInternals (.C:90-122) ---
@@ -471,6 +492,30 @@ double InletRandom::value(double U01) const {
     const double d = (diff >= 0 ? 1.0 : -1.0) * SMALL;   // Foam::sign: +1 for >= 0
     int nIter;
     return newton(m + d, U01, nIter);
+}
+
+double InletRandom::sample(const KeyedRng &k, uint32_t bf, uint32_t step, uint32_t kDraw) const {
+    const double xMax = std::max(UMean + 6.7 * uRms, SMALL);
+    const uint64_t entity = (uint64_t)bf | ((uint64_t)kDraw << 32);
+    for (uint32_t attempt = 0; attempt < (1u << 20); ++attempt) {
+        uint32_t o[4];
+        k.words(entity, step, RNG_INJECT_SAMPLE, attempt, o);
+        float n0, n1;
+        normalPairF32(o[0], o[1], n0, n1);
+        const double u = (double)((((unsigned long long)o[3] << 32) | o[2]) >> 11) * 0x1.0p-53;
+        const double x = UMean + uRms * (double)n0;
+        if (u * xMax < x) return x;
+    }
+    return m;
+}
+
+double InletRandom::sample(SeqRandom &s) const {
+    // mcSamplingInletRandom.C:37-102 with the bound of the scale known in advance instead of taken from a batch
+    const double xMax = std::max(UMean + 8.0 * uRms, SMALL);
+    for (;;) {
+        const double x = UMean + uRms * s.GaussNormal();
+        if (s.scalar01() * xMax < x) return x;
+    }
 }
 
 }  // namespace pdforacle

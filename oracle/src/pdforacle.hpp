@@ -195,7 +195,8 @@ enum RngPurpose : uint32_t {
     RNG_SEED = 6,           // entity = initial particle index
     RNG_INJECT = 7,         // entity = boundary face; sub = 4*k + {0..3}
     RNG_MIX_HASH = 8,       // entity = particle id; sub = round (modifiedCurl: matching order)
-    RNG_MIX_PAIR = 9        // entity = id of the pair's first particle; sub = round (mix?, a)
+    RNG_MIX_PAIR = 9,       // entity = id of the pair's first particle; sub = round (mix?, a)
+    RNG_INJECT_SAMPLE = 10  // entity = boundary face | draw << 32; sub = attempt ("sampling" inflow generator)
 };
 
 struct KeyedRng {
@@ -305,6 +306,9 @@ struct Cloud {
     // model internals (updateInternals products)
     NodeField<double> OmegaN, kN, pStarN, etaN, zVarN;
     NodeField<Vec3> UN, diffUN, UPosCorrN;
+    // externally solved position correction (PDFB200_POSCORR_EXTERNAL): uploaded fields and their node values
+    VectorField pcG0, pcG1, pcG2; ScalarField pcL, pcZeta; double pcScale = 0; bool havePcExt = false;
+    NodeField<Vec3> pcG1N, pcG2N; NodeField<double> pcLN, pcZetaN;
     std::vector<double> diffk;
 
     // inlet caches (mcInletOutletBoundary::getU/getR cache on first use)
@@ -402,6 +406,10 @@ struct InletRandom {
     double CDF(double x) const;
     double newton(double x0, double y, int &nIter) const;
     double value(double U01) const;
+    // "sampling" (mcSamplingInletRandom.C:37-102) on the keyed generator; see InletRnd::sample in pdffoam_b200/csrc/particles.cu
+    double sample(const KeyedRng &k, uint32_t bf, uint32_t step, uint32_t kDraw) const;
+    // the same on a sequential stream (rngMode 1)
+    double sample(SeqRandom &s) const;
 };
 
 }  // namespace pdforacle

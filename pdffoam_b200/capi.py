@@ -60,7 +60,7 @@ class Params(C.Structure):
         ("positionCorrection", C.c_int32), ("pcC", C.c_double), ("pcCFL", C.c_double),
         ("localTimeStepping", C.c_int32), ("ltsUpperBound", C.c_double),
         ("k0", C.c_double), ("deltaT0", C.c_double),
-        ("seed", C.c_uint64), ("rngMode", C.c_int32), ("reserved", C.c_int32),
+        ("seed", C.c_uint64), ("rngMode", C.c_int32), ("inletRandom", C.c_int32),
     ]
 
 
@@ -72,6 +72,11 @@ class FvFields(C.Structure):
         ("epsilon", c_double_p), ("epsilonb", c_double_p),
         ("R", c_double_p), ("Rb", c_double_p),
     ]
+
+
+class PoscorrFields(C.Structure):
+    _fields_ = [("G0", c_double_p), ("G0b", c_double_p), ("G1", c_double_p), ("G1b", c_double_p), ("G2", c_double_p), ("G2b", c_double_p),
+                ("l", c_double_p), ("lb", c_double_p), ("zeta", c_double_p), ("zetab", c_double_p), ("scale", C.c_double)]
 
 
 class CloudFields(C.Structure):
@@ -178,7 +183,7 @@ class PdfError(RuntimeError):
 # every symbol include/pdfb200.h declares (tests check the .so exports them all)
 API_SYMBOLS = [
     "last_error", "create", "destroy", "set_params", "set_flamelet_tables", "upload_fv_fields",
-    "upload_cloud_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
+    "upload_cloud_fields", "upload_poscorr_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
     "kernel_launches", "last_evolve_ms", "profile", "jit_source", "jit_compile", "rng_probe",
@@ -220,6 +225,7 @@ class Library:
         f("evolve").argtypes = [vp, C.c_int32, C.POINTER(StepReport)]
         f("download_cell_fields").argtypes = [vp, C.POINTER(CellFieldsStruct)]
         f("upload_moments").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("upload_poscorr_fields").argtypes = [vp, C.POINTER(PoscorrFields)]
         f("step_counter").argtypes = [vp]; f("step_counter").restype = C.c_int64
         f("set_step_counter").argtypes = [vp, C.c_int64]
         f("id_counter").argtypes = [vp]; f("id_counter").restype = C.c_int64
@@ -379,6 +385,18 @@ class CloudHandle:
             if cov is not None and cov[i] is not None:
                 s.Cov[i], s.Covb[i], s.CovbFixed[i] = d(cov[i]), d(cf["Covb"][i]), u(cf["CovbFixed"][i])
         self.lib.check(self.lib.fn("upload_cloud_fields")(self.h, C.byref(s)), "upload_cloud_fields")
+
+    def upload_poscorr_fields(self, f: Dict):
+        """Fields of an externally solved position correction (pdfb200_poscorr_fields): keys G0, G1, G2 ([nCells,3]),
+        l, zeta ([nCells]) with their boundary values under the key + "b", and "scale"; missing pairs count as zero."""
+        s = PoscorrFields()
+        keep = []
+        for k in ("G0", "G1", "G2", "l", "zeta"):
+            if f.get(k) is not None:
+                for kk in (k, k + "b"):
+                    a = np.ascontiguousarray(f[kk], np.float64); keep.append(a); setattr(s, kk, _dp(a))
+        s.scale = float(f.get("scale", 0.0))
+        self.lib.check(self.lib.fn("upload_poscorr_fields")(self.h, C.byref(s)), "upload_poscorr_fields")
 
     def init_moments(self):
         self.lib.check(self.lib.fn("init_moments")(self.h), "init_moments")

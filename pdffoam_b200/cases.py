@@ -22,7 +22,8 @@ VELOCITY_MODELS = {"none": 0, "SLMFull": 1}                 # mcSLMFullVelocityM
 MIXING_MODELS = {"none": 0, "IEM": 1, "modifiedCurl": 2}     # mcIEMMixingModel.C:37-43; modifiedCurl is new
 OMEGA_MODELS = {"none": 0, "RAS": 1}                        # mcRASOmegaModel.C:63-69
 REACTION_MODELS = {"none": 0, "cold": 1, "BurkeSchumann": 2, "SteadyFlamelet": 3, "naiveFlamelet": 4}
-POSITION_CORRECTIONS = {"none": 0, "limitedSimple": 1}
+POSITION_CORRECTIONS = {"none": 0, "limitedSimple": 1, "simple": 2, "external": 3}   # external: ellipticRelaxation / Muradoglu / integrated solved on the OpenFOAM side
+INLET_RANDOM = {"inversion": 0, "sampling": 1}             # mcInletRandom.C:66-90
 LOCAL_TIME_STEPPING = {"none": 0, "off": 0, "false": 0, "cell": 1, "particle": 2}   # mcLocalTimeStepping.C:56-97
 INTERPOLATION_SCHEMES = {"cell": 0, "cellPointFace": 1}
 
@@ -60,7 +61,7 @@ def default_params(n_phi: int = 1, **kw) -> Params:
     p.seed = 0x5EED
     p.rngMode = 0
     selectors = {"velocityModel": VELOCITY_MODELS, "mixingModel": MIXING_MODELS, "omegaModel": OMEGA_MODELS,
-                 "reactionModel": REACTION_MODELS, "positionCorrection": POSITION_CORRECTIONS,
+                 "reactionModel": REACTION_MODELS, "positionCorrection": POSITION_CORRECTIONS, "inletRandom": INLET_RANDOM,
                  "localTimeStepping": LOCAL_TIME_STEPPING}
     for k, v in kw.items():
         if k in ("mixed", "conserved", "addedIdx"):
@@ -258,7 +259,7 @@ def with_scalars(case: Case, names: Sequence[str], reaction: str, tables: Option
     cov[0] = 0.05 * z * (1 - z)                      # zzCov: some variance so that chi = Cchi*Omega*zVar varies
     case.cf.update(Cov=cov, Covb=[c[_bnd_owner(case.mesh)].copy() for c in cov], CovbFixed=[np.zeros(nb, np.uint8)] * n_cov)
     p = case.params
-    base = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] not in ("mixed", "conserved", "addedIdx", "reserved", "nPhi", "nMixed", "nConserved", "nAdded")}
+    base = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] not in ("mixed", "conserved", "addedIdx", "nPhi", "nMixed", "nConserved", "nAdded")}
     base.update(reactionModel=reaction, zIdx=0)
     if reaction == "SteadyFlamelet":
         base.update(chiIdx=names.index("chi"), addedIdx=[names.index("T")], Cchi=2.0)

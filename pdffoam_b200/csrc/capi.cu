@@ -52,7 +52,8 @@ static void validateParams(const pdfb200_params &p) {
     if (p.mixingModel < 0 || p.mixingModel > PDFB200_MIXING_MODCURL) throw std::invalid_argument("Unknown mcMixingModel type");
     if (p.omegaModel < 0 || p.omegaModel > PDFB200_OMEGA_RAS) throw std::invalid_argument("Unknown mcOmegaModel type");
     if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_NAIVE_FLAMELET) throw std::invalid_argument("Unknown mcReactionModel type");
-    if (p.positionCorrection < 0 || p.positionCorrection > PDFB200_POSCORR_LIMITED_SIMPLE) throw std::invalid_argument("Unknown mcPositionCorrection type");
+    if (p.positionCorrection < 0 || p.positionCorrection > PDFB200_POSCORR_EXTERNAL) throw std::invalid_argument("Unknown mcPositionCorrection type");
+    if (p.inletRandom < 0 || p.inletRandom > PDFB200_INLET_RANDOM_SAMPLING) throw std::invalid_argument("Unknown mcInletRandom type");
     if (p.localTimeStepping < 0 || p.localTimeStepping > PDFB200_LTS_PARTICLE) throw std::invalid_argument("Unknown mcLocalTimeStepping type");
     if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET ||
         p.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET)
@@ -162,6 +163,11 @@ int pdfb200_set_flamelet_tables(pdfb200_cloud *c, int32_t nChi, int32_t nZ, cons
 
 int pdfb200_upload_fv_fields(pdfb200_cloud *c, const pdfb200_fv_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->uploadFv(*f); }); }
 int pdfb200_upload_cloud_fields(pdfb200_cloud *c, const pdfb200_cloud_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->uploadCloudFields(*f); }); }
+int pdfb200_upload_poscorr_fields(pdfb200_cloud *c, const pdfb200_poscorr_fields *f) {
+    if (!f) { g_err = "upload_poscorr_fields: null argument"; return PDFB200_ERR_INVALID; }
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->uploadPoscorr(*f); });
+}
 int pdfb200_init_moments(pdfb200_cloud *c) { USE_DEVICE(c); return guarded([&] { H(c)->initMoments(); }); }
 int pdfb200_seed_particles(pdfb200_cloud *c) { USE_DEVICE(c); return guarded([&] { H(c)->seedParticles(); }); }
 int pdfb200_upload_particles(pdfb200_cloud *c, int64_t n, const pdfb200_particles *p) { USE_DEVICE(c); return guarded([&] { H(c)->uploadParticles(n, *p); }); }

@@ -94,6 +94,11 @@ struct Cloud {
     // step work arrays
     DBuf<double> phiPC, UPC_c, OmegaRaw_c, etaRaw_c;
     DBuf<double> nodeMid, nodePC, cellAux;
+    // externally solved position correction: rows of 12 = (G0, l, G1, zeta, G2, 0) per cell / boundary face
+    DBuf<double> pcExt_c, pcExt_b;
+    double pcScale = 0;
+    bool havePcExt = false;
+    int pcPlanes = 1;                 // 32-byte planes per node of nodePC (3 with external fields)
     DBuf<double> Un, inletU, inletR, fwdTrans, probVec;
     bool inletCached = false;
     // flamelet tables
@@ -141,6 +146,7 @@ struct Cloud {
     void setTables(int nChi, int nZ, const double *chi, const double *z, int nFields, const double *const *fields);
     void uploadFv(const pdfb200_fv_fields &f);
     void uploadCloudFields(const pdfb200_cloud_fields &f);
+    void uploadPoscorr(const pdfb200_poscorr_fields &f);
     void initMoments();
     void uploadMoments(const pdfb200_cell_fields &m);
     void allocParticles();

@@ -35,6 +35,7 @@
 #define RNG_INJECT 7u
 #define RNG_MIX_HASH 8u   // entity = particle id; sub = round (modifiedCurl matching order)
 #define RNG_MIX_PAIR 9u   // entity = id of the pair's first particle; sub = round
+#define RNG_INJECT_SAMPLE 10u   // entity = boundary face | draw << 32; sub = attempt ("sampling" inflow generator)
 
 // The tet table is three planes of 32-byte chunks indexed by the tet label (DMesh::tetA/B/C):
 //   A[t] = { nbr[4], face, nbrCell, g0 }   B[t] = { g1..g4 }   C[t] = { g5..g8 }

@@ -59,6 +59,7 @@ struct K1Args {
     const StepScalars *sc;
     const double *nodeMid, *nodePC, *cellAux;
     int auxStride;
+    double pcScale;        // external position correction: a*U0 (pdfb200_poscorr_fields::scale)
     const double *Un;
     const double *lostShare;
     LostRec *lostList;     // particles lost in this step (k_lost_reduce)
@@ -456,20 +457,56 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
             V3 Ucorr = mk(0, 0, 0);
             if (P.positionCorrection != PDFB200_POSCORR_NONE) {
-                if (P.interpUPosCorr == PDFB200_INTERP_CELL) {
+                // the interpolated vector: limitedSimple UPosCorr (Ucorrection += it, .C:187-192), simple grad(phi), external G0
+                V3 g0 = mk(0, 0, 0);
+                double fb = 0, fc = 0, fa = 0, fd = 0;
+                const bool blend = P.interpUPosCorr != PDFB200_INTERP_CELL;
+                if (!blend) {
                     const D4 q = ld256(A.nodePC + (size_t)cell0 * 4);
-                    Ucorr = mk(q.x, q.y, q.z);
+                    g0 = mk(q.x, q.y, q.z);
                 } else {
                     double a0, a1, a2, a3;
                     baryAt(T, pos - ctr, a0, a1, a2, a3);
-                    const double fb = clamp01(a1), fc = clamp01(a2), fa = clamp01(a0), fd = clamp01(a3);
+                    fb = clamp01(a1); fc = clamp01(a2); fa = clamp01(a0); fd = clamp01(a3);
                     loadPts(M, tet, T);
                     // 32-byte node records: one 256-bit load per node
                     const D4 vb = ld256(A.nodePC + (nodeP + T.ptB) * 4), vc = ld256(A.nodePC + (nodeP + T.ptC) * 4);
                     const D4 va = ld256(A.nodePC + (nodeF + T.face) * 4), vd = ld256(A.nodePC + (size_t)cell0 * 4);
-                    Ucorr.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
-                    Ucorr.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
-                    Ucorr.z = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
+                    g0.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
+                    g0.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
+                    g0.z = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
+                }
+                if (P.positionCorrection == PDFB200_POSCORR_LIMITED_SIMPLE) {
+                    Ucorr = g0;
+                } else if (P.positionCorrection == PDFB200_POSCORR_SIMPLE) {
+                    // mcSimplePositionCorrection::correct (.C:156-163): Ucorrection -= cmptMultiply(Ainv[cell], interp(gradPhi)),
+                    // Ainv = (1./dy*dz, 1./dx*dz, 1./dx*dy) of the cell's bounding box (.C:127, precedence as written)
+                    const V3 d = ld3(M.bbMax, cell0) - ld3(M.bbMin, cell0);
+                    Ucorr = mk(0, 0, 0) - mk((1. / d.y * d.z) * g0.x, (1. / d.x * d.z) * g0.y, (1. / d.x * d.y) * g0.z);
+                } else {
+                    // external (pdfb200_poscorr_fields): Ucorrection -= G0 + scale l (zeta != 0 ? G1 : G2); planes 1 and 2 of
+                    // the node records hold (G1, zeta) and (G2, 0), plane 0 (G0, l)
+                    const size_t nNodes = (size_t)M.nCells + M.nPoints + M.nFaces;
+                    const double *p1 = A.nodePC + nNodes * 4, *p2 = A.nodePC + 2 * nNodes * 4;
+                    V3 g1, g2; double l, zeta;
+                    if (!blend) {
+                        const D4 q0 = ld256(A.nodePC + (size_t)cell0 * 4), q1 = ld256(p1 + (size_t)cell0 * 4), q2 = ld256(p2 + (size_t)cell0 * 4);
+                        l = q0.w; g1 = mk(q1.x, q1.y, q1.z); zeta = q1.w; g2 = mk(q2.x, q2.y, q2.z);
+                    } else {
+                        const size_t ib = nodeP + T.ptB, ic = nodeP + T.ptC, ia = nodeF + T.face, id = (size_t)cell0;
+                        const D4 lb = ld256(A.nodePC + ib * 4), lc = ld256(A.nodePC + ic * 4), la = ld256(A.nodePC + ia * 4), ld = ld256(A.nodePC + id * 4);
+                        l = fma(fd, ld.w, fma(fa, la.w, fma(fc, lc.w, fb * lb.w)));
+                        const D4 vb = ld256(p1 + ib * 4), vc = ld256(p1 + ic * 4), va = ld256(p1 + ia * 4), vd = ld256(p1 + id * 4);
+                        g1.x = fma(fd, vd.x, fma(fa, va.x, fma(fc, vc.x, fb * vb.x)));
+                        g1.y = fma(fd, vd.y, fma(fa, va.y, fma(fc, vc.y, fb * vb.y)));
+                        g1.z = fma(fd, vd.z, fma(fa, va.z, fma(fc, vc.z, fb * vb.z)));
+                        zeta = fma(fd, vd.w, fma(fa, va.w, fma(fc, vc.w, fb * vb.w)));
+                        const D4 wb = ld256(p2 + ib * 4), wc = ld256(p2 + ic * 4), wa = ld256(p2 + ia * 4), wd = ld256(p2 + id * 4);
+                        g2.x = fma(fd, wd.x, fma(fa, wa.x, fma(fc, wc.x, fb * wb.x)));
+                        g2.y = fma(fd, wd.y, fma(fa, wa.y, fma(fc, wc.y, fb * wb.y)));
+                        g2.z = fma(fd, wd.z, fma(fa, wa.z, fma(fc, wc.z, fb * wb.z)));
+                    }
+                    Ucorr = mk(0, 0, 0) - (g0 + (A.pcScale * l) * (zeta != 0 ? g1 : g2));
                 }
             }
             // ---- E4 ----

@@ -25,6 +25,8 @@ struct FieldPtrs {
     // work
     double *phiPC, *UPC_c, *OmegaRaw_c, *etaRaw_c;
     double *nodeMid, *nodePC, *cellAux;
+    const double *pcExt_c, *pcExt_b;   // external position-correction rows (12 per cell / boundary face)
+    int pcPlanes;                       // planes of nodePC: plane q of node n at nodePC[(q * nNodes + n) * 4]
 };
 
 static FieldPtrs fieldPtrs(Cloud &c) {
@@ -39,6 +41,7 @@ static FieldPtrs fieldPtrs(Cloud &c) {
     f.mMom = c.mMom.p; f.VMom = c.VMom.p; f.UMom = c.UMom.p; f.UUMom = c.UUMom.p; f.PhiMom = c.PhiMom.p; f.PhiPhiMom = c.PhiPhiMom.p; f.UPhiMom = c.UPhiMom.p; f.UPhi_c = c.UPhi_c.p;
     f.phiPC = c.phiPC.p; f.UPC_c = c.UPC_c.p; f.OmegaRaw_c = c.OmegaRaw_c.p; f.etaRaw_c = c.etaRaw_c.p;
     f.nodeMid = c.nodeMid.p; f.nodePC = c.nodePC.p; f.cellAux = c.cellAux.p;
+    f.pcExt_c = c.pcExt_c.p; f.pcExt_b = c.pcExt_b.p; f.pcPlanes = c.pcPlanes;
     return f;
 }
 
@@ -58,6 +61,8 @@ __global__ void k_prep_cells(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
                 const double ph = (F.pnd_c[c] - F.rho_c[c]) / F.rho_c[c];
                 F.phiPC[c] = ph;
                 v[0] = fmax(v[0], fabs(ph));
+            } else if (P.positionCorrection == PDFB200_POSCORR_SIMPLE) {
+                F.phiPC[c] = F.pnd_c[c] / F.rho_c[c] - 1.;   // mcSimplePositionCorrection.C:143-145
             }
             const double Om = F.eps_c[c] / F.kfv_c[c];
             F.OmegaRaw_c[c] = Om;
@@ -177,8 +182,18 @@ __global__ void k_nodes_cell(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
     if (P.positionCorrection == PDFB200_POSCORR_LIMITED_SIMPLE) {
         const V3 u = ld3(F.UPC_c, c) * sc->pcCorr;
         pc[0] = u.x; pc[1] = u.y; pc[2] = u.z;
+    } else if (P.positionCorrection == PDFB200_POSCORR_SIMPLE) {
+        // gradPhi = C |Ufv| grad(phi) (mcSimplePositionCorrection.C:149); UPC_c holds -grad(phi)
+        const V3 g = (P.pcC * mag3(U)) * (-ld3(F.UPC_c, c));
+        pc[0] = g.x; pc[1] = g.y; pc[2] = g.z;
     } else { pc[0] = pc[1] = pc[2] = 0; }
     pc[3] = 0;
+    if (P.positionCorrection == PDFB200_POSCORR_EXTERNAL) {
+        const size_t nNodes = (size_t)M.nCells + M.nPoints + M.nFaces;
+        const double *row = F.pcExt_c + (size_t)c * 12;
+        for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < 4; ++k) F.nodePC[(q * nNodes + c) * 4 + k] = row[4 * q + k];
+    }
     double *aux = F.cellAux + (size_t)c * auxStride;
     aux[0] = (sqrt(k / F.kpdf_c[c]) - 1.0) / Tk;   // diffk
     aux[1] = F.p_c[c];
@@ -188,43 +203,55 @@ __global__ void k_nodes_cell(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
 __global__ void k_nodes_point(DMesh M, FieldPtrs F) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M.nPoints) return;
-    double acc[NODE_MID_STRIDE], pc[4];
+    double acc[NODE_MID_STRIDE], pc[12];
 #pragma unroll
     for (int k = 0; k < NODE_MID_STRIDE; ++k) acc[k] = 0;
-    pc[0] = pc[1] = pc[2] = pc[3] = 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) pc[k] = 0;
+    const size_t nNodes = (size_t)M.nCells + M.nPoints + M.nFaces;
+    const int nPl = F.pcPlanes;
     for (int j = M.pointCellStart[p]; j < M.pointCellStart[p + 1]; ++j) {
         const double w = M.pointWeights[j];
         const int c = M.pointCells[j];
-        const NodeRef nm{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)c};
+        const NodeRef nm{F.nodeMid, nNodes, (size_t)c};
 #pragma unroll
         for (int k = 0; k < NODE_MID_STRIDE; ++k) acc[k] += w * nm[k];
-        const double *q = F.nodePC + (size_t)c * 4;
-        pc[0] += w * q[0]; pc[1] += w * q[1]; pc[2] += w * q[2];
+        for (int q = 0; q < nPl; ++q) {
+            const double *r = F.nodePC + (q * nNodes + c) * 4;
+            const int nk = nPl > 1 ? 4 : 3;
+            for (int k = 0; k < nk; ++k) pc[4 * q + k] += w * r[k];
+        }
     }
-    const NodeRef o{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)(M.nCells + p)};
+    const NodeRef o{F.nodeMid, nNodes, (size_t)(M.nCells + p)};
 #pragma unroll
     for (int k = 0; k < NODE_MID_STRIDE; ++k) o[k] = acc[k];
-    double *oq = F.nodePC + (size_t)(M.nCells + p) * 4;
-    oq[0] = pc[0]; oq[1] = pc[1]; oq[2] = pc[2]; oq[3] = 0;
+    for (int q = 0; q < nPl; ++q) {
+        double *oq = F.nodePC + (q * nNodes + M.nCells + p) * 4;
+        oq[0] = pc[4 * q]; oq[1] = pc[4 * q + 1]; oq[2] = pc[4 * q + 2]; oq[3] = pc[4 * q + 3];
+    }
 }
 
 __global__ void k_nodes_face(DMesh M, FieldPtrs F, pdfb200_params P, const StepScalars *sc, int covZZ) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= M.nFaces) return;
-    const NodeRef o{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)(M.nCells + M.nPoints + f)};
-    double *oq = F.nodePC + (size_t)(M.nCells + M.nPoints + f) * 4;
+    const size_t nNodes = (size_t)M.nCells + M.nPoints + M.nFaces, nodeF = (size_t)M.nCells + M.nPoints + f;
+    const NodeRef o{F.nodeMid, nNodes, nodeF};
+    double *oq = F.nodePC + nodeF * 4;
     const int ow = M.owner[f];
-    const NodeRef no{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)ow};
+    const NodeRef no{F.nodeMid, nNodes, (size_t)ow};
     const double *qo = F.nodePC + (size_t)ow * 4;
+    const int nPl = F.pcPlanes;
     if (f < M.nInternalFaces) {
         const double w = M.linWeights[f];
         const int nb = M.neighbour[f];
-        const NodeRef nn{F.nodeMid, (size_t)M.nCells + M.nPoints + M.nFaces, (size_t)nb};
-        const double *qn = F.nodePC + (size_t)nb * 4;
+        const NodeRef nn{F.nodeMid, nNodes, (size_t)nb};
 #pragma unroll
         for (int k = 0; k < NODE_MID_STRIDE; ++k) o[k] = w * no[k] + (1 - w) * nn[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) oq[k] = w * qo[k] + (1 - w) * qn[k];
+        for (int q = 0; q < nPl; ++q) {
+            const double *a = F.nodePC + (q * nNodes + ow) * 4, *b = F.nodePC + (q * nNodes + nb) * 4;
+            double *r = F.nodePC + (q * nNodes + nodeF) * 4;
+            for (int k = 0; k < 4; ++k) r[k] = w * a[k] + (1 - w) * b[k];
+        }
         return;
     }
     const int bf = f - M.nInternalFaces;
@@ -233,8 +260,11 @@ __global__ void k_nodes_face(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
     if (geom == PDFB200_PATCH_EMPTY) {     // "cell value on an empty patch"
 #pragma unroll
         for (int k = 0; k < NODE_MID_STRIDE; ++k) o[k] = no[k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) oq[k] = qo[k];
+        for (int q = 0; q < nPl; ++q) {
+            const double *a = F.nodePC + (q * nNodes + ow) * 4;
+            double *r = F.nodePC + (q * nNodes + nodeF) * 4;
+            for (int k = 0; k < 4; ++k) r[k] = a[k];
+        }
         return;
     }
     const double *T = M.patchFaceT + 9 * BF_PATCH(info);
@@ -249,10 +279,20 @@ __global__ void k_nodes_face(DMesh M, FieldPtrs F, pdfb200_params P, const StepS
     o[NM_ETA] = no[NM_ETA];                                     // zeroGradient
     o[NM_ZVAR] = covZZ >= 0 ? F.Cov_b[(size_t)covZZ * M.nBnd + bf] : 0.0;
     o[11] = 0;
-    // UPosCorr: patch types of rho, fixedValue faces are zero (.C:76-84)
+    if (P.positionCorrection == PDFB200_POSCORR_EXTERNAL) {
+        // boundary values as uploaded (the OpenFOAM side has run correctBoundaryConditions())
+        const double *row = F.pcExt_b + (size_t)bf * 12;
+        for (int q = 0; q < 3; ++q) {
+            double *r = F.nodePC + (q * nNodes + nodeF) * 4;
+            for (int k = 0; k < 4; ++k) r[k] = row[4 * q + k];
+        }
+        return;
+    }
+    // limitedSimple: UPosCorr has the patch types of rho, fixedValue faces are zero (.C:76-84); simple: grad(phi) is
+    // zeroGradient (mcSimplePositionCorrection.C:92-109)
     V3 u = mk(qo[0], qo[1], qo[2]);
     if (geom == PDFB200_PATCH_WEDGE) u = xform(T, u);
-    else if (F.rhoFixed[bf]) u = mk(0, 0, 0);
+    else if (P.positionCorrection == PDFB200_POSCORR_LIMITED_SIMPLE && F.rhoFixed[bf]) u = mk(0, 0, 0);
     oq[0] = u.x; oq[1] = u.y; oq[2] = u.z; oq[3] = 0;
 }
 
@@ -461,7 +501,7 @@ void Cloud::initMoments() {
     momentBlock.alloc(nc * nMom + BLOCK_TAIL); momentBlock.zero(stream);
     phiPC.alloc(nc); UPC_c.alloc(nc * 3); OmegaRaw_c.alloc(nc); etaRaw_c.alloc(nc);
     const size_t nNodes = nc + nPoints + nFaces;
-    nodeMid.alloc(nNodes * NODE_MID_STRIDE); nodePC.alloc(nNodes * 4); cellAux.alloc(nc * cellAuxStride);
+    nodeMid.alloc(nNodes * NODE_MID_STRIDE); nodePC.alloc(nNodes * 4 * pcPlanes); cellAux.alloc(nc * cellAuxStride);
     phiPC.zero(stream); UPC_c.zero(stream); etaRaw_c.zero(stream);
     // TauCloudPDF boundary = R boundary (turbModel_.R()), patch types of k
     CUDA_CHECK(cudaMemcpyAsync(Tau_b.p, R_b.p, nb * 6 * sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -489,11 +529,13 @@ void Cloud::prepareFields() {
     double *scratch = finalSums.p + 64;   // device scratch scalars
     LAUNCH(this, k_prep_cells, gC, B, 0, dm, F, prm, scal.p, k1PartMax.p);
     LAUNCH(this, k_prep_reduce1, 1, 32, 0, gC, k1PartMax.p, prm, scal.p, scratch);
-    if (prm.positionCorrection == PDFB200_POSCORR_LIMITED_SIMPLE) {
+    if (prm.positionCorrection == PDFB200_POSCORR_LIMITED_SIMPLE || prm.positionCorrection == PDFB200_POSCORR_SIMPLE) {
         const int gG = std::min(gridFor(nCells, B), numSMs * 8);
         LAUNCH(this, k_prep_grad, gG, B, 0, dm, F, scal.p, k1PartMax.p);
-        LAUNCH(this, k_prep_reduce2, 1, 32, 0, gG, k1PartMax.p, prm, scal.p, scratch);
+        if (prm.positionCorrection == PDFB200_POSCORR_LIMITED_SIMPLE) LAUNCH(this, k_prep_reduce2, 1, 32, 0, gG, k1PartMax.p, prm, scal.p, scratch);
     }
+    if (prm.positionCorrection == PDFB200_POSCORR_EXTERNAL && !havePcExt)
+        throw std::logic_error("evolve: positionCorrection external selected but no fields uploaded (upload_poscorr_fields)");
     const int zz = covIndexZZ(prm);
     LAUNCH(this, k_nodes_cell, gridFor(nCells, 128), 128, 0, dm, F, prm, scal.p, zz, cellAuxStride);
     LAUNCH(this, k_nodes_point, gridFor(nPoints, 128), 128, 0, dm, F);
@@ -519,6 +561,30 @@ void Cloud::downloadCellFields(pdfb200_cell_fields &o) {
     for (int i = 0; i < nCov; ++i) { dl(o.Cov[i], Cov_c.p + i * nc, nc); dl(o.PhiPhiMom[i], PhiPhiMom.p + i * nc, nc); }
     for (int i = 0; i < prm.nPhi; ++i) { dl(o.UPhi[i], UPhi_c.p + i * nc * 3, nc * 3); dl(o.UPhiMom[i], UPhiMom.p + i * nc * 3, nc * 3); }
     CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// fields of an externally solved position correction (pdfb200_poscorr_fields): packed into rows of 12
+void Cloud::uploadPoscorr(const pdfb200_poscorr_fields &f) {
+    const size_t nc = nCells, nb = nBnd;
+    std::vector<double> hc(nc * 12, 0.0), hb(std::max<size_t>(nb, 1) * 12, 0.0);
+    auto put = [&](const double *cv, const double *bv, int off, int width) {
+        if (!cv) return;
+        if (!bv) throw std::invalid_argument("upload_poscorr_fields: cell values without boundary values");
+        for (size_t i = 0; i < nc; ++i) for (int k = 0; k < width; ++k) hc[i * 12 + off + k] = cv[i * width + k];
+        for (size_t i = 0; i < nb; ++i) for (int k = 0; k < width; ++k) hb[i * 12 + off + k] = bv[i * width + k];
+    };
+    put(f.G0, f.G0b, 0, 3); put(f.l, f.lb, 3, 1);
+    put(f.G1, f.G1b, 4, 3); put(f.zeta, f.zetab, 7, 1);
+    put(f.G2, f.G2b, 8, 3);
+    pcExt_c.upload(hc.data(), hc.size(), stream); pcExt_b.upload(hb.data(), hb.size(), stream);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    pcScale = f.scale;
+    havePcExt = true;
+    if (pcPlanes != 3) {
+        pcPlanes = 3;
+        const size_t nNodes = nc + nPoints + nFaces;
+        if (nodePC.n) { nodePC.alloc(nNodes * 4 * 3); nodePC.zero(stream); CUDA_CHECK(cudaStreamSynchronize(stream)); }
+    }
 }
 
 // the moment fields of a previous run instead of initMoments (mcParticleCloud.C:339-517, checkMoments :739-820)

@@ -605,6 +605,24 @@ struct InletRnd {
         } while (nIter < 50);
         return x0;
     }
+    // "sampling" (mcSamplingInletRandom.C:37-102): x = UMean + uRms N(0,1) is accepted with a probability proportional
+    // to x. The reference scales with the largest |x| of a batch of 1e6 deviates (and a factor 0.1); here the scale is
+    // the largest value the generator can produce (its normals end at 6.66 sigma), so no state is needed and every
+    // (face, step, draw) has its own stream. Same target density x exp(-(x-U)^2 b^2)/Q.
+    __device__ double sample(RngKey key, uint32_t bf, uint32_t step, uint32_t kDraw, double uRms) const {
+        const double xMax = fmax(UMean + 6.7 * uRms, PDF_SMALL);
+        const uint64_t entity = (uint64_t)bf | ((uint64_t)kDraw << 32);   // one stream per (face, draw); sub = attempt
+        for (uint32_t attempt = 0; attempt < (1u << 20); ++attempt) {
+            uint32_t o[4];
+            rngWords(key, entity, step, RNG_INJECT_SAMPLE, attempt, o);
+            float n0, n1;
+            normalPairF32(o[0], o[1], n0, n1);
+            const double u = (double)((((unsigned long long)o[3] << 32) | o[2]) >> 11) * 0x1.0p-53;
+            const double x = UMean + uRms * (double)n0;
+            if (u * xMax < x) return x;
+        }
+        return m;   // (not reached: the acceptance probability is above 5 %)
+    }
 };
 
 // mcInletOutletBoundary::correct(false) (.C:232-354): one WARP per boundary face. The
@@ -663,7 +681,8 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
                 rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 2, a1, a2);
                 rngUniform2(key, (uint32_t)bf, step, RNG_INJECT, 4 * kDraw + 3, uAcc, dummy);
                 // randomVelocity (.C:215-229): U_global = revTrans & Up = fwdTrans^T & Up
-                const V3 UpL = mk(inrnd.value(uVal), Uloc.y + sqRyy * n1, Uloc.z + sqRzz * n2);
+                const double uIn = P.inletRandom == PDFB200_INLET_RANDOM_SAMPLING ? inrnd.sample(key, (uint32_t)bf, step, kDraw, sqrt(R[0])) : inrnd.value(uVal);
+                const V3 UpL = mk(uIn, Uloc.y + sqRyy * n1, Uloc.z + sqRzz * n2);
                 const V3 Up = mk(T[0] * UpL.x + T[3] * UpL.y + T[6] * UpL.z, T[1] * UpL.x + T[4] * UpL.y + T[7] * UpL.z,
                                  T[2] * UpL.x + T[5] * UpL.y + T[8] * UpL.z);
                 // randomPoint (.C:179-212)
@@ -1408,7 +1427,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         K1Args A;
         A.M = dm; A.P = prm; A.in = S[cur]; A.out = S[cur ^ 1];
         A.perm = valsB.p; A.sc = scal.p;
-        A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride;
+        A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride; A.pcScale = pcScale;
         A.Un = Un.p; A.lostShare = lostShare.p; A.lostList = lostList.p; A.lostCount = lostCount.p; A.lostCap = (unsigned)lostList.n;
         A.injPatchTail = injPatchTail.p;
         A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ;

@@ -57,7 +57,7 @@ def test_create_fails_loudly_without_a_gpu():
 def test_ctypes_struct_sizes_match_c(tmp_path):
     src = tmp_path / "sizes.c"
     names = ["pdfb200_mesh", "pdfb200_params", "pdfb200_fv_fields", "pdfb200_cloud_fields", "pdfb200_particles",
-             "pdfb200_step_report", "pdfb200_cell_fields", "pdfb200_mesh_info"]
+             "pdfb200_step_report", "pdfb200_cell_fields", "pdfb200_mesh_info", "pdfb200_poscorr_fields"]
     body = "".join(f'printf("%zu\\n", sizeof({n}));' for n in names)
     src.write_text(f'#include <stdio.h>\n#include "{HEADER}"\nint main(void){{{body} printf("%zu\\n", offsetof(pdfb200_params, seed)); return 0;}}\n'
                    .replace("#include <stdio.h>", "#include <stdio.h>\n#include <stddef.h>"))
@@ -65,7 +65,7 @@ def test_ctypes_struct_sizes_match_c(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     py = [capi.MeshStruct, capi.Params, capi.FvFields, capi.CloudFields, capi.ParticlesStruct, capi.StepReport,
-          capi.CellFieldsStruct, capi.MeshInfo]
+          capi.CellFieldsStruct, capi.MeshInfo, capi.PoscorrFields]
     assert out[:-1] == [C.sizeof(t) for t in py]
     assert out[-1] == capi.Params.seed.offset
 

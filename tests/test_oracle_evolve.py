@@ -27,7 +27,7 @@ def _uniform_case(nx=4, ny=3, nz=3, U=(3.0, 1.0, -2.0), k=1.5, eps=4.5, **kw):
 def _set(case, **kw):
     from pdffoam_b200.cases import default_params
     p = case.params
-    base = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] not in ("mixed", "conserved", "addedIdx", "reserved")}
+    base = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] not in ("mixed", "conserved", "addedIdx")}
     base.pop("nPhi"); base.pop("nMixed"); base.pop("nConserved"); base.pop("nAdded")
     base.update(kw)
     case.params = default_params(p.nPhi, mixed=list(p.mixed[:p.nMixed]), conserved=list(p.conserved[:p.nConserved]), **base)
