@@ -67,7 +67,9 @@ enum {
     PDFB200_REACTION_COLD = 1,            /* "cold"           */
     PDFB200_REACTION_BURKE_SCHUMANN = 2,  /* "BurkeSchumann"  */
     PDFB200_REACTION_STEADY_FLAMELET = 3, /* "SteadyFlamelet" */
-    PDFB200_REACTION_NAIVE_FLAMELET = 4   /* "naiveFlamelet" (mcNaiveFlameletModel.C:64-69): rho = 1 - 3.2 z (1 - z), T = 1e5 / rho */
+    PDFB200_REACTION_NAIVE_FLAMELET = 4,  /* "naiveFlamelet" (mcNaiveFlameletModel.C:64-69): rho = 1 - 3.2 z (1 - z), T = 1e5 / rho */
+    PDFB200_REACTION_KULKARNI = 5         /* "KulkarniAutoIgnition" (mcKulkarniAutoIgnition.C:339-380): progress variable c integrated
+                                             with a tabulated source cdot(z, pv), rho and the added scalars looked up on (z, pv) */
 };
 /* mcPositionCorrection run-time selection (mcPositionCorrection/mcPositionCorrection.C): "limitedSimple" and
  * "simple" (mcSimplePositionCorrection.C:127-163) are algebraic and run entirely on the device. "external" is the
@@ -126,6 +128,7 @@ typedef struct pdfb200_params {
     double  coldDensity;                          /* mcColdReactionModel.C:57 */
     double  bsRfuel, bsRox, bsRstoi, bsTfuel, bsTox, bsTstoi, bsZstoi; /* mcBurkeSchumannReactionModel.C:63-69 */
     int32_t zIdx, TIdx, chiIdx;                   /* indices into the particle scalars */
+    int32_t cIdx, pvIdx;                          /* KulkarniAutoIgnition: progress variable c and its normalised form pv */
     double  Cchi;                                 /* mcSteadyFlamelet: chi = Cchi*Omega*zVar */
     int32_t nAdded; int32_t addedIdx[PDFB200_MAX_ADDED]; /* SteadyFlamelet "scalars (T)" */
     int32_t positionCorrection; double pcC, pcCFL; /* mcLimitedSimplePositionCorrection.C:90-102 */
@@ -260,8 +263,22 @@ int pdfb200_set_flamelet_tables(pdfb200_cloud *cloud, int32_t nChi, int32_t nZ,
                                 const double *chi, const double *z,
                                 int32_t nFields, const double *const *fields);
 
+/* Library of mcKulkarniAutoIgnitionReactionModel (constant/autoIgnition/{z,pv,cEq,cdot,rho,<scalars>},
+ * mcKulkarniAutoIgnition.C:111-335): z[nZ], pv[nPv], cEq[nZ], then nFields tables, each row-major [nZ][nPv]; field 0 is
+ * cdot, field 1 rho, fields 2.. the "added" scalars in addedIdx order.                                              */
+int pdfb200_set_autoignition_tables(pdfb200_cloud *cloud, int32_t nZ, int32_t nPv, const double *z, const double *pv,
+                                    const double *cEq, int32_t nFields, const double *const *fields);
+
 /* Upload the FV-owned fields (once per FV cycle block). */
 int pdfb200_upload_fv_fields(pdfb200_cloud *cloud, const pdfb200_fv_fields *f);
+/* The same in two halves, so that the copy of the next FV state overlaps the particle steps of the current one:
+ * stage starts an asynchronous copy (own stream, second set of device buffers) from the caller's buffers, which
+ * must be page-locked for the copy to overlap and must stay untouched until commit returns; commit waits for the
+ * copy and makes the staged fields the ones evolve() reads (a pointer swap). pdfSimpleFoam changes its FV fields
+ * once per block of PDF steps (tutorials/SandiaD/system/controlDict:41-43: 10 FV : 200 PDF), time-varying inflow
+ * data (timeVaryingMappedFixedValue) more often; either way the particle steps need not wait for the transfer. */
+int pdfb200_stage_fv_fields(pdfb200_cloud *cloud, const pdfb200_fv_fields *f);
+int pdfb200_commit_fv_fields(pdfb200_cloud *cloud);
 /* Upload rho / scalar / covariance fields and their boundary conditions. */
 int pdfb200_upload_cloud_fields(pdfb200_cloud *cloud, const pdfb200_cloud_fields *f);
 /* Upload the fields of an externally solved position correction (see pdfb200_poscorr_fields); once per solve. */

@@ -1,5 +1,6 @@
 // capi.cpp — CPU ORACLE (test infrastructure): the pdfb200.h entry points with
 // the prefix pdforacle_, plus a few probes used by the known-answer tests.
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -63,6 +64,19 @@ int pdforacle_set_flamelet_tables(pdforacle_cloud *h, int32_t nChi, int32_t nZ, 
     return PDFB200_OK;
 }
 
+int pdforacle_set_autoignition_tables(pdforacle_cloud *h, int32_t nZ, int32_t nPv, const double *z, const double *pv, const double *cEq,
+                                      int32_t nFields, const double *const *fields) {
+    Cloud &c = h->c;
+    if (nZ < 2 || nPv < 2 || nFields < 2) { g_err = "auto-ignition tables: need nZ >= 2, nPv >= 2, cdot and rho"; return PDFB200_ERR_INVALID; }
+    for (int i = 1; i < nZ; ++i) if (!(z[i] - z[i - 1] > 0)) { g_err = "auto-ignition z not strictly monotonically increasing"; return PDFB200_ERR_INVALID; }
+    for (int i = 1; i < nPv; ++i) if (!(pv[i] - pv[i - 1] > 0)) { g_err = "auto-ignition pv not strictly monotonically increasing"; return PDFB200_ERR_INVALID; }
+    c.aiZ.assign(z, z + nZ); c.aiPv.assign(pv, pv + nPv); c.aiCEq.assign(cEq, cEq + nZ);
+    c.aiCEqMax = *std::max_element(c.aiCEq.begin(), c.aiCEq.end());
+    c.aiFields.resize(nFields);
+    for (int f = 0; f < nFields; ++f) c.aiFields[f].assign(fields[f], fields[f] + (size_t)nZ * nPv);
+    return PDFB200_OK;
+}
+
 int pdforacle_upload_fv_fields(pdforacle_cloud *h, const pdfb200_fv_fields *f) {
     ORACLE_TRY
     Cloud &c = h->c;
@@ -83,6 +97,33 @@ int pdforacle_upload_fv_fields(pdforacle_cloud *h, const pdfb200_fv_fields *f) {
     ORACLE_CATCH
 }
 
+// stage / commit (pdfb200_stage_fv_fields / pdfb200_commit_fv_fields): the CPU has nothing to overlap; the staged
+// fields are held in a second cloud-side copy until the commit
+struct StagedFv { std::vector<double> U, Ub, p, pb, k, kb, e, eb, R, Rb; std::vector<uint8_t> UbF, kbF; bool have = false; };
+static thread_local StagedFv g_staged;
+int pdforacle_stage_fv_fields(pdforacle_cloud *h, const pdfb200_fv_fields *f) {
+    const int nc = h->c.mesh.nCells, nb = h->c.nBnd();
+    StagedFv &s = g_staged;
+    s.U.assign(f->U, f->U + 3 * nc); s.Ub.assign(f->Ub, f->Ub + 3 * nb); s.p.assign(f->p, f->p + nc); s.pb.assign(f->pb, f->pb + nb);
+    s.k.assign(f->k, f->k + nc); s.kb.assign(f->kb, f->kb + nb); s.e.assign(f->epsilon, f->epsilon + nc); s.eb.assign(f->epsilonb, f->epsilonb + nb);
+    s.R.assign(f->R, f->R + 6 * nc); s.Rb.assign(f->Rb, f->Rb + 6 * nb);
+    s.UbF.assign(nb, 0); s.kbF.assign(nb, 0);
+    if (f->UbFixed) s.UbF.assign(f->UbFixed, f->UbFixed + nb);
+    if (f->kbFixed) s.kbF.assign(f->kbFixed, f->kbFixed + nb);
+    s.have = true;
+    return PDFB200_OK;
+}
+int pdforacle_upload_fv_fields(pdforacle_cloud *h, const pdfb200_fv_fields *f);
+int pdforacle_commit_fv_fields(pdforacle_cloud *h) {
+    StagedFv &s = g_staged;
+    if (!s.have) { g_err = "commit_fv_fields: nothing staged (stage_fv_fields first)"; return PDFB200_ERR_STATE; }
+    pdfb200_fv_fields f{};
+    f.U = s.U.data(); f.Ub = s.Ub.data(); f.UbFixed = s.UbF.data(); f.p = s.p.data(); f.pb = s.pb.data();
+    f.k = s.k.data(); f.kb = s.kb.data(); f.kbFixed = s.kbF.data(); f.epsilon = s.e.data(); f.epsilonb = s.eb.data();
+    f.R = s.R.data(); f.Rb = s.Rb.data();
+    s.have = false;
+    return pdforacle_upload_fv_fields(h, &f);
+}
 int pdforacle_upload_cloud_fields(pdforacle_cloud *h, const pdfb200_cloud_fields *f) {
     ORACLE_TRY
     Cloud &c = h->c;

@@ -395,6 +395,8 @@ void Cloud::curlMixing() {
 }
 
 void Cloud::reactionCorrect(Particle &p) const {
+    if (prm.reactionModel == PDFB200_REACTION_KULKARNI && aiFields.size() < (size_t)(2 + prm.nAdded))
+        throw std::invalid_argument("KulkarniAutoIgnition selected but no auto-ignition tables were set");
     switch (prm.reactionModel) {
     case PDFB200_REACTION_COLD:                  // mcColdReactionModel.C:62-65
         p.rho = prm.coldDensity;
@@ -426,6 +428,25 @@ void Cloud::reactionCorrect(Particle &p) const {
         p.Phi[prm.chiIdx] = chi;
         p.rho = binterp(flFields[0], nZ, ichi, wchi, iz, wz);
         for (int i = 0; i < prm.nAdded; ++i) p.Phi[prm.addedIdx[i]] = binterp(flFields[1 + i], nZ, ichi, wchi, iz, wz);
+        break;
+    }
+    case PDFB200_REACTION_KULKARNI: {            // mcKulkarniAutoIgnition.C:339-380
+        const double z = p.Phi[prm.zIdx];
+        double &c = p.Phi[prm.cIdx];
+        int iz, ic; double wz, wc;
+        findCoeffs(aiZ, z, iz, wz);
+        const double cEq = aiCEq[iz] * (1. - wz) + aiCEq[iz + 1] * wz;
+        c = std::min(c, cEq);
+        const double pv = cEq > 1e-5 * aiCEqMax ? c / cEq : 0.;
+        p.Phi[prm.pvIdx] = pv;
+        findCoeffs(aiPv, pv, ic, wc);
+        const int nPv = (int)aiPv.size();
+        const double cdot = binterp(aiFields[0], nPv, iz, wz, ic, wc);
+        c += cdot * p.eta * deltaT;
+        findCoeffs(aiPv, pv, ic, wc);
+        p.rho = binterp(aiFields[1], nPv, iz, wz, ic, wc);
+        for (int i = 0; i < prm.nAdded; ++i) p.Phi[prm.addedIdx[i]] = binterp(aiFields[2 + i], nPv, iz, wz, ic, wc);
+        p.Co = std::max(p.Co, cdot);
         break;
     }
     default: break;

@@ -302,6 +302,8 @@ struct Cloud {
 
     // flamelet tables
     std::vector<double> flZ, flChi; std::vector<std::vector<double>> flFields; int nChi = 0, nZ = 0;
+    // KulkarniAutoIgnition library: z, pv, cEq[z], tables [nZ][nPv] (0 cdot, 1 rho, 2.. added)
+    std::vector<double> aiZ, aiPv, aiCEq; std::vector<std::vector<double>> aiFields; double aiCEqMax = 0;
 
     // model internals (updateInternals products)
     NodeField<double> OmegaN, kN, pStarN, etaN, zVarN;

@@ -54,7 +54,7 @@ class Params(C.Structure):
         ("coldDensity", C.c_double),
         ("bsRfuel", C.c_double), ("bsRox", C.c_double), ("bsRstoi", C.c_double),
         ("bsTfuel", C.c_double), ("bsTox", C.c_double), ("bsTstoi", C.c_double), ("bsZstoi", C.c_double),
-        ("zIdx", C.c_int32), ("TIdx", C.c_int32), ("chiIdx", C.c_int32),
+        ("zIdx", C.c_int32), ("TIdx", C.c_int32), ("chiIdx", C.c_int32), ("cIdx", C.c_int32), ("pvIdx", C.c_int32),
         ("Cchi", C.c_double),
         ("nAdded", C.c_int32), ("addedIdx", C.c_int32 * MAX_ADDED),
         ("positionCorrection", C.c_int32), ("pcC", C.c_double), ("pcCFL", C.c_double),
@@ -182,7 +182,7 @@ class PdfError(RuntimeError):
 
 # every symbol include/pdfb200.h declares (tests check the .so exports them all)
 API_SYMBOLS = [
-    "last_error", "create", "destroy", "set_params", "set_flamelet_tables", "upload_fv_fields",
+    "last_error", "create", "destroy", "set_params", "set_flamelet_tables", "set_autoignition_tables", "upload_fv_fields", "stage_fv_fields", "commit_fv_fields",
     "upload_cloud_fields", "upload_poscorr_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
@@ -224,7 +224,10 @@ class Library:
         f("download_particles").argtypes = [vp, C.c_int64, C.POINTER(ParticlesStruct), C.POINTER(C.c_int64)]
         f("evolve").argtypes = [vp, C.c_int32, C.POINTER(StepReport)]
         f("download_cell_fields").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("set_autoignition_tables").argtypes = [vp, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int32, C.POINTER(c_double_p)]
         f("upload_moments").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("stage_fv_fields").argtypes = [vp, C.POINTER(FvFields)]
+        f("commit_fv_fields").argtypes = [vp]
         f("upload_poscorr_fields").argtypes = [vp, C.POINTER(PoscorrFields)]
         f("step_counter").argtypes = [vp]; f("step_counter").restype = C.c_int64
         f("set_step_counter").argtypes = [vp, C.c_int64]
@@ -353,6 +356,15 @@ class CloudHandle:
         arr = (c_double_p * len(fl))(*[_dp(f) for f in fl])
         self.lib.check(self.lib.fn("set_flamelet_tables")(self.h, chi.size, z.size, _dp(chi), _dp(z), len(fl), arr), "set_flamelet_tables")
 
+    def set_autoignition_tables(self, z: np.ndarray, pv: np.ndarray, cEq: np.ndarray, fields: Sequence[np.ndarray]):
+        """constant/autoIgnition/* of mcKulkarniAutoIgnitionReactionModel: fields = [cdot, rho, added...], each [nZ][nPv]"""
+        z = np.ascontiguousarray(z, np.float64); pv = np.ascontiguousarray(pv, np.float64); cEq = np.ascontiguousarray(cEq, np.float64)
+        fs = [np.ascontiguousarray(f, np.float64) for f in fields]
+        for f in fs:
+            assert f.shape == (z.size, pv.size), f.shape
+        arr = (c_double_p * len(fs))(*[_dp(f) for f in fs])
+        self.lib.check(self.lib.fn("set_autoignition_tables")(self.h, z.size, pv.size, _dp(z), _dp(pv), _dp(cEq), len(fs), arr), "set_autoignition_tables")
+
     def upload_fv_fields(self, fv: Dict[str, np.ndarray]):
         """fv keys: U,Ub,UbFixed,p,pb,k,kb,kbFixed,epsilon,epsilonb,R,Rb."""
         s = FvFields()
@@ -365,6 +377,23 @@ class CloudHandle:
                 a = np.ascontiguousarray(a, np.float64); setattr(s, name, _dp(a))
             keep[name] = a
         self.lib.check(self.lib.fn("upload_fv_fields")(self.h, C.byref(s)), "upload_fv_fields")
+
+    def stage_fv_fields(self, fv: Dict[str, np.ndarray]):
+        """Start the asynchronous copy of the next FV state (pdfb200_stage_fv_fields); the arrays must be contiguous,
+        of the right dtype (no conversion copy is made here) and stay untouched until commit_fv_fields() returns."""
+        s = FvFields()
+        for name, _ in FvFields._fields_:
+            a = fv[name]
+            want = np.uint8 if name.endswith("Fixed") else np.float64
+            if a.dtype != want or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"stage_fv_fields: {name} must be a contiguous {want.__name__} array")
+            setattr(s, name, _u8p(a) if want is np.uint8 else _dp(a))
+        self._staged_keepalive = fv
+        self.lib.check(self.lib.fn("stage_fv_fields")(self.h, C.byref(s)), "stage_fv_fields")
+
+    def commit_fv_fields(self):
+        self.lib.check(self.lib.fn("commit_fv_fields")(self.h), "commit_fv_fields")
+        self._staged_keepalive = None
 
     def upload_cloud_fields(self, cf: Dict):
         """cf keys: rho,rhob,rhobFixed, Phi[list],Phib[list],PhibFixed[list], optional Cov,Covb,CovbFixed lists."""

@@ -21,7 +21,7 @@ from .meshgen import PolyMesh
 VELOCITY_MODELS = {"none": 0, "SLMFull": 1}                 # mcSLMFullVelocityModel.C:39-45
 MIXING_MODELS = {"none": 0, "IEM": 1, "modifiedCurl": 2}     # mcIEMMixingModel.C:37-43; modifiedCurl is new
 OMEGA_MODELS = {"none": 0, "RAS": 1}                        # mcRASOmegaModel.C:63-69
-REACTION_MODELS = {"none": 0, "cold": 1, "BurkeSchumann": 2, "SteadyFlamelet": 3, "naiveFlamelet": 4}
+REACTION_MODELS = {"none": 0, "cold": 1, "BurkeSchumann": 2, "SteadyFlamelet": 3, "naiveFlamelet": 4, "KulkarniAutoIgnition": 5}
 POSITION_CORRECTIONS = {"none": 0, "limitedSimple": 1, "simple": 2, "external": 3}   # external: ellipticRelaxation / Muradoglu / integrated solved on the OpenFOAM side
 INLET_RANDOM = {"inversion": 0, "sampling": 1}             # mcInletRandom.C:66-90
 LOCAL_TIME_STEPPING = {"none": 0, "off": 0, "false": 0, "cell": 1, "particle": 2}   # mcLocalTimeStepping.C:56-97
@@ -98,7 +98,9 @@ class Case:
         if capacity <= 0:
             capacity = int(self.mesh.n_cells * self.params.particlesPerCell * 1.5) + 4096
         h = CloudHandle(lib, self.mesh, self.params, device=device, capacity=capacity)
-        if self.tables is not None:
+        if self.tables is not None and "pv" in self.tables:
+            h.set_autoignition_tables(self.tables["z"], self.tables["pv"], self.tables["cEq"], self.tables["fields"])
+        elif self.tables is not None:
             h.set_flamelet_tables(self.tables["chi"], self.tables["z"], self.tables["fields"])
         h.upload_fv_fields(self.fv)
         h.upload_cloud_fields(self.cf)
@@ -272,9 +274,21 @@ def with_scalars(case: Case, names: Sequence[str], reaction: str, tables: Option
         case.fv["pb"] = case.fv["pb"] + 1.0e5
     elif reaction == "naiveFlamelet":
         base.update(TIdx=names.index("T"))
+    elif reaction == "KulkarniAutoIgnition":
+        # tutorials/AutoIgnitionBurner/constant/thermophysicalProperties:18-25: scalarFields (z c pv T d), scalars (T)
+        base.update(cIdx=names.index("c"), pvIdx=names.index("pv"), addedIdx=[names.index("T")])
+        case.tables = tables
     base.update(kw)
-    case.params = default_params(n_phi, mixed=[0], conserved=[0], **base)
+    base.setdefault("mixed", [0]); base.setdefault("conserved", [0])
+    case.params = default_params(n_phi, **base)
     return case
+
+
+def load_autoignition_tables(path: str) -> Dict:
+    """tests/golden/autoignition.npz -> {"z","pv","cEq","fields":[cdot, rho, T]} (rows = z, columns = pv,
+    mcKulkarniAutoIgnition.C:111-335)"""
+    t = np.load(path)
+    return dict(z=t["z"], pv=t["pv"], cEq=t["cEq"], fields=[t["cdot"], t["rho"], t["T"]])
 
 
 def load_flamelet_tables(path: str) -> Dict:
@@ -364,9 +378,12 @@ def wedge_jet(nx=24, nr_jet=4, nr_co=10, length=0.3, r_min=2e-4, r_jet=3.6e-3, r
 # available here), which is what "synthetic data of that shape" means for these cases.
 # ---------------------------------------------------------------------------
 def _streams_case(name: str, xs, r_blocks, half_angle_deg, streams, tables_path: Optional[str], scalars: Sequence[str],
-                  reaction: str, numerics: Dict, golden_dir: Optional[str] = None) -> Case:
+                  reaction: str, numerics: Dict, golden_dir: Optional[str] = None, solenoidal: bool = False) -> Case:
     """streams: [(patch name, r_upper, U, z, rho, handler)] from the axis outwards;
-    r_blocks: [(n cells, r_lo, r_hi, grading)] (blockMesh blocks in r)."""
+    r_blocks: [(n cells, r_lo, r_hi, grading)] (blockMesh blocks in r).
+    solenoidal: the frozen velocity field is the similarity solution of the round turbulent jet (Schlichting) in a
+    uniform coflow, derived from a stream function, so that the volume flux is divergence-free and the cloud has a
+    stationary state (the default field spreads outwards everywhere and slowly piles mass up at the outer wall)."""
     rs = np.concatenate([meshgen.graded(n, lo, hi, g)[(1 if i else 0):] for i, (n, lo, hi, g) in enumerate(r_blocks)])
     mesh = meshgen.wedge_mesh(xs, rs, half_angle_deg, inlet_split=[(s[0], s[1], s[5]) for s in streams])
     th = np.deg2rad(half_angle_deg)
@@ -385,8 +402,20 @@ def _streams_case(name: str, xs, r_blocks, half_angle_deg, streams, tables_path:
         idx = np.searchsorted(np.array([s[1] for s in streams]), r, side="left")
         return np.minimum(idx, len(streams) - 1)
 
+    sigma = 15.0
+    x0 = r_jet * sigma / 1.29                 # virtual origin: half-width r_jet at the inlet
+    Kj = (U_jet - U_co) * x0 / (2 * sigma ** 2)
+
     def Ufun(x):
         r = radius(x)
+        if solenoidal:
+            # psi = U_co r^2/2 + K (x+x0) xi^2/(1+xi^2/4), xi = sigma r/(x+x0): ux = psi_r / r, ur = -psi_x / r
+            xx = x[:, 0] + x0
+            xi = sigma * r / xx
+            den = (1 + 0.25 * xi ** 2) ** 2
+            ux = U_co + 2 * Kj * sigma ** 2 / xx / den
+            ur = Kj * sigma * xi * (1 - 0.25 * xi ** 2) / (xx * den)
+            return np.stack([ux, ur, np.zeros_like(ux)], axis=1)
         spread = r_jet * (1 + 8.0 * x[:, 0] / length)
         ux = U_co + (U_jet - U_co) * (r_jet / spread) * np.exp(-(r / spread) ** 2)
         for s in inflow[1:-1]:                                   # pilot-like annular streams decay into the coflow
@@ -467,9 +496,10 @@ def _streams_case(name: str, xs, r_blocks, half_angle_deg, streams, tables_path:
 TUTORIALS = ("SydneyBluffBodyFlow", "SandiaD", "SydneyBluffBodyFlame", "SandiaPropaneJet4x")
 
 
-def tutorial_case(name: str, ppc: Optional[int] = None, refine: int = 1, golden_dir: Optional[str] = None) -> Case:
+def tutorial_case(name: str, ppc: Optional[int] = None, refine: int = 1, golden_dir: Optional[str] = None, solenoidal: bool = False) -> Case:
     """The four tutorial-shaped configurations of BASELINE.json (configs[0..3]); `refine` multiplies the cell
-    counts of the blockMesh blocks in x and r, `ppc` overrides the particles per cell."""
+    counts of the blockMesh blocks in x and r, `ppc` overrides the particles per cell, `solenoidal` selects the
+    divergence-free jet field (see _streams_case; used by the stationary-state validation)."""
     import os
     IO, SLIP = meshgen.BC_INLET_OUTLET, meshgen.BC_SLIP
     if golden_dir is None:
@@ -483,7 +513,8 @@ def tutorial_case(name: str, ppc: Optional[int] = None, refine: int = 1, golden_
             [(8 * f, 1.5e-4, 3.6e-3, 2.0), (6 * f, 3.6e-3, 9.1e-3, 2.0), (20 * f, 9.1e-3, 0.15, 8.0)], 5.0,
             [("jet", 3.6e-3, 49.6, 1.0, 1.08147, IO), ("pilot", 9.1e-3, 11.4, 0.268692, 0.178466, IO), ("coflow", 1e30, 0.9, 0.0, 1.21731, IO)],
             os.path.join(golden_dir, "flamelet_sandiaD.npz"), ("z", "chi", "T"), "SteadyFlamelet",
-            dict(CFL=0.3, averagingCoeff=2e4, particlesPerCell=ppc or 40, ltsUpperBound=50.0, pcC=5e-2, Cmix=2.0, mixingModel="IEM"))
+            dict(CFL=0.3, averagingCoeff=2e4, particlesPerCell=ppc or 40, ltsUpperBound=50.0, pcC=5e-2, Cmix=2.0, mixingModel="IEM"),
+            solenoidal=solenoidal)
     if name == "SydneyBluffBodyFlame":
         # tutorials/SydneyBluffBodyFlame/constant/polyMesh/blockMeshDict:22-48: blocks (1 80 6)(1 80 40)(1 80 34);
         # jet r = 1.8 mm, bluff body r = 25 mm (slip), coflow to 150 mm; BASELINE configs[2]: modified-Curl mixing
@@ -515,3 +546,15 @@ def tutorial_case(name: str, ppc: Optional[int] = None, refine: int = 1, golden_
             None, ("z", "T"), "BurkeSchumann",
             dict(CFL=0.1, averagingCoeff=5e3, particlesPerCell=ppc or 400, ltsUpperBound=20.0, pcC=0.2, Cmix=2.0, mixingModel="IEM"))
     raise KeyError(f"unknown tutorial case {name}; valid: {TUTORIALS}")
+
+
+def sandiaD_validation_case(seed: int = 0x5EED, rng_mode: int = 0) -> Case:
+    """The case of the stationary-state validation (tests/test_gpu_sandiaD_profiles.py, tests/golden/
+    make_sandiaD_ensemble.py): SandiaD-shaped (tutorial_case("SandiaD")) with the divergence-free jet field, a short
+    averaging memory so that 4800 steps reach and sample the stationary state, and no position correction."""
+    case = tutorial_case("SandiaD", solenoidal=True)
+    case.params.averagingCoeff = 200.0
+    case.params.positionCorrection = POSITION_CORRECTIONS["none"]
+    case.params.seed = seed
+    case.params.rngMode = rng_mode
+    return case

@@ -37,6 +37,8 @@ Cloud::~Cloud() {
     if (evArA) cudaEventDestroy(evArA);
     if (evArB) cudaEventDestroy(evArB);
     for (auto &e : evMark) if (e) cudaEventDestroy(e);
+    if (evStaged) cudaEventDestroy(evStaged);
+    if (copyStream) cudaStreamDestroy(copyStream);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -51,12 +53,17 @@ static void validateParams(const pdfb200_params &p) {
     if (p.velocityModel < 0 || p.velocityModel > PDFB200_VELOCITY_SLMFULL) throw std::invalid_argument("Unknown mcVelocityModel type");
     if (p.mixingModel < 0 || p.mixingModel > PDFB200_MIXING_MODCURL) throw std::invalid_argument("Unknown mcMixingModel type");
     if (p.omegaModel < 0 || p.omegaModel > PDFB200_OMEGA_RAS) throw std::invalid_argument("Unknown mcOmegaModel type");
-    if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_NAIVE_FLAMELET) throw std::invalid_argument("Unknown mcReactionModel type");
+    if (p.reactionModel < 0 || p.reactionModel > PDFB200_REACTION_KULKARNI) throw std::invalid_argument("Unknown mcReactionModel type");
     if (p.positionCorrection < 0 || p.positionCorrection > PDFB200_POSCORR_EXTERNAL) throw std::invalid_argument("Unknown mcPositionCorrection type");
     if (p.inletRandom < 0 || p.inletRandom > PDFB200_INLET_RANDOM_SAMPLING) throw std::invalid_argument("Unknown mcInletRandom type");
     if (p.localTimeStepping < 0 || p.localTimeStepping > PDFB200_LTS_PARTICLE) throw std::invalid_argument("Unknown mcLocalTimeStepping type");
+    if (p.reactionModel == PDFB200_REACTION_KULKARNI) {
+        if (p.cIdx < 0 || p.cIdx >= p.nPhi || p.pvIdx < 0 || p.pvIdx >= p.nPhi) throw std::invalid_argument("KulkarniAutoIgnition: cIdx / pvIdx out of range");
+        if (p.nAdded < 0 || p.nAdded > PDFB200_MAX_ADDED) throw std::invalid_argument("KulkarniAutoIgnition: too many added scalars");
+        for (int i = 0; i < p.nAdded; ++i) if (p.addedIdx[i] < 0 || p.addedIdx[i] >= p.nPhi) throw std::invalid_argument("KulkarniAutoIgnition: added scalar out of range");
+    }
     if (p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_STEADY_FLAMELET ||
-        p.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET)
+        p.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET || p.reactionModel == PDFB200_REACTION_KULKARNI)
         if (p.zIdx < 0 || p.zIdx >= p.nPhi) throw std::invalid_argument("reaction model: zIdx out of range");
     if ((p.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN || p.reactionModel == PDFB200_REACTION_NAIVE_FLAMELET) &&
         (p.TIdx < 0 || p.TIdx >= p.nPhi))
@@ -114,9 +121,30 @@ void Cloud::create(const pdfb200_mesh &m, const pdfb200_params &p, int dev, int6
 // mcSteadyFlamelet's constructor fails cleanly when its library is missing or too small (mcSteadyFlamelet.C:120-286);
 // the kernels index the tables without bounds checks, so the same is demanded before anything runs
 void Cloud::requireTables() const {
+    if (prm.reactionModel == PDFB200_REACTION_KULKARNI) {
+        if (tableKind != 2) throw std::invalid_argument("KulkarniAutoIgnition selected but no auto-ignition tables were set (pdfb200_set_autoignition_tables)");
+        if (nFlFields < 2 + prm.nAdded) throw std::invalid_argument("KulkarniAutoIgnition: the library holds fewer tables than cdot + rho + the added scalars");
+        return;
+    }
     if (prm.reactionModel != PDFB200_REACTION_STEADY_FLAMELET) return;
-    if (nChi < 1 || nZ < 2) throw std::invalid_argument("SteadyFlamelet selected but no flamelet tables were set (pdfb200_set_flamelet_tables)");
+    if (tableKind != 1 || nChi < 1 || nZ < 2) throw std::invalid_argument("SteadyFlamelet selected but no flamelet tables were set (pdfb200_set_flamelet_tables)");
     if (nFlFields < 1 + prm.nAdded) throw std::invalid_argument("SteadyFlamelet: the flamelet library holds fewer tables than rho + the added scalars");
+}
+
+// sanity checks of mcKulkarniAutoIgnitionReactionModel's constructor (mcKulkarniAutoIgnition.C:262-335)
+void Cloud::setAutoIgnitionTables(int nZ_, int nPv_, const double *z, const double *pv, const double *cEq, int nFields, const double *const *fields) {
+    if (nZ_ < 2 || nPv_ < 2) throw std::invalid_argument("auto-ignition z and pv must have at least 2 elements");
+    for (int i = 1; i < nZ_; ++i) if (!(z[i] - z[i - 1] > 0)) throw std::invalid_argument("auto-ignition z not strictly monotonically increasing");
+    for (int i = 1; i < nPv_; ++i) if (!(pv[i] - pv[i - 1] > 0)) throw std::invalid_argument("auto-ignition pv not strictly monotonically increasing");
+    if (nFields < 2) throw std::invalid_argument("auto-ignition tables: cdot and rho are required");
+    nChi = nZ_; nZ = nPv_; nFlFields = nFields; tableKind = 2;
+    cEqMax = cEq[0];
+    for (int i = 1; i < nZ_; ++i) cEqMax = std::max(cEqMax, cEq[i]);
+    flChi.upload(z, nZ_, stream); flZ.upload(pv, nPv_, stream); flCEq.upload(cEq, nZ_, stream);
+    flFields.alloc((size_t)nFields * nZ_ * nPv_);
+    for (int f = 0; f < nFields; ++f)
+        CUDA_CHECK(cudaMemcpyAsync(flFields.p + (size_t)f * nZ_ * nPv_, fields[f], (size_t)nZ_ * nPv_ * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 void Cloud::setTables(int nChi_, int nZ_, const double *chi, const double *z, int nFields, const double *const *fields) {
@@ -126,7 +154,7 @@ void Cloud::setTables(int nChi_, int nZ_, const double *chi, const double *z, in
     for (int i = 1; i < nZ_; ++i) if (!(z[i] - z[i - 1] > 0)) throw std::invalid_argument("flamelet z not strictly monotonically increasing");
     for (int i = 1; i < nChi_; ++i) if (!(chi[i] - chi[i - 1] > 0)) throw std::invalid_argument("flamelet chi not strictly monotonically increasing");
     if (nFields < 1) throw std::invalid_argument("flamelet tables: at least rho is required");
-    nChi = nChi_; nZ = nZ_; nFlFields = nFields;
+    nChi = nChi_; nZ = nZ_; nFlFields = nFields; tableKind = 1;
     flChi.upload(chi, nChi, stream); flZ.upload(z, nZ, stream);
     flFields.alloc((size_t)nFields * nChi * nZ);
     for (int f = 0; f < nFields; ++f)
@@ -161,7 +189,15 @@ int pdfb200_set_flamelet_tables(pdfb200_cloud *c, int32_t nChi, int32_t nZ, cons
     return guarded([&] { H(c)->setTables(nChi, nZ, chi, z, nFields, fields); });
 }
 
+int pdfb200_set_autoignition_tables(pdfb200_cloud *c, int32_t nZ, int32_t nPv, const double *z, const double *pv, const double *cEq,
+                                    int32_t nFields, const double *const *fields) {
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->setAutoIgnitionTables(nZ, nPv, z, pv, cEq, nFields, fields); });
+}
+
 int pdfb200_upload_fv_fields(pdfb200_cloud *c, const pdfb200_fv_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->uploadFv(*f); }); }
+int pdfb200_stage_fv_fields(pdfb200_cloud *c, const pdfb200_fv_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->stageFv(*f); }); }
+int pdfb200_commit_fv_fields(pdfb200_cloud *c) { USE_DEVICE(c); return guarded([&] { H(c)->commitFv(); }); }
 int pdfb200_upload_cloud_fields(pdfb200_cloud *c, const pdfb200_cloud_fields *f) { USE_DEVICE(c); return guarded([&] { H(c)->uploadCloudFields(*f); }); }
 int pdfb200_upload_poscorr_fields(pdfb200_cloud *c, const pdfb200_poscorr_fields *f) {
     if (!f) { g_err = "upload_poscorr_fields: null argument"; return PDFB200_ERR_INVALID; }

@@ -80,6 +80,12 @@ struct Cloud {
     // FV-owned
     DBuf<double> Ufv_c, Ufv_b, p_c, p_b, kfv_c, kfv_b, eps_c, eps_b, R_c, R_b;
     DBuf<uint8_t> UbFixed, kbFixed, rhoFixed;
+    // second set of the FV-owned fields: target of pdfb200_stage_fv_fields, swapped in by pdfb200_commit_fv_fields
+    DBuf<double> stg_U_c, stg_U_b, stg_p_c, stg_p_b, stg_k_c, stg_k_b, stg_eps_c, stg_eps_b, stg_R_c, stg_R_b;
+    DBuf<uint8_t> stg_UbFixed, stg_kbFixed;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evStaged = nullptr;
+    bool stagedPending = false;
     // cloud fields (cell + boundary)
     DBuf<double> rho_c, rho_b, rhoInst_c, pnd_c, pndInst_c, Updf_c, Updf_b, Tau_c, Tau_b, kpdf_c, kpdf_b;
     DBuf<double> Phi_c, Phi_b, Cov_c, Cov_b;       // [nPhi][nCells] etc.
@@ -102,8 +108,10 @@ struct Cloud {
     DBuf<double> Un, inletU, inletR, fwdTrans, probVec;
     bool inletCached = false;
     // flamelet tables
-    DBuf<double> flChi, flZ, flFields;
+    DBuf<double> flChi, flZ, flFields, flCEq;     // Kulkarni: flChi = z, flZ = pv, tables [nZ][nPv], flCEq = cEq[nZ]
     int nChi = 0, nZ = 0, nFlFields = 0;
+    double cEqMax = 0;
+    int tableKind = 0;                // 0 none, 1 flamelet (chi, z), 2 auto-ignition (z, pv)
 
     // ---- particles ----
     PState S[2]{};
@@ -143,8 +151,11 @@ struct Cloud {
     void chooseSortKey();                             // mesh_build.cu
     void setParams(const pdfb200_params &p);
     void requireTables() const;
+    void setAutoIgnitionTables(int nZ, int nPv, const double *z, const double *pv, const double *cEq, int nFields, const double *const *fields);
     void setTables(int nChi, int nZ, const double *chi, const double *z, int nFields, const double *const *fields);
     void uploadFv(const pdfb200_fv_fields &f);
+    void stageFv(const pdfb200_fv_fields &f);
+    void commitFv();
     void uploadCloudFields(const pdfb200_cloud_fields &f);
     void uploadPoscorr(const pdfb200_poscorr_fields &f);
     void initMoments();

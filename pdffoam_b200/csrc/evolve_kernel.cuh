@@ -66,8 +66,10 @@ struct K1Args {
     unsigned *lostCount;
     unsigned lostCap;
     const int *injPatchTail;
-    const double *flChi, *flZ, *flFields;
+    const double *flChi, *flZ, *flFields;   // SteadyFlamelet: chi, z, tables [nChi][nZ]; KulkarniAutoIgnition: z, pv, tables [nZ][nPv]
     int nChi, nZ;
+    const double *flCEq;   // KulkarniAutoIgnition: cEq[nZ]
+    double cEqMax;
     RngKey key;
     double *partSum, *partMax;
     int hasOpen;
@@ -189,10 +191,10 @@ __device__ __forceinline__ double stabilise(double x, double y) { return x < 0 ?
 
 // Reaction models on one particle: mcColdReactionModel.C:62-65,
 // mcBurkeSchumannReactionModel.C:77-91, mcSteadyFlamelet.C:304-329.
-struct FlameletTables { const double *chi, *z, *fields; int nChi, nZ; };
+struct FlameletTables { const double *chi, *z, *fields; int nChi, nZ; const double *cEq; double cEqMax; };
 template <int NPHI>
 __device__ __forceinline__ void reactionCorrect(const KParams &P, const FlameletTables &F, double Omega, double zVar,
-                                                double pCell, double (&phi)[NPHI], double &rho) {
+                                                double pCell, double etaDeltaT, double (&phi)[NPHI], double &rho, double &Co) {
     if (P.reactionModel == PDFB200_REACTION_COLD) {
         rho = P.coldDensity;
     } else if (P.reactionModel == PDFB200_REACTION_BURKE_SCHUMANN) {
@@ -225,6 +227,27 @@ __device__ __forceinline__ void reactionCorrect(const KParams &P, const Flamelet
 #pragma unroll
             for (int k = 0; k < NPHI; ++k) if (k == PRM_AT(P, addedIdx, a)) phi[k] = v;
         }
+    } else if (P.reactionModel == PDFB200_REACTION_KULKARNI) {   // mcKulkarniAutoIgnition.C:339-380; rows = z, columns = pv
+        const double z = pickPhi(phi, P.zIdx);
+        double c = pickPhi(phi, P.cIdx);
+        int iz, ic; double wz, wc;
+        findCoeffsDev(F.chi, F.nChi, z, iz, wz);
+        const double cEq = F.cEq[iz] * (1. - wz) + F.cEq[iz + 1] * wz;
+        c = fmin(c, cEq);
+        const double pv = cEq > 1e-5 * F.cEqMax ? c / cEq : 0.;
+        findCoeffsDev(F.z, F.nZ, pv, ic, wc);
+        const size_t tab = (size_t)F.nChi * F.nZ;
+        const double cdot = binterpDev(F.fields, F.nChi, F.nZ, iz, wz, ic, wc);
+        c += cdot * etaDeltaT;
+        rho = binterpDev(F.fields + tab, F.nChi, F.nZ, iz, wz, ic, wc);
+#pragma unroll
+        for (int k = 0; k < NPHI; ++k) { if (k == P.cIdx) phi[k] = c; if (k == P.pvIdx) phi[k] = pv; }
+        for (int a = 0; a < P.nAdded; ++a) {
+            const double v = binterpDev(F.fields + (size_t)(2 + a) * tab, F.nChi, F.nZ, iz, wz, ic, wc);
+#pragma unroll
+            for (int k = 0; k < NPHI; ++k) if (k == PRM_AT(P, addedIdx, a)) phi[k] = v;
+        }
+        Co = fmax(Co, cdot);
     }
 }
 
@@ -697,8 +720,8 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             // reaction model
             {
                 FlameletTables FT;
-                FT.chi = A.flChi; FT.z = A.flZ; FT.fields = A.flFields; FT.nChi = A.nChi; FT.nZ = A.nZ;
-                reactionCorrect(P, FT, Omega, val[NM_ZVAR], aux[1], phi, rho);
+                FT.chi = A.flChi; FT.z = A.flZ; FT.fields = A.flFields; FT.nChi = A.nChi; FT.nZ = A.nZ; FT.cEq = A.flCEq; FT.cEqMax = A.cEqMax;
+                reactionCorrect(P, FT, Omega, val[NM_ZVAR], aux[1], etaOld * deltaT, phi, rho, Co);
             }
             // the scalars have their final values: written now, not carried through the second walk
             A.out.omega[i] = Omega; A.out.rho[i] = rho;

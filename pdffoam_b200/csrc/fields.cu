@@ -463,6 +463,39 @@ void Cloud::uploadFv(const pdfb200_fv_fields &f) {
     haveFv = true;
 }
 
+void Cloud::stageFv(const pdfb200_fv_fields &f) {
+    if (!f.U || !f.Ub || !f.p || !f.pb || !f.k || !f.kb || !f.epsilon || !f.epsilonb || !f.R || !f.Rb)
+        throw std::runtime_error("stage_fv_fields: null field pointer");
+    if (!copyStream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evStaged, cudaEventDisableTiming));
+    }
+    cudaStream_t s = copyStream;
+    const size_t nc = nCells, nb = nBnd;
+    uploadOrZero(stg_U_c, f.U, nc * 3, s); uploadOrZero(stg_U_b, f.Ub, nb * 3, s);
+    uploadOrZero(stg_p_c, f.p, nc, s); uploadOrZero(stg_p_b, f.pb, nb, s);
+    uploadOrZero(stg_k_c, f.k, nc, s); uploadOrZero(stg_k_b, f.kb, nb, s);
+    uploadOrZero(stg_eps_c, f.epsilon, nc, s); uploadOrZero(stg_eps_b, f.epsilonb, nb, s);
+    uploadOrZero(stg_R_c, f.R, nc * 6, s); uploadOrZero(stg_R_b, f.Rb, nb * 6, s);
+    uploadFlags(stg_UbFixed, f.UbFixed, nb, s); uploadFlags(stg_kbFixed, f.kbFixed, nb, s);
+    CUDA_CHECK(cudaEventRecord(evStaged, s));
+    stagedPending = true;
+}
+
+template <class T>
+static void swapBuf(DBuf<T> &a, DBuf<T> &b) { std::swap(a.p, b.p); std::swap(a.n, b.n); }
+
+void Cloud::commitFv() {
+    if (!stagedPending) throw std::logic_error("commit_fv_fields: nothing staged (stage_fv_fields first)");
+    // every later launch on the library's stream sees the staged copy complete; the host does not wait
+    CUDA_CHECK(cudaStreamWaitEvent(stream, evStaged, 0));
+    swapBuf(Ufv_c, stg_U_c); swapBuf(Ufv_b, stg_U_b); swapBuf(p_c, stg_p_c); swapBuf(p_b, stg_p_b);
+    swapBuf(kfv_c, stg_k_c); swapBuf(kfv_b, stg_k_b); swapBuf(eps_c, stg_eps_c); swapBuf(eps_b, stg_eps_b);
+    swapBuf(R_c, stg_R_c); swapBuf(R_b, stg_R_b); swapBuf(UbFixed, stg_UbFixed); swapBuf(kbFixed, stg_kbFixed);
+    stagedPending = false;
+    haveFv = true;
+}
+
 void Cloud::uploadCloudFields(const pdfb200_cloud_fields &f) {
     if (!f.rho || !f.rhob) throw std::runtime_error("upload_cloud_fields: rho missing");
     cudaStream_t s = stream;

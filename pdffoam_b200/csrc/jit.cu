@@ -71,7 +71,7 @@ std::string prologue(const pdfb200_params &p, bool axisym, bool hasOpen, int tet
     JI(interpU) JI(interpk) JI(interpDiffU) JI(interpOmega) JI(interpUPosCorr) JI(interpZVar) JI(interpEta)
     JI(velocityModel) JD(C0) JD(C1) JI(mixingModel) JD(Cmix) JI(omegaModel) JI(reactionModel) JD(coldDensity)
     JD(bsRfuel) JD(bsRox) JD(bsRstoi) JD(bsTfuel) JD(bsTox) JD(bsTstoi) JD(bsZstoi)
-    JI(zIdx) JI(TIdx) JI(chiIdx) JD(Cchi) JI(nAdded) JA(addedIdx, PDFB200_MAX_ADDED)
+    JI(zIdx) JI(TIdx) JI(chiIdx) JI(cIdx) JI(pvIdx) JD(Cchi) JI(nAdded) JA(addedIdx, PDFB200_MAX_ADDED)
     JI(positionCorrection) JI(localTimeStepping) JD(ltsUpperBound)
 #undef JI
 #undef JD

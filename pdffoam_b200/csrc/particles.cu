@@ -519,7 +519,8 @@ __global__ void k_init_models(DMesh M, pdfb200_params P, PState S, int n, const 
 #pragma unroll
     for (int k = 0; k < PDFB200_MAX_PHI; ++k) phi[k] = k < P.nPhi ? S.phi[k][i] : 0.0;
     double rho = S.rho[i];
-    reactionCorrect(P, FT, Omega, val[NM_ZVAR], cellAux[(size_t)cell * auxStride + 1], phi, rho);
+    double CoUnused = 0;
+    reactionCorrect(P, FT, Omega, val[NM_ZVAR], cellAux[(size_t)cell * auxStride + 1], eta * sc->deltaT, phi, rho, CoUnused);
     S.rho[i] = rho;
 #pragma unroll
     for (int k = 0; k < PDFB200_MAX_PHI; ++k) if (k < P.nPhi) S.phi[k][i] = phi[k];
@@ -1146,7 +1147,7 @@ static RngKey makeKey(uint64_t seed) {
 
 static FlameletTables tablesOf(const Cloud &c) {
     FlameletTables f;
-    f.chi = c.flChi.p; f.z = c.flZ.p; f.fields = c.flFields.p; f.nChi = c.nChi; f.nZ = c.nZ;
+    f.chi = c.flChi.p; f.z = c.flZ.p; f.fields = c.flFields.p; f.nChi = c.nChi; f.nZ = c.nZ; f.cEq = c.flCEq.p; f.cEqMax = c.cEqMax;
     return f;
 }
 
@@ -1430,7 +1431,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride; A.pcScale = pcScale;
         A.Un = Un.p; A.lostShare = lostShare.p; A.lostList = lostList.p; A.lostCount = lostCount.p; A.lostCap = (unsigned)lostList.n;
         A.injPatchTail = injPatchTail.p;
-        A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ;
+        A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ; A.flCEq = flCEq.p; A.cEqMax = cEqMax;
         A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
         const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
         // lost-particle bookkeeping of this step starts empty; the cells are only touched when the previous step

@@ -12,6 +12,9 @@ Run in the build container (needs /root/reference for the flamelet tables):
 2. lookup_golden.npz — lookups on those tables evaluated by an independent
    numpy restatement of findCoeffs/binterp (mcSteadyFlamelet.C:44-93) written
    in this script, used to pin the C++ oracle and the CUDA kernel.
+4. autoignition.npz — the auto-ignition library of tutorials/AutoIgnitionBurner
+   (constant/autoIgnition/{z,pv,cEq,cdot,rho,T}), the table input of
+   mcKulkarniAutoIgnitionReactionModel (mcKulkarniAutoIgnition.C:111-335).
 3. inlet_golden.npz — mcInletRandom PDF/CDF/Q (mcInletRandomI.H:28-39,
    mcInletRandom.C:92-108) evaluated with scipy for the parameters of
    tests/mcInletRandom (Umean=2, urms=4), plus numerical quadrature of Q.
@@ -81,6 +84,14 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **t)
         tables[name] = t
         print(name, {k: v.shape for k, v in t.items()})
+
+    # 4. autoignition.npz - the library of mcKulkarniAutoIgnitionReactionModel (tutorials/AutoIgnitionBurner/constant/
+    #    autoIgnition/{z,pv,cEq,cdot,rho,T}; rows = z, columns = pv, mcKulkarniAutoIgnition.C:111-335)
+    d = os.path.join(REF, "AutoIgnitionBurner", "constant", "autoIgnition")
+    ai = {k: parse_foam_list(os.path.join(d, k)) for k in ("z", "pv", "cEq", "cdot", "rho", "T")}
+    assert ai["cdot"].shape == (ai["z"].size, ai["pv"].size) == ai["rho"].shape == ai["T"].shape and ai["cEq"].shape == ai["z"].shape
+    np.savez_compressed(os.path.join(HERE, "autoignition.npz"), **ai)
+    print("autoignition", {k: v.shape for k, v in ai.items()})
 
     rng = np.random.default_rng(2024)
     out = {}

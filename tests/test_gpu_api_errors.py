@@ -89,3 +89,29 @@ def test_default_ids_and_next_id(device_lib):
     h2 = case.make_cloud(device_lib)
     h2.upload_particles(R)
     assert np.array_equal(np.sort(h2.download_particles()["id"]), np.arange(Q["m"].size, dtype=np.uint32))
+
+
+def test_stage_and_commit_equal_a_plain_upload(device_lib):
+    """pdfb200_stage_fv_fields + pdfb200_commit_fv_fields (asynchronous copy into a second buffer set, then a pointer
+    swap) must leave the cloud in the state pdfb200_upload_fv_fields leaves it in, also when the staged copy is
+    issued while an evolve() of the previous fields is what runs next"""
+    case = cases.synthetic_box(6, 4, 3, ppc=12, closed=False, number_control=True)
+    case.params.deltaT0 = 2e-3
+    fv2 = {k: (v.copy() if v.dtype == np.uint8 else np.ascontiguousarray(v * (1.1 if k in ("U", "Ub", "k", "kb") else 1.0))) for k, v in case.fv.items()}
+    fv1 = {k: np.ascontiguousarray(v) for k, v in case.fv.items()}
+    a = case.make_cloud(device_lib); b = case.make_cloud(device_lib)
+    a.seed_particles(); b.seed_particles()
+    with pytest.raises(capi.PdfError, match="nothing staged"):
+        b.commit_fv_fields()
+    for step in range(4):
+        fields = fv2 if step % 2 else fv1
+        a.upload_fv_fields(fields)
+        if step == 0:
+            b.stage_fv_fields(fields)
+        b.commit_fv_fields()
+        b.stage_fv_fields(fv1 if step % 2 else fv2)       # the next state, copied while this step runs
+        ra, rb = a.evolve(1)[0], b.evolve(1)[0]
+        assert ra.deltaTNext == rb.deltaTNext and ra.nParticles == rb.nParticles and ra.UMax == rb.UMax
+    ca, cb = a.download_cell_fields(), b.download_cell_fields()
+    for k in ("rho", "U", "k", "Tau"):
+        assert np.array_equal(ca[k], cb[k]), k

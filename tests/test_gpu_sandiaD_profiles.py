@@ -1,0 +1,93 @@
+"""Stationary-state validation on the SandiaD-shaped case (BASELINE north_star acceptance sentence: "reproducing the
+reference's converged SandiaD mean and RMS profiles within the stated statistical tolerance").
+
+Reference ensemble: tests/golden/sandiaD_ensemble.npz, 8 runs of the CPU oracle with the reference's random-number
+behaviour (one sequential stream in list order, tests/golden/make_sandiaD_ensemble.py) on
+pdffoam_b200.cases.sandiaD_validation_case(): jet / pilot / coflow blocks, graded wedge mesh, (z chi T) with
+SteadyFlamelet on the reference's flamelet library, IEM, RAS, cell local time stepping, number control, 4800 steps.
+Device ensemble: 8 runs of libpdfb200 with its keyed Philox streams and different seeds.
+
+Observables (tutorials/SandiaD/system/case.ini:80-140, sampleDict): UCloudPDF x/y, uRMS = sqrt(Tau_xx),
+vRMS = sqrt(Tau_yy), uv = Tau_xy, z, zRMS = sqrt(max(zzCov, 0)), T, TRMS = sqrt(max(TTCov, 0)); per cell, and as radial
+profiles at x/D = 1, 2, 3, 7.5, 15, 30, 45, 60 (D = 7.2 mm).
+
+Stated tolerance. Per cell a Welch t statistic of the two ensemble means (8 + 8 members, about 14 degrees of freedom):
+|t| <= 6 for at least 99 % of the cells of every observable (two-sided p = 3e-5 per cell); every radial profile: the
+mean of t over the profile's cells, scaled by sqrt(cells/ (1 + 2 rho)) with rho = 0.5 allowing for the correlation of
+neighbouring cells, below 4.5 in magnitude; the domain average of every observable |t| < 4.5; ratio of the two ensemble
+variances, averaged over the domain, within [1/3, 3]."""
+import os
+
+import numpy as np
+import pytest
+
+from pdffoam_b200 import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURE = os.path.join(ROOT, "tests", "golden", "sandiaD_ensemble.npz")
+FIELDS = ("Ux", "Ur", "uRMS", "vRMS", "uv", "z", "zRMS", "T", "TRMS")
+D_JET = 7.2e-3
+STATIONS = (1, 2, 3, 7.5, 15, 30, 45, 60)
+
+
+def _observables(c):
+    return dict(Ux=c["U"][:, 0], Ur=c["U"][:, 1], uRMS=np.sqrt(np.maximum(c["Tau"][:, 0], 0)), vRMS=np.sqrt(np.maximum(c["Tau"][:, 3], 0)),
+                uv=c["Tau"][:, 1], z=c["Phi"][0], zRMS=np.sqrt(np.maximum(c["Cov"][0], 0)), T=c["Phi"][2],
+                TRMS=np.sqrt(np.maximum(c["Cov"][5], 0)))
+
+
+def test_reference_ensemble_is_stationary():
+    """the fixture itself: between steps 3600, 4200 and 4800 the ensemble mean of every domain-averaged observable
+    moves by less than 2.5 standard errors of the ensemble (8 members)"""
+    f = np.load(FIXTURE)
+    n = int(f["n_members"])
+    assert n >= 8 and int(f["n_steps"]) == int(f["probe_steps"][-1])
+    for k in FIELDS:
+        p = f["probe_" + k]                      # [member, probe]
+        for a, b in ((0, 2), (1, 2)):
+            d = p[:, b] - p[:, a]
+            t = d.mean() / (d.std(ddof=1) / np.sqrt(n) + 1e-300)
+            assert abs(t) < 2.5 or abs(d.mean()) < 1e-3 * abs(p[:, b].mean()), f"{k}: drift between steps {f['probe_steps'][a]} and {f['probe_steps'][b]}: t = {t:.2f}"
+
+
+@pytest.mark.gpu
+def test_device_ensemble_reproduces_the_reference_profiles(device_lib):
+    f = np.load(FIXTURE)
+    n_ref, n_steps = int(f["n_members"]), int(f["n_steps"])
+    n_dev = 8
+    runs = []
+    mesh = None
+    for s in range(n_dev):
+        case = cases.sandiaD_validation_case(seed=31337 + 101 * s, rng_mode=0)
+        mesh = case.mesh
+        h = case.make_cloud(device_lib)
+        h.seed_particles()
+        h.evolve(n_steps)
+        runs.append(_observables(h.download_cell_fields()))
+        h.close()
+    cc = mesh.cell_centres_simple()
+    xs = np.unique(np.round(cc[:, 0], 9))
+    worst = {}
+    for k in FIELDS:
+        a = np.stack([r[k] for r in runs])
+        ma, va = a.mean(0), a.var(0, ddof=1)
+        mb, vb = f["mean_" + k], f["var_" + k]
+        se = np.sqrt(va / n_dev + vb / n_ref) + 1e-300
+        t = (ma - mb) / se
+        # cells where both ensembles are constant (e.g. T in the pure coflow) carry no information
+        live = (va + vb) > 1e-24 * (1 + ma ** 2)
+        frac = np.mean(np.abs(t[live]) > 6.0)
+        assert frac <= 0.01, f"{k}: {np.count_nonzero(np.abs(t[live]) > 6.0)} of {live.sum()} cells outside the confidence bound"
+        for xd in STATIONS:
+            x_col = xs[np.argmin(np.abs(xs - xd * D_JET))]
+            sel = live & (np.abs(cc[:, 0] - x_col) < 1e-9)
+            if sel.sum() < 4:
+                continue
+            tp = t[sel].mean() * np.sqrt(sel.sum() / 2.0)
+            worst[(k, xd)] = tp
+            assert abs(tp) < 4.5, f"{k}: radial profile at x/D = {xd} biased, scaled mean t = {tp:.2f}"
+        ga, gb = a.mean(1), f["domain_" + k]
+        tg = (ga.mean() - gb.mean()) / np.sqrt(ga.var(ddof=1) / n_dev + gb.var(ddof=1) / n_ref + 1e-300)
+        assert abs(tg) < 4.5, f"{k}: domain average biased: {ga.mean():.6g} vs {gb.mean():.6g}, t = {tg:.2f}"
+        ratio = va[live].mean() / vb[live].mean()
+        assert 1 / 3 < ratio < 3, f"{k}: ensemble variance ratio {ratio:.3f}"

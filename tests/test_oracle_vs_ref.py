@@ -175,3 +175,36 @@ def test_tet_decomposition_matches_reference_code(oracle_lib, ref, idx):
                 assert ref.lib.pdfref_decomp_inside(d, int(t), dp(p)) == oracle_lib.fn("tet_inside")(h.h, int(t), dp(p))
     finally:
         ref.lib.pdfref_decomp_destroy(d)
+
+
+# ---------------------------------------------------------------------------
+# mcSamplingInletRandom ("sampling"): stateful in the reference (batches of 1e6 deviates on the cloud's Random),
+# stateless and keyed here - only the distribution can agree
+# ---------------------------------------------------------------------------
+def _ks_two_sample(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate([a, b])
+    d = np.abs(np.searchsorted(a, allv, side="right") / a.size - np.searchsorted(b, allv, side="right") / b.size).max()
+    return d, d * np.sqrt(a.size * b.size / (a.size + b.size))
+
+
+@pytest.mark.parametrize("UMean,uRms", [(2.0, 4.0), (20.0, 3.0), (0.0, 1.0)])
+def test_sampling_generator_has_the_reference_distribution(oracle_lib, ref, UMean, uRms):
+    """(2, 4) is the case of tests/mcInletRandom/mcInletRandomTest.C, which histograms both generators. Two-sample
+    Kolmogorov-Smirnov between 2e5 values of the compiled reference class and of the oracle's keyed and sequential
+    generators; and each against the analytic CDF (mcInletRandomI.H:34-38)."""
+    n = 200000
+    r = np.zeros(n)
+    assert ref.lib.pdfref_inlet_sampling(UMean, uRms, 1, n, dp(r)) == 0, ref.error()
+    keyed, seq = np.zeros(n), np.zeros(n)
+    oracle_lib.fn("inlet_sampling")(UMean, uRms, 12345, 7, 3, n, dp(keyed), dp(seq))
+    assert r.min() > 0 and keyed.min() > 0 and seq.min() > 0
+    for name, x in (("keyed", keyed), ("sequential", seq)):
+        d, stat = _ks_two_sample(r, x)
+        assert stat < 1.95, f"{name}: KS distance {d:.4g} (scaled {stat:.3g}) against the reference sample"   # 0.1 % level
+    # against the analytic CDF
+    o = np.zeros(5)
+    xs = np.sort(keyed)[:: n // 2000]
+    cdf = np.array([(oracle_lib.fn("inlet_random")(UMean, uRms, float(x), 0.5, dp(o)), o[3])[1] for x in xs])
+    emp = np.searchsorted(np.sort(keyed), xs, side="right") / n
+    assert np.abs(emp - cdf).max() * np.sqrt(n) < 1.95
