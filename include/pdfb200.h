@@ -366,6 +366,13 @@ int64_t pdfb200_kernel_launches(pdfb200_cloud *cloud);
  * [5] time-averaging + number control + step end; out[6] = steps, out[7] =
  * particle-steps processed. reset != 0 clears the accumulators.              */
 int pdfb200_profile(pdfb200_cloud *cloud, double out[8], int reset);
+/* How evolve() issues its steps. A step is about fifty kernels and never waits for the device in its middle (entry
+ * counts, time step and flags stay on the device; the step reports are fetched once per batch of up to 64 steps).
+ * For small clouds - the tutorial cases hold 1e5 particles, a step is then bound by launch overhead - the step is
+ * captured once into a CUDA graph per state-buffer parity and replayed. mode: -1 automatic (graph when the capacity is
+ * at most 4e6 particles, one rank, cell-only sort key; $PDFB200_GRAPH overrides), 0 never, 1 whenever possible.
+ * pdfb200_profile has no per-region times for replayed steps.                                                    */
+int pdfb200_set_graph_mode(pdfb200_cloud *cloud, int mode);
 /* device time (ms) of the last evolve() call, CUDA events on the library's stream */
 double pdfb200_last_evolve_ms(pdfb200_cloud *cloud);
 /* Run-time selection, GPU style (mcModel::New / run-time selection tables, e.g.

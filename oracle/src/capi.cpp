@@ -295,6 +295,7 @@ int pdforacle_upload_moments(pdforacle_cloud *h, const pdfb200_cell_fields *m) {
     if (m->PaNIC) c.PaNIC.assign(m->PaNIC, m->PaNIC + nc);
     ORACLE_CATCH
 }
+int pdforacle_set_graph_mode(pdforacle_cloud *, int) { return PDFB200_OK; }   // nothing to replay on the CPU
 int64_t pdforacle_id_counter(pdforacle_cloud *h) { return (int64_t)h->c.nextId; }
 int pdforacle_set_id_counter(pdforacle_cloud *h, int64_t id) { h->c.nextId = (uint32_t)id; return PDFB200_OK; }
 int64_t pdforacle_step_counter(pdforacle_cloud *h) { return (int64_t)h->c.step; }

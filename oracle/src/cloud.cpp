@@ -230,8 +230,8 @@ bool Cloud::hitPatch(Particle &p, int face) {
 // at the destination. The exit face of a tet is the one with the smallest
 // crossing parameter p_i/(-q_i) among faces with q_i < 0 whose plane lies
 // before the destination (p_i + q_i < 0), excluding the face just entered;
-// ties keep the lower face index. The CUDA kernel evaluates the same
-// expressions in the same order.
+// ties keep the lower face index (two-round tournament, see below). The CUDA
+// kernel evaluates the same expressions in the same order.
 bool Cloud::move(Particle &p, double tdTrackTime) {
     p.keep = true;
     if (p.isOnInletBoundary) {
@@ -262,11 +262,16 @@ bool Cloud::move(Particle &p, double tdTrackTime) {
             pp[3] = 1.0 - ((pp[0] + pp[1]) + pp[2]);
             qq[0] = dotf(T.gradN[0], dx); qq[1] = dotf(T.gradN[1], dx); qq[2] = dotf(T.gradN[2], dx);
             qq[3] = -((qq[0] + qq[1]) + qq[2]);
+            // exit face: a two-round tournament (a against b, c against d, then the winners); a later face wins only
+            // with a strictly smaller crossing parameter p/(-q), compared cross-multiplied. Same result as a scan in
+            // face order wherever the comparison is transitive; the kernel evaluates exactly this.
+            bool cand[4];
+            for (int i = 0; i < 4; ++i) cand[i] = (i != entry) && (qq[i] < 0) && (pp[i] + qq[i] < 0);
+            const int w01 = (cand[1] && (!cand[0] || pp[1] * qq[0] > pp[0] * qq[1])) ? 1 : 0;
+            const int w23 = (cand[3] && (!cand[2] || pp[3] * qq[2] > pp[2] * qq[3])) ? 3 : 2;
+            const bool c01 = cand[0] || cand[1], c23 = cand[2] || cand[3];
             int best = -1;
-            for (int i = 0; i < 4; ++i) {
-                if (i == entry || !(qq[i] < 0) || !(pp[i] + qq[i] < 0)) continue;
-                if (best < 0 || pp[i] * qq[best] > pp[best] * qq[i]) best = i;
-            }
+            if (c01 || c23) best = (c23 && (!c01 || pp[w23] * qq[w01] > pp[w01] * qq[w23])) ? w23 : w01;
             if (best < 0) {          // destination lies in this tet
                 p.position = destPos;
                 tf = 1.0;

@@ -186,7 +186,7 @@ API_SYMBOLS = [
     "upload_cloud_fields", "upload_poscorr_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
-    "kernel_launches", "last_evolve_ms", "profile", "jit_source", "jit_compile", "rng_probe",
+    "kernel_launches", "last_evolve_ms", "profile", "set_graph_mode", "jit_source", "jit_compile", "rng_probe",
 ]
 
 
@@ -231,6 +231,7 @@ class Library:
         f("upload_poscorr_fields").argtypes = [vp, C.POINTER(PoscorrFields)]
         f("step_counter").argtypes = [vp]; f("step_counter").restype = C.c_int64
         f("set_step_counter").argtypes = [vp, C.c_int64]
+        f("set_graph_mode").argtypes = [vp, C.c_int]
         f("id_counter").argtypes = [vp]; f("id_counter").restype = C.c_int64
         f("set_id_counter").argtypes = [vp, C.c_int64]
         f("delta_t").argtypes = [vp]; f("delta_t").restype = C.c_double
@@ -541,6 +542,10 @@ class CloudHandle:
 
     def step_counter(self) -> int:
         return int(self.lib.fn("step_counter")(self.h))
+
+    def set_graph_mode(self, mode: int):
+        """-1 automatic, 0 plain launches, 1 CUDA-graph replay of the step wherever possible (pdfb200_set_graph_mode)"""
+        self.lib.check(self.lib.fn("set_graph_mode")(self.h, int(mode)), "set_graph_mode")
 
     def id_counter(self) -> int:
         return int(self.lib.fn("id_counter")(self.h))

@@ -32,6 +32,9 @@ Cloud::~Cloud() {
     for (void *p : stateAllocs) cudaFree(p);
     if (hScal) cudaFreeHost(hScal);
     if (hFinal) cudaFreeHost(hFinal);
+    if (hRing) cudaFreeHost(hRing);
+    for (auto &e : evMarks) if (e) cudaEventDestroy(e);
+    dropGraphs();
     if (evStart) cudaEventDestroy(evStart);
     if (evStop) cudaEventDestroy(evStop);
     if (evArA) cudaEventDestroy(evArA);
@@ -80,6 +83,7 @@ void Cloud::setParams(const pdfb200_params &p) {
     if (haveCloudFields && p.nPhi != prm.nPhi) throw std::invalid_argument("set_params: nPhi cannot change after the fields were uploaded");
     prm = p;
     dropSpecialisedKernel();
+    dropGraphs();
     prm.C0 = fmax(0.0, prm.C0);                    // mcSLMFullVelocityModel.C:97-98
     prm.C1 = fmax(0.0, fmin(1.0, prm.C1));
     nCov = prm.nPhi * (prm.nPhi + 1) / 2;
@@ -138,6 +142,7 @@ void Cloud::setAutoIgnitionTables(int nZ_, int nPv_, const double *z, const doub
     for (int i = 1; i < nPv_; ++i) if (!(pv[i] - pv[i - 1] > 0)) throw std::invalid_argument("auto-ignition pv not strictly monotonically increasing");
     if (nFields < 2) throw std::invalid_argument("auto-ignition tables: cdot and rho are required");
     nChi = nZ_; nZ = nPv_; nFlFields = nFields; tableKind = 2;
+    dropGraphs();
     cEqMax = cEq[0];
     for (int i = 1; i < nZ_; ++i) cEqMax = std::max(cEqMax, cEq[i]);
     flChi.upload(z, nZ_, stream); flZ.upload(pv, nPv_, stream); flCEq.upload(cEq, nZ_, stream);
@@ -155,6 +160,7 @@ void Cloud::setTables(int nChi_, int nZ_, const double *chi, const double *z, in
     for (int i = 1; i < nChi_; ++i) if (!(chi[i] - chi[i - 1] > 0)) throw std::invalid_argument("flamelet chi not strictly monotonically increasing");
     if (nFields < 1) throw std::invalid_argument("flamelet tables: at least rho is required");
     nChi = nChi_; nZ = nZ_; nFlFields = nFields; tableKind = 1;
+    dropGraphs();
     flChi.upload(chi, nChi, stream); flZ.upload(z, nZ, stream);
     flFields.alloc((size_t)nFields * nChi * nZ);
     for (int f = 0; f < nFields; ++f)
@@ -219,6 +225,7 @@ int pdfb200_upload_moments(pdfb200_cloud *c, const pdfb200_cell_fields *m) {
     USE_DEVICE(c);
     return guarded([&] { H(c)->uploadMoments(*m); });
 }
+int pdfb200_set_graph_mode(pdfb200_cloud *c, int mode) { c->c.graphMode = mode; return PDFB200_OK; }
 int64_t pdfb200_id_counter(pdfb200_cloud *c) {
     USE_DEVICE(c);
     uint32_t v = 0;

@@ -34,6 +34,8 @@ struct HostPatch { int start, size, geom, handler, reflecting; };
 
 // number of doubles in the trailing global section of the moment block
 #define BLOCK_TAIL 32
+// steps issued without a host synchronisation in between (their reports wait in a ring on the device)
+#define REPORT_RING 64
 
 #include "k1_layout.h"
 
@@ -127,6 +129,13 @@ struct Cloud {
     DBuf<double> ncDelta, cloneDelta;   // cloneDelta: [capacity][K1_NC1], axisymmetric cases only
     DBuf<StepScalars> scal;
     StepScalars *hScal = nullptr;     // pinned mirror
+    DBuf<double> reportRing;          // REPORT_RING step reports of 64 doubles (k_report_out)
+    double *hRing = nullptr;          // pinned copy of the ring
+    std::vector<cudaEvent_t> evMarks; // 7 per step of a batch: the regions of pdfb200_profile
+    void *stepGraph[2] = {nullptr, nullptr};        // cudaGraphExec_t of one step, per parity of the state double buffer
+    long long stepGraphLaunches[2] = {0, 0};
+    bool radixPath = false;
+    int graphMode = -1;               // pdfb200_set_graph_mode
     double *hFinal = nullptr;         // pinned reduction results
     int64_t nParticlesHost = 0;       // alive particles after the last step
     int64_t nSlotsHost = 0;           // slots used in the current buffer (upper bound for launches)
@@ -165,6 +174,8 @@ struct Cloud {
     void uploadParticles(int64_t n, const pdfb200_particles &p);
     void downloadParticles(int64_t maxn, pdfb200_particles &out, int64_t *n);
     void evolve(int nSteps, pdfb200_step_report *reports);
+    void enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t *ev);
+    void dropGraphs();
     void downloadCellFields(pdfb200_cell_fields &o);
     void commInit(int nRanks, int rank, const char id[128]);
 

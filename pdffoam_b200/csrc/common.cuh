@@ -116,6 +116,8 @@ struct StepScalars {
     int nTail;              // appended after the sort (clones, then injected)
     int nInjStart;          // tail index where this step's injected particles start
     int nSlots;             // slots in use in the current state buffer
+    int nEntries;           // entries of the running step (nSorted + nTail after injection): set by k_step_begin
+    int ringIdx;            // slot of the report ring the running step writes (k_step_end advances it)
     int anyLost;            // lost mass to redistribute at the next K1
     uint32_t nextId;
     int overflow;           // capacity exceeded

@@ -353,6 +353,10 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 4
 #endif
+// 1: the walk keeps the start point relative to the cell centre (r) instead of the centre itself (measured: profiles/README.md)
+#ifndef K1_TRACK_R
+#define K1_TRACK_R 1
+#endif
 // dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
 // (the correction velocity and the Courant number, which must survive the tet walks without occupying registers)
 #define K1_NPARK 4
@@ -567,26 +571,31 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     dx = dest - pos;
                 }
                 double tf = 1.0;
+                // start point relative to the centre of the current cell: constant along the sub-step until the walk
+                // changes cell; the centre itself is not kept through the loop (read again after it)
+                V3 r = pos - ctr;
                 for (;;) {
-                    const V3 r = pos - ctr;
+#if !K1_TRACK_R
+                    r = pos - ctr;
+#endif
                     double p0, p1, p2, p3;
                     baryAt(T, r, p0, p1, p2, p3);
                     const double q0 = dotf(T.g0, T.g1, T.g2, dx), q1 = dotf(T.g3, T.g4, T.g5, dx), q2 = dotf(T.g6, T.g7, T.g8, dx);
                     const double q3 = -((q0 + q1) + q2);
-                    // exit face: sequential scan a,b,c,d written with selects (no branches);
-                    // candidate i: not the entry face, moving towards it, and its plane lies before dest
+                    // exit face: two-round tournament written with selects (no branches) - a against b, c against d, then
+                    // the winners; a later face wins only with a strictly smaller crossing parameter p/(-q), compared
+                    // cross-multiplied (oracle Cloud::move: the same expressions). Candidate i: not the entry face, moving
+                    // towards it, and its plane lies before dest
                     const bool c0 = (entry != 0) & (q0 < 0) & (p0 + q0 < 0);
                     const bool c1 = (entry != 1) & (q1 < 0) & (p1 + q1 < 0);
                     const bool c2 = (entry != 2) & (q2 < 0) & (p2 + q2 < 0);
                     const bool c3 = (entry != 3) & (q3 < 0) & (p3 + q3 < 0);
-                    int best = c0 ? 0 : -1;
-                    double pb = c0 ? p0 : 0.0, qb = c0 ? q0 : 0.0;
-                    const bool t1 = c1 & ((best < 0) | (p1 * qb > pb * q1));
-                    best = t1 ? 1 : best; pb = t1 ? p1 : pb; qb = t1 ? q1 : qb;
-                    const bool t2 = c2 & ((best < 0) | (p2 * qb > pb * q2));
-                    best = t2 ? 2 : best; pb = t2 ? p2 : pb; qb = t2 ? q2 : qb;
-                    const bool t3 = c3 & ((best < 0) | (p3 * qb > pb * q3));
-                    best = t3 ? 3 : best;
+                    const bool w1 = c1 & (!c0 | (p1 * q0 > p0 * q1));
+                    const bool w3 = c3 & (!c2 | (p3 * q2 > p2 * q3));
+                    const double pA = w1 ? p1 : p0, qA = w1 ? q1 : q0, pB = w3 ? p3 : p2, qB = w3 ? q3 : q2;
+                    const bool cA = c0 | c1, cB = c2 | c3;
+                    const bool wB = cB & (!cA | (pB * qA > pA * qB));
+                    const int best = (cA | cB) ? (wB ? (w3 ? 3 : 2) : (w1 ? 1 : 0)) : -1;
                     if (best < 0) {
                         // the destination is recomputed (same expression, same bits) instead of kept in registers
                         V3 dest = pos + dt * Utrack;
@@ -603,7 +612,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         tet = (best == 3) ? T.n3 : nb;
                         // across the mesh face: the cell changes, and with it the centre the tets hang on
                         // (requested together with the next record, not after it)
+#if K1_TRACK_R
+                        if (best == 3) { cell = T.nbrCell; r = pos - cellCentre(M, cell); }
+#else
                         if (best == 3) { cell = T.nbrCell; ctr = cellCentre(M, cell); }
+#endif
                         loadTet(M, tet, T);
                         entry = best ^ (((best == 1) | (best == 2)) ? 3 : 0);   // the shared face is opposite c (b) in the tet across b (c)
                         continue;
@@ -674,6 +687,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 }
                 dt *= tf;
                 tEnd -= dt;
+#if K1_TRACK_R
+                ctr = cellCentre(M, cell);
+#endif
             }
             if (status != 0) break;
             if (phase == 1) break;

@@ -449,6 +449,7 @@ static void uploadFlags(DBuf<uint8_t> &d, const uint8_t *h, size_t n, cudaStream
 }
 
 void Cloud::uploadFv(const pdfb200_fv_fields &f) {
+    dropGraphs();
     if (!f.U || !f.Ub || !f.p || !f.pb || !f.k || !f.kb || !f.epsilon || !f.epsilonb || !f.R || !f.Rb)
         throw std::runtime_error("upload_fv_fields: null field pointer");
     cudaStream_t s = stream;
@@ -494,9 +495,11 @@ void Cloud::commitFv() {
     swapBuf(R_c, stg_R_c); swapBuf(R_b, stg_R_b); swapBuf(UbFixed, stg_UbFixed); swapBuf(kbFixed, stg_kbFixed);
     stagedPending = false;
     haveFv = true;
+    dropGraphs();   // the captured steps hold the old pointers
 }
 
 void Cloud::uploadCloudFields(const pdfb200_cloud_fields &f) {
+    dropGraphs();
     if (!f.rho || !f.rhob) throw std::runtime_error("upload_cloud_fields: rho missing");
     cudaStream_t s = stream;
     const size_t nc = nCells, nb = nBnd;
@@ -524,6 +527,7 @@ void Cloud::uploadCloudFields(const pdfb200_cloud_fields &f) {
 }
 
 void Cloud::initMoments() {
+    dropGraphs();
     if (!haveFv || !haveCloudFields) throw std::logic_error("init_moments: upload the FV and cloud fields first");
     const size_t nc = nCells, nb = nBnd;
     const int nPhi = std::max(prm.nPhi, 1), nC = std::max(nCov, 1);
@@ -598,6 +602,7 @@ void Cloud::downloadCellFields(pdfb200_cell_fields &o) {
 
 // fields of an externally solved position correction (pdfb200_poscorr_fields): packed into rows of 12
 void Cloud::uploadPoscorr(const pdfb200_poscorr_fields &f) {
+    dropGraphs();
     const size_t nc = nCells, nb = nBnd;
     std::vector<double> hc(nc * 12, 0.0), hb(std::max<size_t>(nb, 1) * 12, 0.0);
     auto put = [&](const double *cv, const double *bv, int off, int width) {

@@ -150,28 +150,36 @@ __global__ void k_cell_bounds(int n, const uint32_t *keys, int tetBits, const in
 // ---------------------------------------------------------------------------
 // (forms the key — the rank of the particle's new cell in the processing order — from the state the particle
 // kernel has just written, and keeps it for the scatter)
-__global__ void k_cs_hist(int n, const int *cell, const int *cellRank, uint32_t *keys, int *count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t key = KEY_DEAD;
-    if (i < n) {
-        const int c = cell[i];
-        if (c >= 0) key = (uint32_t)__ldg(cellRank + c);
-        keys[i] = key;
+// (the entry count is read on the device - no host round trip in the middle of a step; the trip count of the
+// grid-stride loop is uniform per CTA, so every warp enters the match with all its lanes)
+__global__ void k_cs_hist(const StepScalars *sc, const int *cell, const int *cellRank, uint32_t *keys, int *count) {
+    const int n = sc->nEntries;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        uint32_t key = KEY_DEAD;
+        if (i < n) {
+            const int c = cell[i];
+            if (c >= 0) key = (uint32_t)__ldg(cellRank + c);
+            keys[i] = key;
+        }
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (key != KEY_DEAD && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(count + key, __popc(m));
     }
-    const unsigned m = __match_any_sync(0xffffffffu, key);
-    if (key != KEY_DEAD && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(count + key, __popc(m));
 }
 
-__global__ void k_cs_scatter(int n, const uint32_t *keys, const int *cellStart, int *cursor, uint32_t *perm) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_cs_scatter(const StepScalars *sc, const uint32_t *keys, const int *cellStart, int *cursor, uint32_t *perm) {
+    const int n = sc->nEntries;
     const int lane = threadIdx.x & 31;
-    const uint32_t key = i < n ? keys[i] : KEY_DEAD;
-    const unsigned m = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (key != KEY_DEAD && lane == leader) base = atomicAdd(cursor + key, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (key != KEY_DEAD) perm[cellStart[key] + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    for (int base0 = blockIdx.x * blockDim.x; base0 < n; base0 += gridDim.x * blockDim.x) {
+        const int i = base0 + threadIdx.x;
+        const uint32_t key = i < n ? keys[i] : KEY_DEAD;
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (key != KEY_DEAD && lane == leader) base = atomicAdd(cursor + key, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key != KEY_DEAD) perm[cellStart[key] + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
 }
 
 // bitonic sort of 32*K values held K per lane (element index = k*32 + lane), ascending
@@ -1005,7 +1013,16 @@ struct DevReport {
 #define RP_LOSTSUM (RP_INJ + K1_NC1)     // K1_NC1: lost mass re-spread, per depth, x {1, conserved scalars}
 #define RP_CLONEDELTA (RP_LOSTSUM + K1_NC1)   // K1_NC1: axisymmetric mass-per-depth change of the clones
 #define RP_MIXDELTA (RP_CLONEDELTA + K1_NC1)   // K1_MAXCONS: change of the conserved-scalar balance by pair mixing
-#define RP_END (RP_MIXDELTA + K1_MAXCONS)
+#define RP_STEP (RP_MIXDELTA + K1_MAXCONS)     // 8: what the host used to read from StepScalars in the middle of the step
+#define RP_DT_USED (RP_STEP + 0)
+#define RP_DT_NEXT (RP_STEP + 1)
+#define RP_N_ENTRIES (RP_STEP + 2)
+#define RP_N_INJECTED (RP_STEP + 3)
+#define RP_N_SORTED (RP_STEP + 4)              // alive after the sort
+#define RP_N_CLONED (RP_STEP + 5)
+#define RP_N_ELIMINATED (RP_STEP + 6)
+#define RP_OVERFLOW (RP_STEP + 7)
+#define RP_END (RP_STEP + 8)
 static_assert(RP_END <= 64, "DevReport too small");
 
 // Lost particles (mcParticleCloud.C:1257-1260,1346-1351, notifyLostParticle :2088-2092): the particle
@@ -1094,17 +1111,32 @@ __global__ void k_colsum_nc1(int n, const double *in, double *partial, const int
         for (int k = 0; k < K1_NC1; ++k) partial[blockIdx.x * K1_NC1 + k] = v[k];
 }
 
-__global__ void k_set_slots(StepScalars *sc, int total) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSlots = total;
+__global__ void k_set_slots(StepScalars *sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSlots = sc->nEntries;
+}
+
+// after the injection: the entry count of the step, kept on the device for every later kernel; also empties the list
+// of lost particles and notes what the report needs from the state at this point
+__global__ void k_step_begin(StepScalars *sc, DevReport *rp, unsigned *lostCount) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    sc->nEntries = sc->nSorted + sc->nTail;
+    *lostCount = 0u;
+    rp->v[RP_DT_USED] = sc->deltaT;
+    rp->v[RP_N_ENTRIES] = (double)sc->nEntries;
+    rp->v[RP_N_INJECTED] = (double)(sc->nTail - sc->nInjStart);
 }
 
 __global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int nTailClones, const int *ncCounts,
-                           int total, int nRanksForId) {
+                           int nRanksForId) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double CoMax = rp->v[RP_K1MAX + ACC_COMAX];
     if (CoMax > 0) sc->deltaT = P.CFL / CoMax;
     sc->step += 1;
-    sc->nSlots = total;
+    sc->nSlots = sc->nEntries;
+    rp->v[RP_DT_NEXT] = sc->deltaT;
+    rp->v[RP_N_SORTED] = (double)sc->nSorted;
+    rp->v[RP_N_CLONED] = ncCounts ? (double)ncCounts[0] : 0.0;
+    rp->v[RP_N_ELIMINATED] = ncCounts ? (double)ncCounts[1] : 0.0;
     const int nCl = ncCounts ? ncCounts[0] : 0;
     sc->nTail = nCl;
     sc->nInjStart = nCl;
@@ -1112,6 +1144,16 @@ __global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int
     sc->nextId += (uint32_t)nCl * (uint32_t)nRanksForId;
     sc->anyLost = rp->v[RP_K1SUM + ACC_N_LOST] > 0 ? 1 : 0;
     sc->nLostTotal += (long long)rp->v[RP_K1SUM + ACC_N_LOST];
+}
+
+// last kernel of a step: the finished report goes into its slot of the ring that the host reads once per batch of steps
+__global__ void k_report_out(StepScalars *sc, DevReport *rp, DevReport *ring, int ringSize) {
+    const int slot = sc->ringIdx % ringSize;
+    if (threadIdx.x == 0) rp->v[RP_OVERFLOW] = (double)sc->overflow;
+    __syncthreads();
+    if (threadIdx.x < 64) ring[slot].v[threadIdx.x] = rp->v[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) sc->ringIdx = sc->ringIdx + 1;
 }
 
 __global__ void k_rng_probe(RngKey key, int n, const uint64_t *entity, uint32_t step, uint32_t purpose, uint32_t sub, double *out6) {
@@ -1201,10 +1243,22 @@ void Cloud::allocParticles() {
     cellPartSum.alloc((size_t)maxGrid * 8); finalSums.alloc(256);
     const size_t lostCap = (size_t)std::min<int64_t>(capacity, 65536);
     lostList.alloc(lostCap); lostSorted.alloc(lostCap); lostCount.alloc(1); lostCount.zero(stream);
+    // nothing may be allocated while a step is being captured into a graph: scan scratch for the largest scan up front
+    {
+        const int nTiles = (std::max(nCells, nBnd) + SCAN_TILE - 1) / SCAN_TILE + 1;
+        scanTileSums.alloc(nTiles); scanTileOffs.alloc(nTiles);
+    }
+    reportRing.alloc((size_t)REPORT_RING * 64);
+    if (!hRing) CUDA_CHECK(cudaMallocHost((void **)&hRing, (size_t)REPORT_RING * 64 * sizeof(double)));
+    if (evMarks.empty()) {
+        evMarks.resize((size_t)REPORT_RING * 7);
+        for (auto &e : evMarks) CUDA_CHECK(cudaEventCreate(&e));
+    }
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 void Cloud::seedParticles() {
+    dropGraphs();
     if (!haveMoments) throw std::logic_error("seed_particles: init_moments first");
     requireTables();
     allocParticles();
@@ -1241,6 +1295,7 @@ __global__ void k_default_ids(int n, uint32_t *id, int rank, int nRanks) {
 }
 
 void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
+    dropGraphs();
     allocParticles();
     if (n > capacity) throw std::length_error("upload_particles: capacity too small");
     if (!p.pos || !p.U || !p.m || !p.Omega || !p.rho || !p.eta || !p.cell) throw std::invalid_argument("upload_particles: null column");
@@ -1366,13 +1421,187 @@ static void launchMoments(Cloud &c, const PState &S, const uint32_t *perm) {
     LAUNCH(&c, k_moments<N>, G, B, 0, c.dm, S, perm, c.cellStart.p, c.cellEnd.p, c.momentBlock.p, c.nMom);
 }
 
+// Everything one step launches, in order, on the library's stream. Nothing in here waits for the device or reads a
+// device value on the host (entry counts, time step, overflow flags all stay on the device; the step's report goes
+// into a ring, see evolve()), so a step can be issued behind the previous one - and captured into a CUDA graph.
+// `ev`: seven events that bracket the six regions of pdfb200_profile, or nullptr (graph capture).
+void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t *ev) {
+    const RngKey key = makeKey(prm.seed);
+    DevReport *dRep = reinterpret_cast<DevReport *>(finalSums.p + 128);
+    DevReport *dRing = reinterpret_cast<DevReport *>(reportRing.p);
+    auto mark = [&](int r) { if (ev) CUDA_CHECK(cudaEventRecord(ev[r], stream)); };
+    void (*k1)(const K1Args) = prm.nPhi <= 1 ? k_evolve<1> : prm.nPhi == 2 ? k_evolve<2> : prm.nPhi == 3 ? k_evolve<3> : k_evolve<PDFB200_MAX_PHI>;
+    const long long cap = capacity;
+
+    // ---- cell-side preparation (all updateInternals) ----
+    mark(0);
+    prepareFields();
+    if (hasOpen) LAUNCH(this, k_open_un, gridFor(nBnd, 128), 128, 0, dm, Ufv_b.p, Un.p);
+    if (hasInlet) {
+        if (!inletCached) {
+            LAUNCH(this, k_inlet_cache, gridFor(nBnd, 128), 128, 0, dm, prm.k0, Ufv_b.p, Tau_b.p, fwdTrans.p, probVec.p, inletU.p, inletR.p);
+            inletCached = true;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            LAUNCH(this, k_inject, std::min(gridFor((long long)nBnd * 32, 128), numSMs * 16), 128, 0, dm, prm, pass, S[cur], key, scal.p, Un.p, rho_b.p, Phi_b.p, inletU.p,
+                   inletR.p, fwdTrans.p, probVec.p, nodeMid.p, injCount.p, injOffset.p, injPatchTail.p, injSums.p, nRanks, rank, cap);
+            if (pass == 0) scanInts(*this, nBnd, injCount.p, injOffset.p, scanTmp.p);
+        }
+        LAUNCH(this, k_inject_finish, 1, 32, 0, nBnd, scanTmp.p, scal.p, cap, nRanks);
+        const int gI = std::min(gridFor(nBnd, 256), numSMs * 2);
+        LAUNCH(this, k_colsum_nc1, gI, 256, 0, nBnd, injSums.p, k1PartSum.p);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_INJ, 0, K1_NC1 * sizeof(double), stream));
+    }
+    // entry count of the step (device side), empty lost-particle list
+    LAUNCH(this, k_step_begin, 1, 32, 0, scal.p, dRep, lostCount.p);
+
+    // ---- the fused particle kernel: persistent grid, the kernel reads the entry count itself ----
+    K1Args A;
+    A.M = dm; A.P = prm; A.in = S[cur]; A.out = S[cur ^ 1];
+    A.perm = valsB.p; A.sc = scal.p;
+    A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride; A.pcScale = pcScale;
+    A.Un = Un.p; A.lostShare = lostShare.p; A.lostList = lostList.p; A.lostCount = lostCount.p; A.lostCap = (unsigned)lostList.n;
+    A.injPatchTail = injPatchTail.p;
+    A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ; A.flCEq = flCEq.p; A.cEqMax = cEqMax;
+    A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
+    const int gridK1 = (int)std::max<long long>(1, std::min<long long>(gridFor(cap, K1_THREADS), (long long)numSMs * k1Blocks));
+    // the lost mass of the previous step has been handed out (lostShare): its cells start empty again
+    CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
+    mark(1);
+    if (k1Jit) {
+        void *kargs[] = {&A};
+        CUDA_CHECK(cudaLaunchKernel(k1Jit, dim3(gridK1), dim3(K1_THREADS), kargs, k1JitSmem, stream));
+        ++launches;
+    } else {
+        LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
+    }
+    mark(2);
+    LAUNCH(this, k_lost_reduce, 1, 1024, 0, lostList.p, lostSorted.p, lostCount.p, (unsigned)lostList.n, lostMass.p, scal.p);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
+    cur ^= 1;
+
+    // ---- sort by cell + segment bounds ----
+    if (!radixPath) {
+        // counting sort by cell (see k_cs_*): same permutation as the stable radix sort
+        CUDA_CHECK(cudaMemsetAsync(csCount.p, 0, nCells * sizeof(int), stream));
+        CUDA_CHECK(cudaMemsetAsync(csCursor.p, 0, nCells * sizeof(int), stream));
+        const int gS = std::min(gridFor(cap, 256), numSMs * 16);
+        LAUNCH(this, k_cs_hist, gS, 256, 0, scal.p, S[cur].cell, cellRank.p, keysA.p, csCount.p);
+        scanInts(*this, nCells, csCount.p, csStart.p, scanTmp.p + 2);
+        LAUNCH(this, k_cs_scatter, gS, 256, 0, scal.p, keysA.p, csStart.p, csCursor.p, valsB.p);
+        mark(3);
+        LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, csStart.p, csCount.p, cellOfRank.p, cellStart.p,
+               cellEnd.p, valsB.p, keysB.p);
+        LAUNCH(this, k_cs_finish, 1, 32, 0, scanTmp.p + 2, scal.p);
+    } else {
+        // radix sort by (cell, tet): the library call needs the entry count on the host, so this path waits for it
+        // (cells of 256 and more particles per rank only; evolve() issues one step per batch here)
+        CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        const int total = hScal->nEntries;
+        size_t tempBytes = cubTemp.n;
+        if (total > 0) {
+            LAUNCH(this, k_make_keys, gridFor(total, 256), 256, 0, dm, total, S[cur].cell, S[cur].tet, keysA.p);
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
+        }
+        mark(3);
+        CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
+        CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
+        if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellOfRank.p, cellStart.p, cellEnd.p, scal.p);
+        else CUDA_CHECK(cudaMemsetAsync(&scal.p->nSorted, 0, sizeof(int), stream));
+    }
+    // "modifiedCurl" pair mixing on the sorted order, before the moments are taken
+    if (prm.mixingModel == PDFB200_MIXING_MODCURL && prm.nMixed > 0) {
+        const int gM = std::min(gridFor(nCells, MIX_WARPS), numSMs * 8);
+        LAUNCH(this, k_mix_curl, gM, MIX_WARPS * 32, 0, dm, prm, S[cur], valsB.p,
+               cellStart.p, cellEnd.p, scal.p, key, keysA.p, valsA.p, cellPartSum.p);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gM, K1_MAXCONS, cellPartSum.p, dRep->v + RP_MIXDELTA, 0);
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_MIXDELTA, 0, K1_MAXCONS * sizeof(double), stream));
+    }
+    switch (prm.nPhi) {
+    case 0: launchMoments<0>(*this, S[cur], valsB.p); break;
+    case 1: launchMoments<1>(*this, S[cur], valsB.p); break;
+    case 2: launchMoments<2>(*this, S[cur], valsB.p); break;
+    case 3: launchMoments<3>(*this, S[cur], valsB.p); break;
+    case 4: launchMoments<4>(*this, S[cur], valsB.p); break;
+    case 5: launchMoments<5>(*this, S[cur], valsB.p); break;
+    default: launchMoments<6>(*this, S[cur], valsB.p); break;
+    }
+    mark(4);
+    // ---- cross-GPU sum of the moment block ----
+    float arMs = 0;
+    if (nRanks > 1) commAllreduceMoments(*this, &arMs);
+    mark(5);
+
+    // ---- time-averaging, mean fields, boundary conditions ----
+    const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
+    fieldsFinalise(*this, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, gF);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
+
+    // ---- particle-number control ----
+    CUDA_CHECK(cudaMemsetAsync(ncCounts.p, 0, 2 * sizeof(int), stream));
+    const bool nc = prm.particleNumberControl != 0;
+    if (nc) {
+        CUDA_CHECK(cudaMemsetAsync(scanTmp.p + 3, 0, sizeof(int), stream));
+        LAUNCH(this, k_nc_classify, gridFor(nCells, 256), 256, 0, dm, prm, PaNIC.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, nRanks,
+               csCursor.p, scanTmp.p + 3);
+        scanInts(*this, nCells, ncCount.p, ncOffset.p, scanTmp.p + 1);
+        CUDA_CHECK(cudaMemsetAsync(ncDelta.p, 0, (size_t)nCells * K1_NC1 * sizeof(double), stream));
+        // nSlots for the clones = this step's entry count
+        LAUNCH(this, k_set_slots, 1, 32, 0, scal.p);
+        const int gN = std::min(gridFor(nCells, 8), numSMs * 16);
+        LAUNCH(this, k_nc_apply, gN, 256, 0, dm, prm, S[cur], valsB.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, ncOffset.p,
+               PaNIC.p, scal.p, key, rank, nRanks, cap, ncDelta.p, ncCounts.p, keysA.p, csCursor.p, scanTmp.p + 3);
+        // the clones: one thread per task (scanTmp[1] = number of tasks); keysA is free until the next step
+        LAUNCH(this, k_nc_clone, numSMs * 8, 128, 0, dm, prm, S[cur], keysA.p, scanTmp.p + 1, scal.p, key, nRanks, cap,
+               cloneDelta.p);
+        // fold ncDelta over cells deterministically: per-CTA partials, then rows
+        const int gR = std::min(gridFor(nCells, 256), numSMs * 4);
+        LAUNCH(this, k_colsum_nc1, gR, 256, 0, nCells, ncDelta.p, k1PartSum.p);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
+        if (axisym) {
+            LAUNCH(this, k_colsum_nc1, gR, 256, 0, 0, cloneDelta.p, k1PartSum.p, scanTmp.p + 1);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_CLONEDELTA, 0);
+        } else {
+            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
+        }
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_NCDELTA, 0, K1_NC1 * sizeof(double), stream));
+        CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
+    }
+    // ---- lost mass shares ----
+    {
+        const int gL = std::min(gridFor(nCells, 256), numSMs * 4);
+        LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, momentBlock.p, nMom, lostShare.p);
+    }
+    LAUNCH(this, k_step_end, 1, 32, 0, scal.p, dRep, prm, 0, nc ? ncCounts.p : nullptr, nRanks);
+    {
+        // after k_step_end: nSorted / nTail / nSlots describe the particles the next step starts from
+        const int gB = numSMs * 4;
+        LAUNCH(this, k_lost_balance, gB, 256, 0, dm, prm, S[cur], valsB.p, scal.p, lostCount.p, lostShare.p, k1PartSum.p);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gB, K1_NC1, k1PartSum.p, dRep->v + RP_LOSTSUM, 0);
+    }
+    LAUNCH(this, k_report_out, 1, 64, 0, scal.p, dRep, dRing, REPORT_RING);
+    mark(6);
+}
+
+void Cloud::dropGraphs() {
+    for (auto &g : stepGraph) { if (g) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(g)); g = nullptr; }
+}
+
 void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     if (!haveMoments) throw std::logic_error("evolve: fields/moments not initialised");
     if (stateAllocs.empty()) throw std::logic_error("evolve: no particles (seed_particles or upload_particles first)");
     if (prm.nConserved > K1_MAXCONS) throw std::invalid_argument("evolve: at most 3 conserved scalars are supported");
     requireTables();
-    const RngKey key = makeKey(prm.seed);
-    DevReport *dRep = reinterpret_cast<DevReport *>(finalSums.p + 128);
+    if (prm.positionCorrection == PDFB200_POSCORR_EXTERNAL && !havePcExt)
+        throw std::logic_error("evolve: positionCorrection external selected but no fields uploaded (upload_poscorr_fields)");
+    if (nSteps <= 0) return;
     CUDA_CHECK(cudaEventRecord(evStart, stream));
     int k1Blocks = 0;
     // the scalars live in registers: instantiate the kernel for nPhi <= 1, 2, 3 and the general bound
@@ -1387,218 +1616,105 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         if (const char *x = std::getenv("PDFB200_K1_BLOCKS")) k1Blocks = std::max(1, std::atoi(x));   // with -DK1_MIN_BLOCKS in PDFB200_JIT_FLAGS
         if (const char *x = std::getenv("PDFB200_K1_SMEM")) k1JitSmem = (size_t)std::atol(x);          // with flags that change K1_SMEM_BYTES
     }
-    auto mark = [&](int r) { CUDA_CHECK(cudaEventRecord(evMark[r], stream)); };
+    static const bool forceRadix = [] { const char *e = std::getenv("PDFB200_SORT"); return e && std::string(e) == "radix"; }();
+    radixPath = tetBits != 0 || forceRadix;
+    if (prm.mixingModel == PDFB200_MIXING_MODCURL && valsA.n < (size_t)capacity) valsA.alloc(capacity);
 
-    for (int st = 0; st < nSteps; ++st) {
-        // ---- cell-side preparation (all updateInternals) ----
-        mark(0);
-        prepareFields();
-        int nInjected = 0;
-        if (hasOpen) LAUNCH(this, k_open_un, gridFor(nBnd, 128), 128, 0, dm, Ufv_b.p, Un.p);
-        if (hasInlet) {
-            if (!inletCached) {
-                LAUNCH(this, k_inlet_cache, gridFor(nBnd, 128), 128, 0, dm, prm.k0, Ufv_b.p, Tau_b.p, fwdTrans.p, probVec.p, inletU.p, inletR.p);
-                inletCached = true;
-            }
-            for (int pass = 0; pass < 2; ++pass) {
-                LAUNCH(this, k_inject, std::min(gridFor((long long)nBnd * 32, 128), numSMs * 16), 128, 0, dm, prm, pass, S[cur], key, scal.p, Un.p, rho_b.p, Phi_b.p, inletU.p,
-                       inletR.p, fwdTrans.p, probVec.p, nodeMid.p, injCount.p, injOffset.p, injPatchTail.p, injSums.p, nRanks, rank,
-                       (long long)capacity);
-                if (pass == 0) scanInts(*this, nBnd, injCount.p, injOffset.p, scanTmp.p);
-            }
-            LAUNCH(this, k_inject_finish, 1, 32, 0, nBnd, scanTmp.p, scal.p, (long long)capacity, nRanks);
-            const int gI = std::min(gridFor(nBnd, 256), numSMs * 2);
-            LAUNCH(this, k_colsum_nc1, gI, 256, 0, nBnd, injSums.p, k1PartSum.p);
-            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
-        } else {
-            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_INJ, 0, K1_NC1 * sizeof(double), stream));
-        }
-        // the host needs the entry count to size the sort
-        CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        if (hScal->overflow == 3) throw std::runtime_error("evolve: the 32-bit particle id space is exhausted");
-        if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
-        const int nSorted = hScal->nSorted, nTail = hScal->nTail;
-        const int total = nSorted + nTail;
-        nInjected = nTail - hScal->nInjStart;
-        if (total > capacity) throw std::length_error("evolve: particle capacity exceeded");
-        const double dtUsed = hScal->deltaT;
-
-        // ---- the fused particle kernel ----
-        K1Args A;
-        A.M = dm; A.P = prm; A.in = S[cur]; A.out = S[cur ^ 1];
-        A.perm = valsB.p; A.sc = scal.p;
-        A.nodeMid = nodeMid.p; A.nodePC = nodePC.p; A.cellAux = cellAux.p; A.auxStride = cellAuxStride; A.pcScale = pcScale;
-        A.Un = Un.p; A.lostShare = lostShare.p; A.lostList = lostList.p; A.lostCount = lostCount.p; A.lostCap = (unsigned)lostList.n;
-        A.injPatchTail = injPatchTail.p;
-        A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ; A.flCEq = flCEq.p; A.cEqMax = cEqMax;
-        A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
-        const int gridK1 = std::max(1, std::min(gridFor(total, K1_THREADS), numSMs * k1Blocks));
-        // lost-particle bookkeeping of this step starts empty; the cells are only touched when the previous step
-        // left something in them
-        if (lostDirty) { CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream)); lostDirty = false; }
-        CUDA_CHECK(cudaMemsetAsync(lostCount.p, 0, sizeof(unsigned), stream));
-        mark(1);
-        if (k1Jit) {
-            void *kargs[] = {&A};
-            CUDA_CHECK(cudaLaunchKernel(k1Jit, dim3(gridK1), dim3(K1_THREADS), kargs, k1JitSmem, stream));
-            ++launches;
-        } else {
-            LAUNCH(this, k1, gridK1, K1_THREADS, K1_SMEM_BYTES, A);
-        }
-        mark(2);
-        LAUNCH(this, k_lost_reduce, 1, 1024, 0, lostList.p, lostSorted.p, lostCount.p, (unsigned)lostList.n, lostMass.p, scal.p);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
-        cur ^= 1;
-
-        // ---- sort by cell + segment bounds ----
-        static const bool forceRadix = [] { const char *e = std::getenv("PDFB200_SORT"); return e && std::string(e) == "radix"; }();
-        if (tetBits == 0 && !forceRadix) {
-            // counting sort by cell (see k_cs_*): same permutation as the stable radix sort
-            CUDA_CHECK(cudaMemsetAsync(csCount.p, 0, nCells * sizeof(int), stream));
-            CUDA_CHECK(cudaMemsetAsync(csCursor.p, 0, nCells * sizeof(int), stream));
-            if (total > 0) LAUNCH(this, k_cs_hist, gridFor(total, 256), 256, 0, total, S[cur].cell, cellRank.p, keysA.p, csCount.p);
-            scanInts(*this, nCells, csCount.p, csStart.p, scanTmp.p + 2);
-            if (total > 0) LAUNCH(this, k_cs_scatter, gridFor(total, 256), 256, 0, total, keysA.p, csStart.p, csCursor.p, valsB.p);
-            mark(3);
-            LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, csStart.p, csCount.p, cellOfRank.p, cellStart.p,
-                   cellEnd.p, valsB.p, keysB.p);
-            LAUNCH(this, k_cs_finish, 1, 32, 0, scanTmp.p + 2, scal.p);
-        } else {
-            // radix sort by (cell, tet)
-            size_t tempBytes = cubTemp.n;
-            if (total > 0) {
-                LAUNCH(this, k_make_keys, gridFor(total, 256), 256, 0, dm, total, S[cur].cell, S[cur].tet, keysA.p);
-                CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp.p, tempBytes, keysA.p, keysB.p, iota.p, valsB.p, total, 0, keyBits + 1, stream));
-            }
-            mark(3);
-            CUDA_CHECK(cudaMemsetAsync(cellStart.p, 0, nCells * sizeof(int), stream));
-            CUDA_CHECK(cudaMemsetAsync(cellEnd.p, 0, nCells * sizeof(int), stream));
-            if (total > 0) LAUNCH(this, k_cell_bounds, gridFor(total, 256), 256, 0, total, keysB.p, tetBits, cellOfRank.p, cellStart.p, cellEnd.p, scal.p);
-            else { hScal->nSorted = 0; }
-        }
-        // "modifiedCurl" pair mixing on the sorted order, before the moments are taken
-        if (prm.mixingModel == PDFB200_MIXING_MODCURL && prm.nMixed > 0 && total > 0) {
-            if (valsA.n < (size_t)capacity) valsA.alloc(capacity);
-            const int gM = std::min(gridFor(nCells, MIX_WARPS), numSMs * 8);
-            LAUNCH(this, k_mix_curl, gM, MIX_WARPS * 32, 0, dm, prm, S[cur], valsB.p,
-                   cellStart.p, cellEnd.p, scal.p, key, keysA.p, valsA.p, cellPartSum.p);
-            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gM, K1_MAXCONS, cellPartSum.p, dRep->v + RP_MIXDELTA, 0);
-        } else {
-            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_MIXDELTA, 0, K1_MAXCONS * sizeof(double), stream));
-        }
-        switch (prm.nPhi) {
-        case 0: launchMoments<0>(*this, S[cur], valsB.p); break;
-        case 1: launchMoments<1>(*this, S[cur], valsB.p); break;
-        case 2: launchMoments<2>(*this, S[cur], valsB.p); break;
-        case 3: launchMoments<3>(*this, S[cur], valsB.p); break;
-        case 4: launchMoments<4>(*this, S[cur], valsB.p); break;
-        case 5: launchMoments<5>(*this, S[cur], valsB.p); break;
-        default: launchMoments<6>(*this, S[cur], valsB.p); break;
-        }
-        mark(4);
-        // ---- cross-GPU sum of the moment block ----
-        float arMs = 0;
-        if (nRanks > 1) commAllreduceMoments(*this, &arMs);
-        mark(5);
-
-        // ---- time-averaging, mean fields, boundary conditions ----
-        const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
-        fieldsFinalise(*this, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, gF);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
-
-        // ---- particle-number control ----
-        CUDA_CHECK(cudaMemsetAsync(ncCounts.p, 0, 2 * sizeof(int), stream));
-        const bool nc = prm.particleNumberControl != 0;
-        if (nc) {
-            CUDA_CHECK(cudaMemsetAsync(scanTmp.p + 3, 0, sizeof(int), stream));
-            LAUNCH(this, k_nc_classify, gridFor(nCells, 256), 256, 0, dm, prm, PaNIC.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, nRanks,
-                   csCursor.p, scanTmp.p + 3);
-            scanInts(*this, nCells, ncCount.p, ncOffset.p, scanTmp.p + 1);
-            CUDA_CHECK(cudaMemsetAsync(ncDelta.p, 0, (size_t)nCells * K1_NC1 * sizeof(double), stream));
-            // nSlots for the clones = this step's entry count
-            LAUNCH(this, k_set_slots, 1, 32, 0, scal.p, total);
-            const int gN = std::min(gridFor(nCells, 8), numSMs * 16);
-            LAUNCH(this, k_nc_apply, gN, 256, 0, dm, prm, S[cur], valsB.p, cellStart.p, cellEnd.p, ncFlag.p, ncCount.p, ncOffset.p,
-                   PaNIC.p, scal.p, key, rank, nRanks, (long long)capacity, ncDelta.p, ncCounts.p, keysA.p, csCursor.p, scanTmp.p + 3);
-            // the clones: one thread per task (scanTmp[1] = number of tasks); keysA is free until the next step
-            LAUNCH(this, k_nc_clone, numSMs * 8, 128, 0, dm, prm, S[cur], keysA.p, scanTmp.p + 1, scal.p, key, nRanks, (long long)capacity,
-                   cloneDelta.p);
-            // fold ncDelta over cells deterministically: per-CTA partials, then rows
-            const int gR = std::min(gridFor(nCells, 256), numSMs * 4);
-            LAUNCH(this, k_colsum_nc1, gR, 256, 0, nCells, ncDelta.p, k1PartSum.p);
-            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
-            if (axisym) {
-                LAUNCH(this, k_colsum_nc1, gR, 256, 0, 0, cloneDelta.p, k1PartSum.p, scanTmp.p + 1);
-                LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_CLONEDELTA, 0);
+    // Steps are issued in batches without waiting for the device in between: every step leaves its report in a ring on
+    // the device, the host fetches the ring once per batch. One step per batch where the host has to see the entry
+    // count of every step (the (cell, tet) radix sort of a library) or time the all-reduce (several ranks).
+    // Small clouds are launch-bound (a step is ~50 kernels of a few microseconds): there the step is captured once into
+    // a CUDA graph per state-buffer parity and replayed (PDFB200_GRAPH=0/1 overrides; no per-region timing in that mode).
+    static const int graphEnv = [] { const char *e = std::getenv("PDFB200_GRAPH"); return e ? std::atoi(e) : -1; }();
+    const bool mayGraph = !radixPath && nRanks == 1 && (!hasInlet || inletCached);
+    const int gm = graphMode >= 0 ? graphMode : graphEnv;
+    const bool useGraph = mayGraph && (gm >= 0 ? gm != 0 : capacity <= 4000000);
+    const int batchMax = (radixPath || nRanks > 1) ? 1 : REPORT_RING;
+    for (int done = 0; done < nSteps;) {
+        const int nb = std::min(batchMax, nSteps - done);
+        int zero = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&scal.p->ringIdx, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+        for (int b = 0; b < nb; ++b) {
+            if (useGraph) {
+                void *&ge = stepGraph[cur];
+                if (!ge) {
+                    const long long launchesBefore = launches;
+                    const int curBefore = cur;
+                    cudaGraph_t g = nullptr;
+                    CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                    try {
+                        enqueueStep(k1Jit, k1JitSmem, k1Blocks, nullptr);
+                    } catch (...) {
+                        cudaStreamEndCapture(stream, &g);
+                        if (g) cudaGraphDestroy(g);
+                        cur = curBefore;
+                        throw;
+                    }
+                    CUDA_CHECK(cudaStreamEndCapture(stream, &g));
+                    cudaGraphExec_t exec = nullptr;
+                    CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
+                    cudaGraphDestroy(g);
+                    stepGraph[curBefore] = exec;
+                    stepGraphLaunches[curBefore] = launches - launchesBefore;
+                    launches = launchesBefore;
+                    cur = curBefore;          // the capture has flipped it; the launch below does the step
+                }
+                CUDA_CHECK(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(stepGraph[cur]), stream));
+                launches += stepGraphLaunches[cur];
+                cur ^= 1;
             } else {
-                CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
+                enqueueStep(k1Jit, k1JitSmem, k1Blocks, evMarks.data() + (size_t)b * 7);
             }
-        } else {
-            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_NCDELTA, 0, K1_NC1 * sizeof(double), stream));
-            CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
         }
-        // ---- lost mass shares ----
-        {
-            const int gL = std::min(gridFor(nCells, 256), numSMs * 4);
-            LAUNCH(this, k_lost_share, gL, 256, 0, nCells, lostMass.p, PaNIC.p, cellStart.p, cellEnd.p, momentBlock.p, nMom, lostShare.p);
-        }
-        LAUNCH(this, k_step_end, 1, 32, 0, scal.p, dRep, prm, 0, nc ? ncCounts.p : nullptr, total, nRanks);
-        {
-            // after k_step_end: nSorted / nTail / nSlots describe the particles the next step starts from
-            const int gB = numSMs * 4;
-            LAUNCH(this, k_lost_balance, gB, 256, 0, dm, prm, S[cur], valsB.p, scal.p, lostCount.p, lostShare.p, k1PartSum.p);
-            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gB, K1_NC1, k1PartSum.p, dRep->v + RP_LOSTSUM, 0);
-        }
-
-        // ---- report ----
-        CUDA_CHECK(cudaMemcpyAsync(hFinal, dRep, sizeof(DevReport), cudaMemcpyDeviceToHost, stream));
+        // ---- the batch's reports ----
+        CUDA_CHECK(cudaMemcpyAsync(hRing, reportRing.p, (size_t)nb * sizeof(DevReport), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
-        int hNc[2] = {0, 0};
-        CUDA_CHECK(cudaMemcpyAsync(hNc, ncCounts.p, sizeof(hNc), cudaMemcpyDeviceToHost, stream));
-        mark(6);
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        float arMs = 0;
         if (nRanks > 1) CUDA_CHECK(cudaEventElapsedTime(&arMs, evArA, evArB));
-        // per-region device times: prep+inject, evolve kernel, sort, bounds+moments, allreduce, finalise+control
-        for (int r = 0; r < 6; ++r) {
-            float t = 0;
-            CUDA_CHECK(cudaEventElapsedTime(&t, evMark[r], evMark[r + 1]));
-            profMs[r] += t;
+        for (int b = 0; b < nb; ++b) {
+            const double *v = hRing + (size_t)b * 64;
+            if (!useGraph) {
+                // per-region device times: prep+inject, evolve kernel, sort, bounds+moments, allreduce, finalise+control
+                for (int r = 0; r < 6; ++r) {
+                    float t = 0;
+                    CUDA_CHECK(cudaEventElapsedTime(&t, evMarks[(size_t)b * 7 + r], evMarks[(size_t)b * 7 + r + 1]));
+                    profMs[r] += t;
+                }
+                ++profSteps;
+                profParticleSteps += v[RP_N_ENTRIES];
+            }
+            const int ov = (int)v[RP_OVERFLOW];
+            if (ov == 2) throw std::runtime_error("evolve: more than " + std::to_string(lostList.n) + " particles lost in one step");
+            if (ov == 3) throw std::runtime_error("evolve: the 32-bit particle id space is exhausted");
+            if (ov) throw std::length_error("evolve: particle capacity exceeded");
+            nParticlesHost = (int64_t)v[RP_N_SORTED] + (int64_t)v[RP_N_CLONED] - (int64_t)v[RP_N_ELIMINATED];
+            nSlotsHost = (int64_t)v[RP_N_ENTRIES];
+            if (reports) {
+                pdfb200_step_report &r = reports[done + b];
+                std::memset(&r, 0, sizeof(r));
+                r.deltaT = v[RP_DT_USED]; r.deltaTNext = v[RP_DT_NEXT];
+                r.rhoRes = v[RP_CELLSUM] / nCells; r.rhoErrMin = -v[RP_CELLMAX]; r.rhoErrMax = v[RP_CELLMAX + 1];
+                r.totalMass = v[RP_CELLSUM + 1]; r.totalParticleMass = v[RP_CELLSUM + 2];
+                r.UMax = std::max(0.0, v[RP_K1MAX + ACC_UMAX]); r.UcorrMax = std::max(0.0, v[RP_K1MAX + ACC_UCORRMAX]);
+                r.etaMax = std::max(0.0, v[RP_K1MAX + ACC_ETAMAX]); r.etaMin = -v[RP_K1MAX + ACC_NEG_ETAMIN];
+                r.CoMax = std::max(0.0, v[RP_K1MAX + ACC_COMAX]);
+                for (int k = 0; k <= prm.nConserved; ++k) {
+                    r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + (v[RP_NCDELTA + k] + v[RP_CLONEDELTA + k]) + v[RP_LOSTSUM + k];
+                    r.massInInst[k] = v[RP_K1SUM + ACC_MASS_IN + k] + v[RP_INJ + k];
+                    r.massOutInst[k] = v[RP_K1SUM + ACC_MASS_OUT + k];
+                }
+                for (int k = 1; k <= prm.nConserved; ++k) r.deltaMassInst[k] += v[RP_MIXDELTA + k - 1];
+                r.nParticles = nParticlesHost;
+                r.nInjected = (int64_t)v[RP_N_INJECTED]; r.nDeleted = (int64_t)v[RP_K1SUM + ACC_N_DELETED];
+                r.nCloned = (int64_t)v[RP_N_CLONED]; r.nEliminated = (int64_t)v[RP_N_ELIMINATED]; r.nLost = (int64_t)v[RP_K1SUM + ACC_N_LOST];
+                r.momentsAllreduceMs = arMs;
+            }
         }
-        profParticleSteps += (double)total;
-        ++profSteps;
-        if (hScal->overflow == 2) throw std::runtime_error("evolve: more than " + std::to_string(lostList.n) + " particles lost in one step");
-        if (hScal->overflow == 3) throw std::runtime_error("evolve: the 32-bit particle id space is exhausted");
-        if (hScal->overflow) throw std::length_error("evolve: particle capacity exceeded");
-        const double *v = hFinal;
-        if (v[RP_K1SUM + ACC_N_LOST] > 0) lostDirty = true;
-        nParticlesHost = (int64_t)hScal->nSorted + hNc[0] - hNc[1];
-        nSlotsHost = total;
         deltaTHost = hScal->deltaT;
         stepHost = hScal->step;
         sortedValid = true;
-        if (reports) {
-            pdfb200_step_report &r = reports[st];
-            std::memset(&r, 0, sizeof(r));
-            r.deltaT = dtUsed; r.deltaTNext = hScal->deltaT;
-            r.rhoRes = v[RP_CELLSUM] / nCells; r.rhoErrMin = -v[RP_CELLMAX]; r.rhoErrMax = v[RP_CELLMAX + 1];
-            r.totalMass = v[RP_CELLSUM + 1]; r.totalParticleMass = v[RP_CELLSUM + 2];
-            r.UMax = std::max(0.0, v[RP_K1MAX + ACC_UMAX]); r.UcorrMax = std::max(0.0, v[RP_K1MAX + ACC_UCORRMAX]);
-            r.etaMax = std::max(0.0, v[RP_K1MAX + ACC_ETAMAX]); r.etaMin = -v[RP_K1MAX + ACC_NEG_ETAMIN];
-            r.CoMax = std::max(0.0, v[RP_K1MAX + ACC_COMAX]);
-            for (int k = 0; k <= prm.nConserved; ++k) {
-                r.deltaMassInst[k] = v[RP_K1SUM + ACC_DM_MINUS + k] + v[RP_K1SUM + ACC_DM_PLUS + k] + (v[RP_NCDELTA + k] + v[RP_CLONEDELTA + k]) + v[RP_LOSTSUM + k];
-                r.massInInst[k] = v[RP_K1SUM + ACC_MASS_IN + k] + v[RP_INJ + k];
-                r.massOutInst[k] = v[RP_K1SUM + ACC_MASS_OUT + k];
-            }
-            for (int k = 1; k <= prm.nConserved; ++k) r.deltaMassInst[k] += v[RP_MIXDELTA + k - 1];
-            r.nParticles = nParticlesHost;
-            r.nInjected = nInjected; r.nDeleted = (int64_t)v[RP_K1SUM + ACC_N_DELETED];
-            r.nCloned = hNc[0]; r.nEliminated = hNc[1]; r.nLost = (int64_t)v[RP_K1SUM + ACC_N_LOST];
-            r.momentsAllreduceMs = arMs;
-        }
+        done += nb;
     }
     CUDA_CHECK(cudaEventRecord(evStop, stream));
     CUDA_CHECK(cudaEventSynchronize(evStop));
