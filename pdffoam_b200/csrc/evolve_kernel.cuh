@@ -353,9 +353,14 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 4
 #endif
-// 1: the walk keeps the start point relative to the cell centre (r) instead of the centre itself (measured: profiles/README.md)
+// 1: the walk keeps the start point relative to the cell centre (r) instead of the centre itself; measured slower
+// (21.2 against 18.7 ms per launch, profiles/README.md), kept as an option
 #ifndef K1_TRACK_R
-#define K1_TRACK_R 1
+#define K1_TRACK_R 0
+#endif
+// 1: the permutation is requested one iteration ahead; 2: the cell and tet labels as well (see evolveBody)
+#ifndef K1_PF
+#define K1_PF 1
 #endif
 // dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
 // (the correction velocity and the Courant number, which must survive the tet walks without occupying registers)
@@ -410,25 +415,48 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
 
     // the slot of an entry comes through the permutation of the last sort: requested one iteration ahead so that
-    // the state loads of an iteration do not start with a dependent load
-    int slotNext = 0;
+    // the state loads of an iteration do not start with a dependent load. The request is unconditional (index
+    // clamped into the sorted range): a predicated load would be merged with the old value by a select right
+    // behind it, which waits for the load at once (ncu: 3.7 % of the stall samples of the v3 kernel).
+    // K1_PF 2: the cell and tet labels of the next entry are requested one iteration ahead as well (the permutation
+    // two ahead), so that the tet record and the state columns can be requested at the top of an iteration.
+    const int gstride = gridDim.x * blockDim.x;
+    const int permLast = max(nSorted - 1, 0);
+#if K1_PF >= 2
+    int pvNext, slotCur, cellCur, tetCur;
     {
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i0 < nSorted) slotNext = (int)A.perm[i0];
+        const int ic = min(i0, max(total - 1, 0));
+        slotCur = (ic < nSorted) ? (int)A.perm[min(ic, permLast)] : (total > 0 ? nSlotsIn + (ic - nSorted) : 0);
+        pvNext = (int)A.perm[min(i0 + gstride, permLast)];
+        cellCur = A.in.cell[slotCur]; tetCur = A.in.tet[slotCur];
     }
-    for (int base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+#else
+    int slotNext = (int)A.perm[min((int)(blockIdx.x * blockDim.x + threadIdx.x), permLast)];
+#endif
+    for (int base = blockIdx.x * blockDim.x; base < total; base += gstride) {
         const int i = base + threadIdx.x;
-        const int slotPerm = slotNext;
+#if K1_PF >= 2
+        const int slot = slotCur, cell0 = cellCur, tet0 = tetCur;
         {
-            const int iN = i + gridDim.x * blockDim.x;
-            if (iN < nSorted) slotNext = (int)A.perm[iN];
+            const int iN = min(i + gstride, total - 1);
+            slotCur = (iN < nSorted) ? pvNext : nSlotsIn + (iN - nSorted);
+            pvNext = (int)A.perm[min(i + 2 * gstride, permLast)];
+            cellCur = A.in.cell[slotCur]; tetCur = A.in.tet[slotCur];
         }
+        if (i >= total) continue;
+#else
+        const int slotPerm = slotNext;
+        slotNext = (int)A.perm[min(i + gstride, permLast)];
         if (i >= total) continue;
         const int slot = (i < nSorted) ? slotPerm : nSlotsIn + (i - nSorted);
         const int cell0 = A.in.cell[slot];
+#endif
         if (cell0 < 0) { A.out.cell[i] = -1; continue; }
         V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
+#if K1_PF < 2
         const int tet0 = A.in.tet[slot];
+#endif
         int tet = tet0;
         const bool injected = (i >= nSorted + nInjStart);
 

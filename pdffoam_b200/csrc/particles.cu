@@ -269,6 +269,54 @@ __global__ void k_cs_finish(const int *total, StepScalars *sc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSorted = *total;
 }
 
+// Sums of NACC per-lane accumulators over the lanes of a warp. A butterfly per accumulator (x += shfl_xor(x, 16), 8,
+// 4, 2, 1) costs 5 NACC 64-bit shuffles per cell, which made the shuffle pipe a bound of k_moments (2e6 cells x 80 at
+// nPhi = 1). Recursive halving instead: at distance 16 a lane hands half of its accumulators to its partner and takes
+// the partner's copies of the half it keeps, at distance 8 a quarter, ... - about NACC shuffles in total. Every
+// partial sum is formed from the same two operands as in the butterfly (own + partner's; floating-point addition
+// commutes), so the results are bit-identical to it. A group of C accumulators (a power of two <= 32) leaves
+// accumulator k in the lanes l with (l >> log2(32 / C)) == k.
+__host__ __device__ constexpr int pow2Ceil(int x) { int c = 1; while (c < x) c <<= 1; return c; }
+__host__ __device__ constexpr int log2Floor(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
+template <int C>
+__device__ __forceinline__ double laneSums(double (&v)[C], int lane) {
+    int n = C;   // folds to constants once the loop is unrolled
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+        if (n > 1) {
+            const int half = n >> 1;
+#pragma unroll
+            for (int k = 0; k < C / 2; ++k) {
+                if (k < half) {
+                    const double send = upper ? v[k] : v[k + half];
+                    const double keep = upper ? v[k + half] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            n = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        }
+    }
+    return v[0];
+}
+template <int NACC, int G0>
+__device__ __forceinline__ void reduceStoreGroups(const double (&a)[NACC], int lane, double *out) {
+    if constexpr (G0 < NACC) {
+        constexpr int LEFT = (NACC - G0 < 32) ? NACC - G0 : 32;
+        constexpr int C = pow2Ceil(LEFT);
+        constexpr int SHIFT = log2Floor(32 / C);
+        double v[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) v[k] = (k < LEFT) ? a[G0 + (k < LEFT ? k : 0)] : 0.0;
+        const double x = laneSums<C>(v, lane);
+        const int k = lane >> SHIFT;
+        if ((lane & ((1 << SHIFT) - 1)) == 0 && k < LEFT) out[G0 + k] = x;
+        reduceStoreGroups<NACC, G0 + 32>(a, lane, out);
+    }
+}
+
 // updateCloudPDF first half (mcParticleCloud.C:929-956): one warp per cell,
 // lanes stride over the cell's segment of the sorted order, butterfly reduction
 // in a fixed order -> deterministic sums without atomics.
@@ -315,18 +363,9 @@ __global__ void __launch_bounds__(256, (NPHI <= 1 ? 4 : NPHI <= 3 ? 2 : 1)) k_mo
                 uu[6 + 3 * k] += mp * U.x; uu[7 + 3 * k] += mp * U.y; uu[8 + 3 * k] += mp * U.z;
             }
         }
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-            double x = a[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            a[k] = x;
-        }
         double *b = block + (size_t)c * nMom;
         if (lane == 0) b[0] = (double)(e - s);
-        // lanes share the stores
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) if (lane == (k & 31)) b[1 + k] = a[k];
+        reduceStoreGroups<NACC, 0>(a, lane, b + 1);
     }
 }
 
