@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TRAFFIC_PROFILE = "r02_k_evolve_v3_metrics.csv"   # ncu --set full capture of the shipped k_evolve_jit (profiles/README.md)
+TRAFFIC_PROFILE = "r02_k_evolve_final_metrics.csv"   # ncu --set full capture of the shipped k_evolve_jit (profiles/README.md)
 METRIC = "particle-steps/sec"
 UNIT = "particle-steps/s"
 

@@ -176,7 +176,7 @@ typedef struct pdfb200_particles {
     double  *Phi[PDFB200_MAX_PHI];    /* [n] each */
     int32_t *cell;     /* [n] */
     int32_t *tet;      /* [n] global tet label (tetFacePointCellDecomposition order) */
-    uint32_t *id;      /* [n] persistent particle id (RNG counter) */
+    uint64_t *id;      /* [n] persistent particle id, 64 bits (keys the random streams; Particle<>::origId) */
 } pdfb200_particles;
 
 /* ---- per-step scalars printed/returned by evolve (mcParticleCloud.C:1376-1530) ---- */

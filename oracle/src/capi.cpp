@@ -190,9 +190,14 @@ int pdforacle_upload_particles(pdforacle_cloud *h, int64_t n, const pdfb200_part
         for (int k = 0; k < c.prm.nPhi; ++k) q.Phi[k] = p->Phi[k][i];
         q.cell = p->cell[i];
         q.tet = p->tet ? p->tet[i] : c.mesh.locate(q.position, q.cell);
-        q.id = p->id ? p->id[i] : (uint32_t)i;
+        q.id = p->id ? p->id[i] : (uint64_t)i;
     }
-    c.nextId = (uint32_t)n + (uint32_t)c.rank;
+    // the next free id: above every id in use and congruent to the rank (ids advance in steps of nRanks); for the
+    // default ids 0..n-1 of one rank this is n
+    uint64_t idEnd = 0;
+    for (const Particle &q : c.particles) idEnd = std::max<uint64_t>(idEnd, q.id + 1);
+    const uint64_t nr = (uint64_t)std::max(c.nRanks, 1);
+    c.nextId = (idEnd + nr - 1) / nr * nr + (uint64_t)c.rank;
     ORACLE_CATCH
 }
 
@@ -297,7 +302,7 @@ int pdforacle_upload_moments(pdforacle_cloud *h, const pdfb200_cell_fields *m) {
 }
 int pdforacle_set_graph_mode(pdforacle_cloud *, int) { return PDFB200_OK; }   // nothing to replay on the CPU
 int64_t pdforacle_id_counter(pdforacle_cloud *h) { return (int64_t)h->c.nextId; }
-int pdforacle_set_id_counter(pdforacle_cloud *h, int64_t id) { h->c.nextId = (uint32_t)id; return PDFB200_OK; }
+int pdforacle_set_id_counter(pdforacle_cloud *h, int64_t id) { h->c.nextId = (uint64_t)id; return PDFB200_OK; }
 int64_t pdforacle_step_counter(pdforacle_cloud *h) { return (int64_t)h->c.step; }
 int pdforacle_set_step_counter(pdforacle_cloud *h, int64_t step) { h->c.step = (uint32_t)step; return PDFB200_OK; }
 

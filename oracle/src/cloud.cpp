@@ -351,7 +351,7 @@ void Cloud::curlMixing() {
     const int RMAX = 8;
     std::vector<std::vector<size_t>> addr(mesh.nCells);
     for (size_t i = 0; i < particles.size(); ++i) addr[particles[i].cell].push_back(i);
-    struct Ent { uint32_t h, id; size_t i; };
+    struct Ent { uint32_t h; uint64_t id; size_t i; };
     std::vector<Ent> ord;
     for (int c = 0; c < mesh.nCells; ++c) {
         const std::vector<size_t> &L = addr[c];
@@ -593,7 +593,7 @@ void Cloud::injectPatch(int patchI) {
                 if (prm.rngMode == 1) uAcc = srng.scalar01();
                 if (uAcc > (mIn - mGen) / p.m) break;
             }
-            p.id = nextId; nextId += (uint32_t)nRanks;
+            p.id = nextId; nextId += (uint64_t)nRanks;
             particles.push_back(p);
             gen.push_back(particles.size() - 1);
             mGen += p.m;
@@ -760,7 +760,7 @@ void Cloud::updateCloudPDF(double existWt) {
 }
 
 // mcParticleCloud::randomPointsInCell (mcParticleCloud.C:2040-2085)
-std::vector<Vec3> Cloud::randomPointsInCell(int n, int cell, uint32_t entityBase, uint32_t purpose, uint32_t stepCtr) {
+std::vector<Vec3> Cloud::randomPointsInCell(int n, int cell, uint64_t entityBase, uint32_t purpose, uint32_t stepCtr) {
     std::vector<Vec3> pts(n);
     const Vec3 minb = mesh.bbMin[cell];
     const Vec3 dimb = mesh.bbMax[cell] - minb;
@@ -826,7 +826,7 @@ void Cloud::particleNumberControl() {
                 Particle q = p;
                 q.position = pos[0];
                 q.tet = mesh.locate(q.position, c);
-                q.id = nextId; nextId += (uint32_t)nRanks;
+                q.id = nextId; nextId += (uint64_t)nRanks;
                 clones.push_back(q);
             }
             PaNIC[c] += n;
@@ -883,7 +883,7 @@ void Cloud::seedParticles() {
         std::vector<Particle *> gen;
         const size_t first = particles.size();
         for (int j = rank; j < Npc; j += nRanks) {
-            const uint32_t idx = (uint32_t)((int64_t)c * Npc + j);
+            const uint64_t idx = (uint64_t)((int64_t)c * Npc + j);
             // every draw is keyed by the *global* particle index, so the union of
             // all ranks' particles equals the single-rank population
             std::vector<Vec3> pos = randomPointsInCell(1, c, idx, RNG_SEED, 0);
@@ -904,7 +904,7 @@ void Cloud::seedParticles() {
         for (size_t i = first; i < particles.size(); ++i) gen.push_back(&particles[i]);
         adjustAxiSymmetricMass(gen);
     }
-    nextId = (uint32_t)((int64_t)mesh.nCells * Npc + rank);   // ids of later particles: stride nRanks
+    nextId = (uint64_t)((int64_t)mesh.nCells * Npc + rank);   // ids of later particles: stride nRanks
     // correct mass according to local time-stepping, then Omega and reaction
     updateModelInternals();
     for (Particle &p : particles) { ltsCorrect(p); p.m /= p.eta; }

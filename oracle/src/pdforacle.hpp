@@ -272,7 +272,7 @@ struct Particle {
     bool reflected = false, isOnInletBoundary = false, reflectedAtOpenBoundary = false;
     bool keep = true;
     int injPatch = -1;        // patch that injected it this step (cull ordering, see cloud.cpp)
-    uint32_t id = 0;
+    uint64_t id = 0;
     std::array<double, PDFB200_MAX_PHI> Phi{};
 };
 
@@ -325,7 +325,7 @@ struct Cloud {
     std::vector<Particle> particles;
     double deltaT = 100 * SMALL;
     uint32_t step = 0;
-    uint32_t nextId = 0;
+    uint64_t nextId = 0;
     int rank = 0, nRanks = 1;
     KeyedRng krng; SeqRandom srng;
     int64_t nLostTotal = 0;
@@ -386,7 +386,7 @@ struct Cloud {
     void positionCorrectionCorrect(Particle &p) const;  // mcLimitedSimplePositionCorrection.C:187-192
 
     void seedParticles();                               // mcParticleCloud.C:1534-1629
-    std::vector<Vec3> randomPointsInCell(int n, int cell, uint32_t entityBase, uint32_t purpose, uint32_t stepCtr);
+    std::vector<Vec3> randomPointsInCell(int n, int cell, uint64_t entityBase, uint32_t purpose, uint32_t stepCtr);
     void adjustAxiSymmetricMass(std::vector<Particle *> &ps) const;  // mcParticleCloud.C:2095-2117
 
     // step-local diagnostics

@@ -21,6 +21,7 @@ c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_uint8_p = C.POINTER(C.c_uint8)
 c_uint32_p = C.POINTER(C.c_uint32)
+c_uint64_p = C.POINTER(C.c_uint64)
 
 
 class MeshStruct(C.Structure):
@@ -92,7 +93,7 @@ class ParticlesStruct(C.Structure):
         ("pos", c_double_p), ("U", c_double_p),
         ("m", c_double_p), ("Omega", c_double_p), ("rho", c_double_p), ("eta", c_double_p),
         ("Phi", c_double_p * MAX_PHI),
-        ("cell", c_int32_p), ("tet", c_int32_p), ("id", c_uint32_p),
+        ("cell", c_int32_p), ("tet", c_int32_p), ("id", c_uint64_p),
     ]
 
 
@@ -158,11 +159,11 @@ def _u8p(a: Optional[np.ndarray]):
     return a.ctypes.data_as(c_uint8_p)
 
 
-def _u32p(a: Optional[np.ndarray]):
+def _u64p(a: Optional[np.ndarray]):
     if a is None:
         return None
-    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
-    return a.ctypes.data_as(c_uint32_p)
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_uint64_p)
 
 
 def jit_compile(lib: "Library", params: Params, axisym: bool, has_open: bool, tet_bits: int = 0,
@@ -454,19 +455,19 @@ class CloudHandle:
         if P.get("tet") is not None:
             tet = np.ascontiguousarray(P["tet"], np.int32); keep.append(tet); s.tet = _ip(tet)
         if P.get("id") is not None:
-            pid = np.ascontiguousarray(P["id"], np.uint32); keep.append(pid); s.id = _u32p(pid)
+            pid = np.ascontiguousarray(P["id"], np.uint64); keep.append(pid); s.id = _u64p(pid)
         self.lib.check(self.lib.fn("upload_particles")(self.h, n, C.byref(s)), "upload_particles")
 
     def download_particles(self) -> Dict[str, np.ndarray]:
         n = self.num_particles()
         P = dict(pos=np.zeros((n, 3)), U=np.zeros((n, 3)), m=np.zeros(n), Omega=np.zeros(n), rho=np.zeros(n),
                  eta=np.zeros(n), Phi=[np.zeros(n) for _ in range(self.n_phi)], cell=np.zeros(n, np.int32),
-                 tet=np.zeros(n, np.int32), id=np.zeros(n, np.uint32))
+                 tet=np.zeros(n, np.int32), id=np.zeros(n, np.uint64))
         s = ParticlesStruct()
         s.pos, s.U, s.m, s.Omega, s.rho, s.eta = _dp(P["pos"]), _dp(P["U"]), _dp(P["m"]), _dp(P["Omega"]), _dp(P["rho"]), _dp(P["eta"])
         for i in range(self.n_phi):
             s.Phi[i] = _dp(P["Phi"][i])
-        s.cell, s.tet, s.id = _ip(P["cell"]), _ip(P["tet"]), _u32p(P["id"])
+        s.cell, s.tet, s.id = _ip(P["cell"]), _ip(P["tet"]), _u64p(P["id"])
         nn = C.c_int64(0)
         self.lib.check(self.lib.fn("download_particles")(self.h, n, C.byref(s), C.byref(nn)), "download_particles")
         assert nn.value == n

@@ -131,7 +131,7 @@ class Case:
         rho = self.cf["rho"][cell]
         P = dict(pos=pos, U=U, m=rho * vol[cell] / ppc, Omega=(self.fv["epsilon"] / self.fv["k"])[cell].copy(),
                  rho=rho.copy(), eta=np.ones(n), Phi=[self.cf["Phi"][i][cell].copy() for i in range(self.params.nPhi)],
-                 cell=cell, id=np.arange(n, dtype=np.uint32))
+                 cell=cell, id=np.arange(n, dtype=np.uint64))
         return P
 
 

@@ -228,19 +228,19 @@ int pdfb200_upload_moments(pdfb200_cloud *c, const pdfb200_cell_fields *m) {
 int pdfb200_set_graph_mode(pdfb200_cloud *c, int mode) { c->c.graphMode = mode; return PDFB200_OK; }
 int64_t pdfb200_id_counter(pdfb200_cloud *c) {
     USE_DEVICE(c);
-    uint32_t v = 0;
-    if (cudaMemcpy(&v, &c->c.scal.p->nextId, sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, &c->c.scal.p->nextId, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int64_t)v;
 }
 int pdfb200_set_id_counter(pdfb200_cloud *c, int64_t id) {
     USE_DEVICE(c);
     return guarded([&] {
         Cloud &C = c->c;
-        if (id < 0 || id > 0xffffffffLL) throw std::invalid_argument("set_id_counter: out of range");
+        if (id < 0) throw std::invalid_argument("set_id_counter: out of range");
         if (id % C.nRanks != C.rank) throw std::invalid_argument("set_id_counter: the id must be congruent to the rank modulo the number of ranks");
-        const uint32_t v = (uint32_t)id;
+        const unsigned long long v = (unsigned long long)id;
         C.hScal->nextId = v;
-        CUDA_CHECK(cudaMemcpy(&C.scal.p->nextId, &v, sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(&C.scal.p->nextId, &v, sizeof(v), cudaMemcpyHostToDevice));
     });
 }
 int64_t pdfb200_step_counter(pdfb200_cloud *c) { return (int64_t)c->c.stepHost; }

@@ -102,7 +102,7 @@ struct PState {
     double *m, *omega, *rho, *eta;
     double *phi[PDFB200_MAX_PHI];
     int *cell, *tet;
-    uint32_t *id;
+    uint64_t *id;             // persistent particle id (keys the random streams), 64 bits
 };
 
 // per-step scalars living on the device (kernels read deltaT etc. from here)
@@ -119,8 +119,8 @@ struct StepScalars {
     int nEntries;           // entries of the running step (nSorted + nTail after injection): set by k_step_begin
     int ringIdx;            // slot of the report ring the running step writes (k_step_end advances it)
     int anyLost;            // lost mass to redistribute at the next K1
-    uint32_t nextId;
     int overflow;           // capacity exceeded
+    unsigned long long nextId;   // id of the next injected or cloned particle (advances in steps of nRanks)
     long long nLostTotal;
 };
 

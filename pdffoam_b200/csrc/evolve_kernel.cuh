@@ -362,10 +362,28 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #ifndef K1_PF
 #define K1_PF 1
 #endif
+#ifndef K1_COMPACT_ACC
+#define K1_COMPACT_ACC 1
+#endif
 // dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
 // (the correction velocity and the Courant number, which must survive the tet walks without occupying registers)
-#define K1_NPARK 4
-#define K1_SMEM_BYTES ((ACC_NSUM + ACC_NMAX + K1_NPARK) * K1_THREADS * sizeof(double))
+// The specialised kernel carries the sum rows of the conserved scalars the case has, not of K1_MAXCONS (k1_layout.h:
+// K1_SMEM_ROWS(nConserved)); with one conserved scalar five CTAs then need 105 KB instead of 140 KB of shared memory,
+// which moves the SM's carve-out from 164 to 132 KB and leaves 124 instead of 92 KB of L1 for the tet and node records.
+#if defined(K1_JIT) && K1_COMPACT_ACC
+#define KNC1 (1 + JitP::nConserved)
+#else
+#define KNC1 K1_NC1
+#endif
+#define KACC_DM_MINUS 0
+#define KACC_DM_PLUS (KACC_DM_MINUS + KNC1)
+#define KACC_MASS_IN (KACC_DM_PLUS + KNC1)
+#define KACC_MASS_OUT (KACC_MASS_IN + KNC1)
+#define KACC_N_DELETED (KACC_MASS_OUT + KNC1)
+#define KACC_N_LOST (KACC_N_DELETED + 1)
+#define KACC_N_ALIVE (KACC_N_LOST + 1)
+#define KACC_NSUM (KACC_N_ALIVE + 1)
+#define K1_SMEM_BYTES (K1_SMEM_ROWS(K1_MAXCONS) * K1_THREADS * sizeof(double))
 
 // Loads of this thread's own state columns that the compiler must not merge with an earlier load
 // of the same address: the kernel deliberately drops cold values (m, Omega, rho, phi, id, the old
@@ -377,9 +395,30 @@ __device__ __forceinline__ double reloadD(const double *p) {
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// the same for the input state, which the kernel never writes: no ordering against its stores needed
+// K1_STATE_NA 1: the gathered loads of the input state do not allocate in L1 (a warp touches about seven 128-byte
+// lines per column and uses a third of each; twenty resident warps would flood the L1 that the tet and node records
+// of the warp's cells should stay in)
+#ifndef K1_STATE_NA
+#define K1_STATE_NA 0
+#endif
+__device__ __forceinline__ double ldInD(const double *p) {
+#if K1_STATE_NA
+    double v;
+    asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+// the same for the input state, which the kernel never writes
 __device__ __forceinline__ double reloadInD(const double *p) {
+#if K1_STATE_NA
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+#else
     return reloadD(p);
+#endif
 }
 __device__ __forceinline__ int reloadI(const int *p) {
     int v;
@@ -392,10 +431,10 @@ template <int NPHI>
 __device__ __forceinline__ void evolveBody(const K1Args &A) {
     extern __shared__ double smem[];
     double *accS = smem + threadIdx.x;                         // sums: accS[k*K1_THREADS]
-    double *accM = smem + ACC_NSUM * K1_THREADS + threadIdx.x;  // maxima
-    double *park = smem + (ACC_NSUM + ACC_NMAX) * K1_THREADS + threadIdx.x;   // park[k*K1_THREADS]: Ucorr
+    double *accM = smem + KACC_NSUM * K1_THREADS + threadIdx.x;  // maxima
+    double *park = smem + (KACC_NSUM + ACC_NMAX) * K1_THREADS + threadIdx.x;   // park[k*K1_THREADS]: Ucorr
 #pragma unroll
-    for (int k = 0; k < ACC_NSUM; ++k) accS[k * K1_THREADS] = 0.0;
+    for (int k = 0; k < KACC_NSUM; ++k) accS[k * K1_THREADS] = 0.0;
 #pragma unroll
     for (int k = 0; k < ACC_NMAX; ++k) accM[k * K1_THREADS] = -PDF_VGREAT;
 
@@ -453,7 +492,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         const int cell0 = A.in.cell[slot];
 #endif
         if (cell0 < 0) { A.out.cell[i] = -1; continue; }
-        V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
+        V3 pos = mk(ldInD(A.in.px + slot), ldInD(A.in.py + slot), ldInD(A.in.pz + slot));
 #if K1_PF < 2
         const int tet0 = A.in.tet[slot];
 #endif
@@ -484,22 +523,22 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         const double4 n4 = M.bfNormal[bf];
                         const V3 Cf = ld3(M.faceCentres, M.nInternalFaces + bf);
                         const double xp = dot3(mk(n4.x, n4.y, n4.z), Cf - pos);
-                        if (xp < A.in.eta[slot] * (Un * deltaT)) {
+                        if (xp < ldInD(A.in.eta + slot) * (Un * deltaT)) {
                             const double mpd = massPerDepth(M, pos, m);
-                            accS[ACC_MASS_OUT * K1_THREADS] -= mpd;
+                            accS[KACC_MASS_OUT * K1_THREADS] -= mpd;
                             for (int cs = 0; cs < P.nConserved; ++cs)
-                                accS[(ACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * A.in.phi[PRM_AT(P, conserved, cs)][slot];
+                                accS[(KACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * ldInD(A.in.phi[PRM_AT(P, conserved, cs)] + slot);
                             status = 1;
                         }
                     }
                 }
             }
-            if (status != 0) { accS[ACC_N_DELETED * K1_THREADS] += 1; A.out.cell[i] = -1; continue; }
+            if (status != 0) { accS[KACC_N_DELETED * K1_THREADS] += 1; A.out.cell[i] = -1; continue; }
             // ---- E2 ----
             const double mpd = massPerDepth(M, pos, m);
-            accS[ACC_DM_MINUS * K1_THREADS] -= mpd;
+            accS[KACC_DM_MINUS * K1_THREADS] -= mpd;
             for (int cs = 0; cs < P.nConserved; ++cs)
-                accS[(ACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * A.in.phi[PRM_AT(P, conserved, cs)][slot];
+                accS[(KACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * ldInD(A.in.phi[PRM_AT(P, conserved, cs)] + slot);
         }
         // the walk state: tet record, the cell the tet belongs to and its centre (vertex d)
         TetL T;
@@ -509,7 +548,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         // ---- E3: position correction gather ----
         V3 Utrack;
         {
-            V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
+            V3 U = mk(ldInD(A.in.ux + slot), ldInD(A.in.uy + slot), ldInD(A.in.uz + slot));
             V3 Ucorr = mk(0, 0, 0);
             if (P.positionCorrection != PDFB200_POSCORR_NONE) {
                 // the interpolated vector: limitedSimple UPosCorr (Ucorrection += it, .C:187-192), simple grad(phi), external G0
@@ -676,7 +715,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         if (Un < 0 || !BF_REFLECTING(info)) {
                             // the particle leaves through an open face: its mass and scalars as they are at this point
                             const double mpd = massPerDepth(M, pos, massIn());
-                            const int baseAcc = (Un < 0) ? ACC_MASS_IN : ACC_MASS_OUT;
+                            const int baseAcc = (Un < 0) ? KACC_MASS_IN : KACC_MASS_OUT;
                             accS[baseAcc * K1_THREADS] -= mpd;
                             for (int cs = 0; cs < P.nConserved; ++cs) {
                                 const int sIdx = PRM_AT(P, conserved, cs);
@@ -746,7 +785,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             double phi[NPHI];
 #pragma unroll
             for (int k = 0; k < NPHI; ++k) phi[k] = (k < nPhi) ? reloadInD(A.in.phi[k] + slot) : 0.0;
-            const uint32_t id = (uint32_t)reloadI(reinterpret_cast<const int *>(A.in.id) + slot);
+            const uint64_t id = (uint64_t)__double_as_longlong(reloadInD(reinterpret_cast<const double *>(A.in.id) + slot));
             // mcRASOmegaModel::correct
             if (P.omegaModel != PDFB200_OMEGA_NONE) Omega = fmax(val[NM_OMEGA], PDF_SMALL);
             // mcIEMMixingModel::correct
@@ -849,8 +888,8 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 const double m = massIn();
                 const unsigned k = atomicAdd(A.lostCount, 1u);
                 if (k < A.lostCap) { LostRec r; r.idx = (uint32_t)i; r.cell = cell; r.m = m; A.lostList[k] = r; }
-                accS[ACC_N_LOST * K1_THREADS] += 1;
-            } else accS[ACC_N_DELETED * K1_THREADS] += 1;
+                accS[KACC_N_LOST * K1_THREADS] += 1;
+            } else accS[KACC_N_DELETED * K1_THREADS] += 1;
             A.out.cell[i] = -1;
             continue;
         }
@@ -873,10 +912,10 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         {
             const double m = reloadD(A.out.m + i), eta = reloadD(A.out.eta + i);
             const double mpd = massPerDepth(M, pos, m);
-            accS[ACC_DM_PLUS * K1_THREADS] += mpd;
+            accS[KACC_DM_PLUS * K1_THREADS] += mpd;
             for (int cs = 0; cs < P.nConserved; ++cs)
-                accS[(ACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * reloadD(A.out.phi[PRM_AT(P, conserved, cs)] + i);
-            accS[ACC_N_ALIVE * K1_THREADS] += 1;
+                accS[(KACC_DM_PLUS + 1 + cs) * K1_THREADS] += mpd * reloadD(A.out.phi[PRM_AT(P, conserved, cs)] + i);
+            accS[KACC_N_ALIVE * K1_THREADS] += 1;
             const V3 Ucorr = mk(park[0], park[K1_THREADS], park[2 * K1_THREADS]);
             accM[ACC_UMAX * K1_THREADS] = fmax(accM[ACC_UMAX * K1_THREADS], mag3(U));
             accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
@@ -890,18 +929,25 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     __syncthreads();
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        // warp w reduces rows w, w+4, ...
+        // warp w reduces rows w, w+4, ... of the host's layout (k1_layout.h); the rows of conserved scalars the
+        // specialised kernel does not carry are written as zeros
         for (int k = warp; k < ACC_NSUM + ACC_NMAX; k += K1_THREADS / 32) {
             const bool isMax = k >= ACC_NSUM;
+            int row;   // row of this kernel's accumulators, -1: none
+            if (isMax) row = KACC_NSUM + (k - ACC_NSUM);
+            else if (k >= 4 * K1_NC1) row = 4 * KNC1 + (k - 4 * K1_NC1);
+            else row = (k % K1_NC1 < KNC1) ? (k / K1_NC1) * KNC1 + k % K1_NC1 : -1;
             double x = isMax ? -PDF_VGREAT : 0.0;
-            for (int t = lane; t < K1_THREADS; t += 32) {
-                const double y = smem[k * K1_THREADS + t];
-                x = isMax ? fmax(x, y) : x + y;
-            }
+            if (row >= 0) {
+                for (int t = lane; t < K1_THREADS; t += 32) {
+                    const double y = smem[row * K1_THREADS + t];
+                    x = isMax ? fmax(x, y) : x + y;
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double y = __shfl_down_sync(0xffffffffu, x, o);
-                x = isMax ? fmax(x, y) : x + y;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double y = __shfl_down_sync(0xffffffffu, x, o);
+                    x = isMax ? fmax(x, y) : x + y;
+                }
             }
             if (lane == 0) {
                 if (isMax) A.partMax[blockIdx.x * ACC_NMAX + (k - ACC_NSUM)] = x;

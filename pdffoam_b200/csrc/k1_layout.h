@@ -27,4 +27,9 @@
 #define ACC_NEG_ETAMIN 3
 #define ACC_COMAX 4
 #define ACC_NMAX 5
+// dynamic shared memory of the particle kernel: thread-private rows of K1_THREADS doubles - the sums (with the rows of
+// nCons conserved scalars), the maxima, and K1_NPARK parking rows (the correction velocity and the Courant number,
+// which must survive the tet walks without occupying registers)
+#define K1_NPARK 4
+#define K1_SMEM_ROWS(nCons) (4 * (1 + (nCons)) + 3 + ACC_NMAX + K1_NPARK)
 

@@ -223,7 +223,28 @@ __device__ __forceinline__ void sortSegment(uint32_t *seg, int n, int lane) {
     for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; if (j < n) seg[j] = v[k]; }
 }
 
-// one warp per cell: segment end + canonical (ascending) order of the segment
+// canonical (ascending) order of one cell's segment of the permutation, by one warp
+__device__ __forceinline__ void orderSegment(uint32_t *seg, int n, int lane, uint32_t *scratchSeg) {
+    if (n <= 1) return;
+    if (n <= 32) sortSegment<1>(seg, n, lane);
+    else if (n <= 64) sortSegment<2>(seg, n, lane);
+    else if (n <= 128) sortSegment<4>(seg, n, lane);
+    else if (n <= 256) sortSegment<8>(seg, n, lane);
+    else {
+        // very full cells: rank by counting through the scratch array (values are distinct)
+        for (int j = lane; j < n; j += 32) {
+            const uint32_t x = seg[j];
+            int rk = 0;
+            for (int q = 0; q < n; ++q) rk += seg[q] < x ? 1 : 0;
+            scratchSeg[rk] = x;
+        }
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) seg[j] = scratchSeg[j];
+        __syncwarp();
+    }
+}
+
+// one warp per cell: segment end + canonical order of the segment
 __global__ void k_cs_order(int nCells, const int *rankStart, const int *count, const int *cellOfRank, int *cellStart, int *cellEnd,
                            uint32_t *perm, uint32_t *scratch) {
     const int lane = threadIdx.x & 31;
@@ -231,24 +252,7 @@ __global__ void k_cs_order(int nCells, const int *rankStart, const int *count, c
     for (int r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < nCells; r += gridDim.x * warpsPerBlock) {
         const int s = rankStart[r], n = count[r];
         if (lane == 0) { const int c = cellOfRank[r]; cellStart[c] = s; cellEnd[c] = s + n; }
-        if (n <= 1) continue;
-        uint32_t *seg = perm + s;
-        if (n <= 32) sortSegment<1>(seg, n, lane);
-        else if (n <= 64) sortSegment<2>(seg, n, lane);
-        else if (n <= 128) sortSegment<4>(seg, n, lane);
-        else if (n <= 256) sortSegment<8>(seg, n, lane);
-        else {
-            // very full cells: rank by counting through the scratch array (values are distinct)
-            for (int j = lane; j < n; j += 32) {
-                const uint32_t x = seg[j];
-                int rk = 0;
-                for (int q = 0; q < n; ++q) rk += seg[q] < x ? 1 : 0;
-                scratch[s + rk] = x;
-            }
-            __syncwarp();
-            for (int j = lane; j < n; j += 32) seg[j] = scratch[s + j];
-            __syncwarp();
-        }
+        orderSegment(perm + s, n, lane, scratch + s);
     }
 }
 
@@ -324,48 +328,87 @@ __device__ __forceinline__ void reduceStoreGroups(const double (&a)[NACC], int l
 // velocity-scalar flux moment (BASELINE north_star "scalar fluxes"; the reference's moments stop at MUU).
 // Compiled for 4 CTAs per SM (64 registers) up to one scalar, where the kernel is latency-bound; the wider
 // instantiations hold 20 + 6 nPhi + nCov accumulators and would spill at that limit.
+#define MOM_MIN_BLOCKS(NPHI) ((NPHI) <= 1 ? 4 : (NPHI) <= 3 ? 2 : 1)
+// moments of cell c from its segment [s, e) of the sorted order, by one warp
 template <int NPHI>
-__global__ void __launch_bounds__(256, (NPHI <= 1 ? 4 : NPHI <= 3 ? 2 : 1)) k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
-                          double *block, int nMom) {
+__device__ __forceinline__ void momentsOfSegment(const DMesh &M, const PState &S, const uint32_t *perm, int c, int s, int e, int lane,
+                                                 double *block, int nMom) {
     constexpr int NCOV = NPHI * (NPHI + 1) / 2;
     constexpr int NACC = 11 + NPHI + NCOV + 3 * NPHI;   // all but the count
+    double a[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) a[k] = 0.0;
+    struct Rec { V3 U; double mpd, rho; double ph[NPHI > 0 ? NPHI : 1]; };
+    auto fetch = [&](int j, Rec &R) {
+        const int slot = (int)perm[j];
+        R.U = mk(S.ux[slot], S.uy[slot], S.uz[slot]);
+        double mpd = S.m[slot];
+        if (M.axisym) mpd = massPerDepth(M, mk(S.px[slot], S.py[slot], S.pz[slot]), mpd);
+        R.mpd = S.eta[slot] * mpd;
+        R.rho = S.rho[slot];
+#pragma unroll
+        for (int k = 0; k < NPHI; ++k) R.ph[k] = S.phi[k][slot];
+    };
+    auto accumulate = [&](const Rec &R) {
+        const double mpd = R.mpd;
+        const V3 U = R.U;
+        a[0] += mpd;
+        a[1] += mpd / R.rho;
+        a[2] += mpd * U.x; a[3] += mpd * U.y; a[4] += mpd * U.z;
+#pragma unroll
+        for (int k = 0; k < NPHI; ++k) a[5 + k] += mpd * R.ph[k];
+        int pp = 0;
+#pragma unroll
+        for (int k = 0; k < NPHI; ++k)
+#pragma unroll
+            for (int l = k; l < NPHI; ++l, ++pp) a[5 + NPHI + pp] += mpd * R.ph[k] * R.ph[l];
+        double *uu = a + 5 + NPHI + NCOV;
+        uu[0] += mpd * (U.x * U.x); uu[1] += mpd * (U.x * U.y); uu[2] += mpd * (U.x * U.z);
+        uu[3] += mpd * (U.y * U.y); uu[4] += mpd * (U.y * U.z); uu[5] += mpd * (U.z * U.z);
+#pragma unroll
+        for (int k = 0; k < NPHI; ++k) {
+            const double mp = mpd * R.ph[k];
+            uu[6 + 3 * k] += mp * U.x; uu[7 + 3 * k] += mp * U.y; uu[8 + 3 * k] += mp * U.z;
+        }
+    };
+    // (two entries per lane and trip, both gathers requested before either is accumulated, measured slower:
+    // 2.66 against 2.27 ms at 64 particles per cell - the registers it needs cost a CTA per SM)
+    for (int j = s + lane; j < e; j += 32) {
+        Rec R0;
+        fetch(j, R0);
+        accumulate(R0);
+    }
+    double *b = block + (size_t)c * nMom;
+    if (lane == 0) b[0] = (double)(e - s);
+    reduceStoreGroups<NACC, 0>(a, lane, b + 1);
+}
+
+template <int NPHI>
+__global__ void __launch_bounds__(256, MOM_MIN_BLOCKS(NPHI)) k_moments(DMesh M, PState S, const uint32_t *perm, const int *cellStart, const int *cellEnd,
+                          double *block, int nMom) {
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
     for (int r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < M.nCells; r += gridDim.x * warpsPerBlock) {
         const int c = M.cellOfRank[r];   // cells in processing order: neighbouring segments of the sorted arrays
-        const int s = cellStart[c], e = cellEnd[c];
-        double a[NACC];
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.0;
-        for (int j = s + lane; j < e; j += 32) {
-            const int slot = (int)perm[j];
-            const V3 U = mk(S.ux[slot], S.uy[slot], S.uz[slot]);
-            double mpd = S.m[slot];
-            if (M.axisym) mpd = massPerDepth(M, mk(S.px[slot], S.py[slot], S.pz[slot]), mpd);
-            mpd = S.eta[slot] * mpd;
-            a[0] += mpd;
-            a[1] += mpd / S.rho[slot];
-            a[2] += mpd * U.x; a[3] += mpd * U.y; a[4] += mpd * U.z;
-            double ph[NPHI > 0 ? NPHI : 1];
-#pragma unroll
-            for (int k = 0; k < NPHI; ++k) { ph[k] = S.phi[k][slot]; a[5 + k] += mpd * ph[k]; }
-            int pp = 0;
-#pragma unroll
-            for (int k = 0; k < NPHI; ++k)
-#pragma unroll
-                for (int l = k; l < NPHI; ++l, ++pp) a[5 + NPHI + pp] += mpd * ph[k] * ph[l];
-            double *uu = a + 5 + NPHI + NCOV;
-            uu[0] += mpd * (U.x * U.x); uu[1] += mpd * (U.x * U.y); uu[2] += mpd * (U.x * U.z);
-            uu[3] += mpd * (U.y * U.y); uu[4] += mpd * (U.y * U.z); uu[5] += mpd * (U.z * U.z);
-#pragma unroll
-            for (int k = 0; k < NPHI; ++k) {
-                const double mp = mpd * ph[k];
-                uu[6 + 3 * k] += mp * U.x; uu[7 + 3 * k] += mp * U.y; uu[8 + 3 * k] += mp * U.z;
-            }
-        }
-        double *b = block + (size_t)c * nMom;
-        if (lane == 0) b[0] = (double)(e - s);
-        reduceStoreGroups<NACC, 0>(a, lane, b + 1);
+        momentsOfSegment<NPHI>(M, S, perm, c, cellStart[c], cellEnd[c], lane, block, nMom);
+    }
+}
+
+// k_cs_order and k_moments in one pass over the cells (counting-sort path without pair mixing): the warp that has put
+// a cell's segment into its canonical order takes the cell's moments from it straight away - one launch, one read of
+// the per-cell tables and the segment still in L1 instead of a second pass over the permutation
+template <int NPHI>
+__global__ void __launch_bounds__(256, MOM_MIN_BLOCKS(NPHI)) k_order_moments(DMesh M, PState S, const int *rankStart, const int *count, int *cellStart,
+                                int *cellEnd, uint32_t *perm, uint32_t *scratch, double *block, int nMom) {
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    for (int r = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < M.nCells; r += gridDim.x * warpsPerBlock) {
+        const int c = M.cellOfRank[r];
+        const int s = rankStart[r], n = count[r];
+        if (lane == 0) { cellStart[c] = s; cellEnd[c] = s + n; }
+        orderSegment(perm + s, n, lane, scratch + s);
+        __syncwarp();   // the segment as the other lanes have written it
+        momentsOfSegment<NPHI>(M, S, perm, c, s, s + n, lane, block, nMom);
     }
 }
 
@@ -437,14 +480,15 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
                     }
             }
         };
-        auto hashOf = [&](uint32_t id, int r) {
+        auto hashOf = [&](uint64_t id, int r) {
             uint32_t o[4];
             rngWords(key, id, step, RNG_MIX_HASH, (uint32_t)r, o);
             return o[0];
         };
         for (int r = 0; r < R; ++r) {
             if (n <= 128) {
-                uint32_t hv[4], idv[4];
+                uint32_t hv[4];
+                uint64_t idv[4];
                 int slotv[4], rkv[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
@@ -452,7 +496,7 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
                     const bool valid = j < e;
                     const int slot = valid ? (int)perm[j] : 0;
                     slotv[it] = slot;
-                    idv[it] = valid ? S.id[slot] : 0xffffffffu;
+                    idv[it] = valid ? S.id[slot] : ~0ull;
                     hv[it] = valid ? hashOf(idv[it], r) : 0xffffffffu;
                     rkv[it] = 0;
                 }
@@ -461,7 +505,7 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
                     const int nr = min(32, n - 32 * rr);   // warp-uniform
                     for (int l = 0; l < nr; ++l) {
                         const uint32_t hq = __shfl_sync(0xffffffffu, hv[rr], l);
-                        const uint32_t iq = __shfl_sync(0xffffffffu, idv[rr], l);
+                        const uint64_t iq = __shfl_sync(0xffffffffu, idv[rr], l);
 #pragma unroll
                         for (int it = 0; it < 4; ++it) rkv[it] += (hq < hv[it] || (hq == hv[it] && iq < idv[it])) ? 1 : 0;
                     }
@@ -477,7 +521,8 @@ __global__ void __launch_bounds__(MIX_WARPS * 32) k_mix_curl(DMesh M, pdfb200_pa
                 __syncwarp();
                 for (int j = s + lane; j < e; j += 32) {
                     const int slot = (int)perm[j];
-                    const uint32_t h = hashScratch[j], id = S.id[slot];
+                    const uint32_t h = hashScratch[j];
+                    const uint64_t id = S.id[slot];
                     int rk = 0;
                     for (int q = s; q < e; ++q) {
                         const uint32_t hq = hashScratch[q];
@@ -513,7 +558,7 @@ __global__ void k_seed(DMesh M, pdfb200_params P, PState S, RngKey key, int rank
     double sumR = 0.;
     size_t o = (size_t)c * nLoc;
     for (int j = rank; j < Npc; j += nRanks, ++o) {
-        const uint32_t idx = (uint32_t)((long long)c * Npc + j);
+        const uint64_t idx = (uint64_t)((long long)c * Npc + j);
         const V3 pos = randomPointInCell(M, key, c, idx, RNG_SEED, 0);
         double g0, g1, g2, g3;
         rngNormal2(key, idx, 0, RNG_SEED, 1000000, g0, g1);
@@ -786,7 +831,7 @@ __global__ void k_inject(DMesh M, pdfb200_params P, int pass, PState S, RngKey k
                             S.m[slot] = mm; S.omega[slot] = 0; S.rho[slot] = 0; S.eta[slot] = eta;
                             for (int k = 0; k < P.nPhi; ++k) S.phi[k][slot] = Phi_b[(size_t)k * M.nBnd + bf];
                             S.cell[slot] = cellI; S.tet[slot] = tet;
-                            S.id[slot] = sc->nextId + (uint32_t)(offset[bf] + made + lane) * (uint32_t)nRanks;
+                            S.id[slot] = sc->nextId + (uint64_t)(offset[bf] + made + lane) * (uint64_t)nRanks;
                             injPatchTail[tailIdx] = BF_PATCH(info);
                         }
                     }
@@ -814,8 +859,7 @@ __global__ void k_inject_finish(int nBnd, const int *total, StepScalars *sc, lon
     if ((long long)sc->nSlots + sc->nTail + t > capacity) { sc->overflow = 1; t = max(0, (int)(capacity - sc->nSlots - sc->nTail)); }
     sc->nTail += t;
     // ids are 32 bits wide: running out of them must stop the run, not hand two particles one random stream
-    if ((unsigned long long)sc->nextId + (unsigned long long)t * (unsigned long long)nRanks > 0xffffffffull) sc->overflow = 3;
-    sc->nextId += (uint32_t)t * (uint32_t)nRanks;
+    sc->nextId += (uint64_t)t * (uint64_t)nRanks;
 }
 
 // ---------------------------------------------------------------------------
@@ -874,9 +918,9 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
             // cloneParticles (:1107-1139): the n heaviest by eta*m (see cloneWeight; ties by id) are split
             const int n = nClone[c];
             // the clones themselves are created by k_nc_clone, one thread per task
-            auto makeClone = [&](int slot, int rk, uint32_t) { cloneSrc[cloneOffset[c] + rk] = (uint32_t)slot; };
+            auto makeClone = [&](int slot, int rk, uint64_t) { cloneSrc[cloneOffset[c] + rk] = (uint32_t)slot; };
             if (inRegs) {
-                double keyv[4]; uint32_t idv[4]; int slotv[4], rkv[4];
+                double keyv[4]; uint64_t idv[4]; int slotv[4], rkv[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int j = s + lane + 32 * it;
@@ -884,7 +928,7 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
                     const int slot = valid ? (int)perm[j] : 0;
                     slotv[it] = slot;
                     keyv[it] = valid ? cloneWeight(S.eta[slot], S.m[slot]) : -PDF_VGREAT;
-                    idv[it] = valid ? S.id[slot] : 0xffffffffu;
+                    idv[it] = valid ? S.id[slot] : ~0ull;
                     rkv[it] = 0;
                 }
                 // rank every entry against all others through warp shuffles
@@ -893,7 +937,7 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
                     const int nr = min(32, cnt - 32 * r);   // warp-uniform
                     for (int l = 0; l < nr; ++l) {
                         const double kq = __shfl_sync(0xffffffffu, keyv[r], l);
-                        const uint32_t iq = __shfl_sync(0xffffffffu, idv[r], l);
+                        const uint64_t iq = __shfl_sync(0xffffffffu, idv[r], l);
 #pragma unroll
                         for (int it = 0; it < 4; ++it) rkv[it] += (kq > keyv[it] || (kq == keyv[it] && iq < idv[it])) ? 1 : 0;
                     }
@@ -911,7 +955,7 @@ __global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *
                 for (int j = s + lane; j < e; j += 32, ++it) {
                     const int slot = (int)perm[j];
                     const double key_i = cloneWeight(S.eta[slot], S.m[slot]);
-                    const uint32_t id_i = S.id[slot];
+                    const uint64_t id_i = S.id[slot];
                     int rk = 0;
                     for (int q = s; q < e; ++q) {
                         const int sq = (int)perm[q];
@@ -1027,7 +1071,7 @@ __global__ void k_nc_clone(DMesh M, pdfb200_params P, PState S, const uint32_t *
         S.m[dst] = mHalf; S.omega[dst] = S.omega[slot]; S.rho[dst] = S.rho[slot]; S.eta[dst] = S.eta[slot];
         for (int k = 0; k < P.nPhi; ++k) S.phi[k][dst] = S.phi[k][slot];
         S.cell[dst] = c; S.tet[dst] = locateTet(M, pos, c);
-        S.id[dst] = sc->nextId + (uint32_t)t * (uint32_t)nRanks;
+        S.id[dst] = sc->nextId + (uint64_t)t * (uint64_t)nRanks;
         if (M.axisym) {
             const double d = massPerDepth(M, pos, mHalf) + massPerDepth(M, posOld, mHalf) - massPerDepth(M, posOld, mOld);
             cloneDelta[(size_t)t * K1_NC1] = d;
@@ -1179,8 +1223,7 @@ __global__ void k_step_end(StepScalars *sc, DevReport *rp, pdfb200_params P, int
     const int nCl = ncCounts ? ncCounts[0] : 0;
     sc->nTail = nCl;
     sc->nInjStart = nCl;
-    if ((unsigned long long)sc->nextId + (unsigned long long)nCl * (unsigned long long)nRanksForId > 0xffffffffull) sc->overflow = 3;
-    sc->nextId += (uint32_t)nCl * (uint32_t)nRanksForId;
+    sc->nextId += (uint64_t)nCl * (uint64_t)nRanksForId;
     sc->anyLost = rp->v[RP_K1SUM + ACC_N_LOST] > 0 ? 1 : 0;
     sc->nLostTotal += (long long)rp->v[RP_K1SUM + ACC_N_LOST];
 }
@@ -1260,7 +1303,7 @@ void Cloud::allocParticles() {
         allocD(s.m); allocD(s.omega); allocD(s.rho); allocD(s.eta);
         for (int k = 0; k < PDFB200_MAX_PHI; ++k) { s.phi[k] = nullptr; if (k < prm.nPhi) allocD(s.phi[k]); }
         allocI(s.cell); allocI(s.tet);
-        int *idp; allocI(idp); s.id = reinterpret_cast<uint32_t *>(idp);
+        double *idp; allocD(idp); s.id = reinterpret_cast<uint64_t *>(idp);   // 64-bit ids: a column as wide as a double
     }
     keysA.alloc(cap); keysB.alloc(cap); valsB.alloc(cap); iota.alloc(cap);
     LAUNCH(this, k_iota, gridFor((long long)cap, 256), 256, 0, iota.p, (int)cap);
@@ -1311,7 +1354,7 @@ void Cloud::seedParticles() {
     LAUNCH(this, k_init_models, gridFor(n, 128), 128, 0, dm, prm, S[cur], (int)n, nodeMid.p, cellAux.p, cellAuxStride, scal.p, tablesOf(*this));
     StepScalars h = *hScal;
     h.nSorted = 0; h.nTail = (int)n; h.nInjStart = (int)n; h.nSlots = 0; h.anyLost = 0;
-    h.nextId = (uint32_t)((long long)nCells * Npc + rank);
+    h.nextId = (uint64_t)((long long)nCells * Npc + rank);
     *hScal = h;
     CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1328,9 +1371,9 @@ __global__ void k_check_labels(DMesh M, int n, const int *cell, const int *tet, 
     if (!ok) atomicAdd(bad, 1);
 }
 // ids when the caller gives none: running index, interleaved over the ranks so that no two ranks share one
-__global__ void k_default_ids(int n, uint32_t *id, int rank, int nRanks) {
+__global__ void k_default_ids(int n, uint64_t *id, int rank, int nRanks) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) id[i] = (uint32_t)i * (uint32_t)nRanks + (uint32_t)rank;
+    if (i < n) id[i] = (uint64_t)i * (uint64_t)nRanks + (uint64_t)rank;
 }
 
 void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
@@ -1354,14 +1397,13 @@ void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
     // the next free id: above every id in use and congruent to the rank (ids advance in steps of nRanks)
     uint64_t idEnd = 0;
     if (p.id) {
-        CUDA_CHECK(cudaMemcpy(s.id, p.id, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(s.id, p.id, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
         for (int64_t i = 0; i < n; ++i) idEnd = std::max<uint64_t>(idEnd, (uint64_t)p.id[i] + 1);
     } else {
         if (n > 0) LAUNCH(this, k_default_ids, gridFor(n, 256), 256, 0, (int)n, s.id, rank, nRanks);
         idEnd = (uint64_t)n * (uint64_t)nRanks;
     }
     const uint64_t nextId64 = (idEnd + (uint64_t)nRanks - 1) / (uint64_t)nRanks * (uint64_t)nRanks + (uint64_t)rank;
-    if (nextId64 > 0xffffffffull) throw std::invalid_argument("upload_particles: particle ids exhaust the 32-bit id space");
     if (p.tet) CUDA_CHECK(cudaMemcpy(s.tet, p.tet, n * sizeof(int), cudaMemcpyHostToDevice));
     if (n > 0) {
         // labels are validated before any kernel indexes a mesh table with them (cell first: the locate kernel needs it)
@@ -1375,7 +1417,7 @@ void Cloud::uploadParticles(int64_t n, const pdfb200_particles &p) {
     }
     StepScalars h = *hScal;
     h.nSorted = 0; h.nTail = (int)n; h.nInjStart = (int)n; h.nSlots = 0; h.anyLost = 0;
-    h.nextId = (uint32_t)nextId64;
+    h.nextId = nextId64;
     *hScal = h;
     CUDA_CHECK(cudaMemcpyAsync(scal.p, hScal, sizeof(StepScalars), cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1402,6 +1444,13 @@ __global__ void k_gather_d(int n, int nSorted, int nSlots, const uint32_t *perm,
     if (alive) alive[i] = cell[slot] >= 0;
 }
 __global__ void k_gather_i(int n, int nSorted, int nSlots, const uint32_t *perm, const int *src, int *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = i < nSorted ? (int)perm[i] : nSlots + (i - nSorted);
+    dst[i] = src[slot];
+}
+
+__global__ void k_gather_u64(int n, int nSorted, int nSlots, const uint32_t *perm, const uint64_t *src, uint64_t *dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int slot = i < nSorted ? (int)perm[i] : nSlots + (i - nSorted);
@@ -1446,7 +1495,12 @@ void Cloud::downloadParticles(int64_t maxn, pdfb200_particles &out, int64_t *nOu
     for (int k = 0; k < prm.nPhi; ++k) { col(s.phi[k]); put(out.Phi[k], 1, 0); }
     coli(s.cell); if (out.cell) for (int64_t k = 0; k < na; ++k) out.cell[k] = hi[aliveIdx[k]];
     coli(s.tet); if (out.tet) for (int64_t k = 0; k < na; ++k) out.tet[k] = hi[aliveIdx[k]];
-    coli(reinterpret_cast<const int *>(s.id)); if (out.id) for (int64_t k = 0; k < na; ++k) out.id[k] = (uint32_t)hi[aliveIdx[k]];
+    if (out.id) {
+        // 64-bit ids: gathered as 8-byte words into the double staging buffer, copied bit for bit
+        if (n) { LAUNCH(this, k_gather_u64, G, B, 0, n, nSorted, nSlots, perm, s.id, reinterpret_cast<uint64_t *>(d.p)); d.download(h.data(), n, stream); }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int64_t k = 0; k < na; ++k) std::memcpy(&out.id[k], &h[aliveIdx[k]], sizeof(uint64_t));
+    }
     *nOut = na;
 }
 
@@ -1459,6 +1513,27 @@ static void launchMoments(Cloud &c, const PState &S, const uint32_t *perm) {
     const int G = std::min(gridFor(c.nCells, warps), c.numSMs * 16);
     LAUNCH(&c, k_moments<N>, G, B, 0, c.dm, S, perm, c.cellStart.p, c.cellEnd.p, c.momentBlock.p, c.nMom);
 }
+// segment ordering of the counting sort + moments in one kernel (k_order_moments)
+template <int N>
+static void launchOrderMoments(Cloud &c, const PState &S) {
+    const int B = 256, warps = B / 32;
+    const int G = std::min(gridFor(c.nCells, warps), c.numSMs * 16);
+    LAUNCH(&c, k_order_moments<N>, G, B, 0, c.dm, S, c.csStart.p, c.csCount.p, c.cellStart.p, c.cellEnd.p, c.valsB.p, c.keysB.p, c.momentBlock.p, c.nMom);
+}
+template <template <int> class F, class... Args>
+static void dispatchNPhi(int nPhi, Args &&...args) {
+    switch (nPhi) {
+    case 0: F<0>::run(args...); break;
+    case 1: F<1>::run(args...); break;
+    case 2: F<2>::run(args...); break;
+    case 3: F<3>::run(args...); break;
+    case 4: F<4>::run(args...); break;
+    case 5: F<5>::run(args...); break;
+    default: F<6>::run(args...); break;
+    }
+}
+template <int N> struct MomentsLauncher { static void run(Cloud &c, const PState &S, const uint32_t *perm) { launchMoments<N>(c, S, perm); } };
+template <int N> struct OrderMomentsLauncher { static void run(Cloud &c, const PState &S) { launchOrderMoments<N>(c, S); } };
 
 // Everything one step launches, in order, on the library's stream. Nothing in here waits for the device or reads a
 // device value on the host (entry counts, time step, overflow flags all stay on the device; the step's report goes
@@ -1523,6 +1598,8 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
     cur ^= 1;
 
     // ---- sort by cell + segment bounds ----
+    static const bool fuseEnv = [] { const char *e = std::getenv("PDFB200_FUSE_ORDER"); return !e || std::atoi(e) != 0; }();
+    const bool fusedOrder = !radixPath && fuseEnv && !(prm.mixingModel == PDFB200_MIXING_MODCURL && prm.nMixed > 0);
     if (!radixPath) {
         // counting sort by cell (see k_cs_*): same permutation as the stable radix sort
         CUDA_CHECK(cudaMemsetAsync(csCount.p, 0, nCells * sizeof(int), stream));
@@ -1532,8 +1609,11 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
         scanInts(*this, nCells, csCount.p, csStart.p, scanTmp.p + 2);
         LAUNCH(this, k_cs_scatter, gS, 256, 0, scal.p, keysA.p, csStart.p, csCursor.p, valsB.p);
         mark(3);
-        LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, csStart.p, csCount.p, cellOfRank.p, cellStart.p,
-               cellEnd.p, valsB.p, keysB.p);
+        // the segments are put into their canonical order by the moments kernel itself (k_order_moments) unless the
+        // pair mixing has to run on the ordered segments first
+        if (!fusedOrder)
+            LAUNCH(this, k_cs_order, std::min(gridFor(nCells, 8), numSMs * 16), 256, 0, nCells, csStart.p, csCount.p, cellOfRank.p, cellStart.p,
+                   cellEnd.p, valsB.p, keysB.p);
         LAUNCH(this, k_cs_finish, 1, 32, 0, scanTmp.p + 2, scal.p);
     } else {
         // radix sort by (cell, tet): the library call needs the entry count on the host, so this path waits for it
@@ -1561,15 +1641,8 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
     } else {
         CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_MIXDELTA, 0, K1_MAXCONS * sizeof(double), stream));
     }
-    switch (prm.nPhi) {
-    case 0: launchMoments<0>(*this, S[cur], valsB.p); break;
-    case 1: launchMoments<1>(*this, S[cur], valsB.p); break;
-    case 2: launchMoments<2>(*this, S[cur], valsB.p); break;
-    case 3: launchMoments<3>(*this, S[cur], valsB.p); break;
-    case 4: launchMoments<4>(*this, S[cur], valsB.p); break;
-    case 5: launchMoments<5>(*this, S[cur], valsB.p); break;
-    default: launchMoments<6>(*this, S[cur], valsB.p); break;
-    }
+    if (fusedOrder) dispatchNPhi<OrderMomentsLauncher>(prm.nPhi, *this, S[cur]);
+    else dispatchNPhi<MomentsLauncher>(prm.nPhi, *this, S[cur], (const uint32_t *)valsB.p);
     mark(4);
     // ---- cross-GPU sum of the moment block ----
     float arMs = 0;
@@ -1652,6 +1725,8 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
     size_t k1JitSmem = K1_SMEM_BYTES;
     if (k1Jit) {
         k1Blocks = K1_JIT_MIN_BLOCKS;
+        // the specialised kernel carries the sum rows of this case's conserved scalars only (evolve_kernel.cuh, K1_COMPACT_ACC)
+        k1JitSmem = (size_t)K1_SMEM_ROWS(prm.nConserved) * K1_THREADS * sizeof(double);
         if (const char *x = std::getenv("PDFB200_K1_BLOCKS")) k1Blocks = std::max(1, std::atoi(x));   // with -DK1_MIN_BLOCKS in PDFB200_JIT_FLAGS
         if (const char *x = std::getenv("PDFB200_K1_SMEM")) k1JitSmem = (size_t)std::atol(x);          // with flags that change K1_SMEM_BYTES
     }
@@ -1725,7 +1800,7 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
             }
             const int ov = (int)v[RP_OVERFLOW];
             if (ov == 2) throw std::runtime_error("evolve: more than " + std::to_string(lostList.n) + " particles lost in one step");
-            if (ov == 3) throw std::runtime_error("evolve: the 32-bit particle id space is exhausted");
+
             if (ov) throw std::length_error("evolve: particle capacity exceeded");
             nParticlesHost = (int64_t)v[RP_N_SORTED] + (int64_t)v[RP_N_CLONED] - (int64_t)v[RP_N_ELIMINATED];
             nSlotsHost = (int64_t)v[RP_N_ENTRIES];

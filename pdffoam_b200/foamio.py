@@ -143,7 +143,7 @@ def read_lagrangian(case_dir: str, time_name: str, scalar_names: Sequence[str], 
              Phi=[must(name) for name in scalar_names])
     pid = os.path.join(d, "origId")
     if os.path.exists(pid):
-        P["id"] = read_field(pid).astype(np.uint32)
+        P["id"] = read_field(pid).astype(np.uint64)
     return P
 
 

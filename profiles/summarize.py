@@ -84,6 +84,21 @@ def kernel(rep, prefix):
                 lines.append((cur, int(x[0]), x[1].strip(), int(x[6]), int(x[7])))
             except ValueError:
                 pass
+    # a kernel compiled at run time from the sources embedded in the library carries line numbers but no readable
+    # file: take the text from the source tree (the embedded copy is made from it at build time)
+    import os
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pdffoam_b200", "csrc")
+    cache = {}
+    def text(fn, ln, have):
+        if have and not have.startswith("<Unable"):
+            return have
+        if fn not in cache:
+            try:
+                cache[fn] = open(os.path.join(csrc, fn)).read().splitlines()
+            except OSError:
+                cache[fn] = []
+        return cache[fn][ln - 1].strip() if 0 < ln <= len(cache[fn]) else have
+    lines = [(l[0], l[1], text(l[0], l[1], l[2]), l[3], l[4]) for l in lines]
     ts, te = sum(l[3] for l in lines) or 1, sum(l[4] for l in lines) or 1
     with open(prefix + "_lines.csv", "w", newline="") as f:
         w = csv.writer(f)

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from pdffoam_b200 import capi, cases
+from parity_util import compare_particles
 
 pytestmark = pytest.mark.gpu
 
@@ -72,7 +73,7 @@ def test_default_ids_and_next_id(device_lib):
     case = cases.synthetic_box(4, 3, 2, ppc=10, closed=True, number_control=True)
     case.params.deltaT0 = 2e-3
     P = case.random_particles(10, seed=4)
-    P["id"] = (np.arange(P["m"].size, dtype=np.uint32) * 7 + 1000).astype(np.uint32)
+    P["id"] = (np.arange(P["m"].size, dtype=np.uint64) * 7 + 1000).astype(np.uint64)
     # thin out a few cells so that number control clones
     keep = ~np.isin(P["cell"], [1, 2, 3]) | (np.arange(P["m"].size) % 3 == 0)
     Q = {k: (v[keep] if k != "Phi" else [a[keep] for a in v]) for k, v in P.items()}
@@ -88,7 +89,7 @@ def test_default_ids_and_next_id(device_lib):
     R = dict(Q); R.pop("id")
     h2 = case.make_cloud(device_lib)
     h2.upload_particles(R)
-    assert np.array_equal(np.sort(h2.download_particles()["id"]), np.arange(Q["m"].size, dtype=np.uint32))
+    assert np.array_equal(np.sort(h2.download_particles()["id"]), np.arange(Q["m"].size, dtype=np.uint64))
 
 
 def test_stage_and_commit_equal_a_plain_upload(device_lib):
@@ -115,3 +116,32 @@ def test_stage_and_commit_equal_a_plain_upload(device_lib):
     ca, cb = a.download_cell_fields(), b.download_cell_fields()
     for k in ("rho", "U", "k", "Tau"):
         assert np.array_equal(ca[k], cb[k]), k
+
+
+def test_ids_beyond_32_bits(device_lib, oracle_lib):
+    """Particle ids are 64 bits wide (a 1e9-particle cloud with number control runs through 2^32 ids in a
+    few hundred steps). Ids above 2^32 key their own random streams - the same ones on the device and in the oracle -
+    survive the step, and the particles created afterwards are numbered above them."""
+    case = cases.synthetic_box(6, 4, 3, ppc=16, closed=False, number_control=True)
+    case.params.deltaT0 = 2e-3
+    P = case.random_particles(16, seed=3)
+    base = (1 << 33) + 12345
+    P["id"] = (np.arange(P["m"].size, dtype=np.uint64) + np.uint64(base))
+    dev, ora = case.make_cloud(device_lib, device=0), case.make_cloud(oracle_lib)
+    dev.upload_particles(P); ora.upload_particles(P)
+    assert dev.id_counter() == ora.id_counter() == base + P["m"].size
+    for step in range(4):
+        rd, ro = dev.evolve(1)[0], ora.evolve(1)[0]
+        compare_particles(dev.download_particles(), ora.download_particles(), rtol=1e-10, atol=1e-12, what=f"step {step}")
+    Q = dev.download_particles()
+    assert Q["id"].dtype == np.uint64 and Q["id"].min() >= base
+    assert np.setdiff1d(Q["id"], P["id"]).size > 0, "the open box injects and clones: new ids expected"
+    assert dev.id_counter() == ora.id_counter() > base + P["m"].size
+    # the high word is part of the stream key: the same particles with the low words alone evolve differently
+    low = case.make_cloud(device_lib, device=0)
+    P2 = dict(P); P2["id"] = P["id"] - np.uint64(1 << 33)
+    low.upload_particles(P2); low.evolve(1)
+    hi1 = case.make_cloud(device_lib, device=0); hi1.upload_particles(P); hi1.evolve(1)
+    a, b = low.download_particles(), hi1.download_particles()
+    n = min(a["U"].shape[0], b["U"].shape[0])
+    assert not np.allclose(np.sort(a["U"][:n, 0]), np.sort(b["U"][:n, 0]))

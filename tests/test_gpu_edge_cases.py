@@ -56,7 +56,7 @@ def test_crowded_cell(device_lib, oracle_lib):
     idx = np.nonzero(P["cell"] == 5)[0]
     dup = np.tile(idx, 8)                                   # 40 + 320 particles in cell 5
     Q = {k: (np.concatenate([v, v[dup]]) if k != "Phi" else [np.concatenate([a, a[dup]]) for a in v]) for k, v in P.items()}
-    Q["id"] = np.arange(Q["m"].shape[0], dtype=np.uint32)
+    Q["id"] = np.arange(Q["m"].shape[0], dtype=np.uint64)
     lo, hi = case.info["cell_lo"][5], case.info["cell_hi"][5]
     Q["pos"] = Q["pos"].copy()
     Q["pos"][-dup.size:] = lo + rng.uniform(0.05, 0.95, size=(dup.size, 3)) * (hi - lo)

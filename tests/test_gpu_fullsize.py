@@ -69,14 +69,14 @@ def test_large_closed_box_particles_stay_consistent(device_lib):
     n0 = P0["id"].shape[0]
     assert n0 == nx * ny * nz * 64
     o0 = np.argsort(P0["id"])
-    assert np.array_equal(P0["id"][o0], np.arange(n0, dtype=np.uint32))
+    assert np.array_equal(P0["id"][o0], np.arange(n0, dtype=np.uint64))
     m0 = P0["m"][o0].copy()
     del P0
     reps = h.evolve(5)
     assert all(r.nLost == 0 and r.nDeleted == 0 and r.nInjected == 0 for r in reps)
     P = h.download_particles()
     o = np.argsort(P["id"])
-    assert np.array_equal(P["id"][o], np.arange(n0, dtype=np.uint32)), "ids not preserved"
+    assert np.array_equal(P["id"][o], np.arange(n0, dtype=np.uint64)), "ids not preserved"
     assert np.array_equal(P["m"][o], m0), "particle masses changed in a closed box without number control"
     lo, hi = case.info["cell_lo"][P["cell"]], case.info["cell_hi"][P["cell"]]
     tol = 1e-12

@@ -91,7 +91,7 @@ def test_particle_number_control(device_lib, oracle_lib):
     Q = {k: (v[keep] if k != "Phi" else [a[keep] for a in v]) for k, v in P.items()}
     dup = np.nonzero(np.isin(Q["cell"], np.arange(1, case.mesh.n_cells, 7)))[0]
     R = {k: (np.concatenate([v, v[dup]]) if k != "Phi" else [np.concatenate([a, a[dup]]) for a in v]) for k, v in Q.items()}
-    R["id"] = np.arange(R["m"].shape[0], dtype=np.uint32)
+    R["id"] = np.arange(R["m"].shape[0], dtype=np.uint64)
     R["pos"] = R["pos"].copy()
     R["pos"][-dup.size:] += 1e-4 * (rng.random((dup.size, 3)) - 0.5)
     R["m"] = R["m"] * rng.uniform(0.5, 1.5, size=R["m"].shape[0])

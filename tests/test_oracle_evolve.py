@@ -206,7 +206,7 @@ def test_clone_conserves_mass_exactly_and_eliminate_in_expectation(oracle_lib):
 
     # too many: 40 per cell -> eliminate; mass conserved in expectation over seeds
     many = {k: (np.concatenate([v, v]) if k != "Phi" else [np.concatenate([a, a]) for a in v]) for k, v in base.items()}
-    many["id"] = np.arange(many["m"].size, dtype=np.uint32)
+    many["id"] = np.arange(many["m"].size, dtype=np.uint64)
     ratios = []
     for seed in range(40):
         case.params.seed = 1000 + seed
