@@ -304,6 +304,12 @@ int pdfb200_evolve(pdfb200_cloud *cloud, int32_t nSteps, pdfb200_step_report *re
 
 /* Cell fields of updateCloudPDF (mcParticleCloud.C:824-1009) back to the host. */
 int pdfb200_download_cell_fields(pdfb200_cloud *cloud, pdfb200_cell_fields *out);
+/* The same without waiting: the copies are queued on a stream of their own behind everything issued so far, into host
+ * buffers that should be page-locked; pdfb200_sync_downloads() returns when they have landed. The next evolve() may be
+ * called at once - the step that overwrites the fields (updateCloudPDF) waits on the device for the copies - so the
+ * read-back of step n (rho for the FV side, pdfSimpleFoam/createFields.H:18) runs under step n+1.                     */
+int pdfb200_download_cell_fields_async(pdfb200_cloud *cloud, const pdfb200_cell_fields *out);
+int pdfb200_sync_downloads(pdfb200_cloud *cloud);
 /* Restart: the time-averaged moment fields of a previous run instead of init_moments — the mMoment, VMoment,
  * UMoment, UUMoment, <Phi>Moment and <Phi><Phi>Moment fields that mcParticleCloud's constructor reads with
  * READ_IF_PRESENT (mcParticleCloud.C:339-517) and checkMoments() accepts only as a complete set (:739-820:

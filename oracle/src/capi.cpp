@@ -201,6 +201,14 @@ int pdforacle_upload_particles(pdforacle_cloud *h, int64_t n, const pdfb200_part
     ORACLE_CATCH
 }
 
+// the CPU has nothing to overlap: the "asynchronous" download copies at once
+int pdforacle_download_cell_fields(pdforacle_cloud *h, pdfb200_cell_fields *o);
+int pdforacle_download_cell_fields_async(pdforacle_cloud *h, const pdfb200_cell_fields *o) {
+    pdfb200_cell_fields tmp = *o;
+    return pdforacle_download_cell_fields(h, &tmp);
+}
+int pdforacle_sync_downloads(pdforacle_cloud *) { return PDFB200_OK; }
+
 int64_t pdforacle_num_particles(pdforacle_cloud *h) { return (int64_t)h->c.particles.size(); }
 
 int pdforacle_download_particles(pdforacle_cloud *h, int64_t maxn, pdfb200_particles *out, int64_t *n) {

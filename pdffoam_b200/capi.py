@@ -185,7 +185,7 @@ class PdfError(RuntimeError):
 API_SYMBOLS = [
     "last_error", "create", "destroy", "set_params", "set_flamelet_tables", "set_autoignition_tables", "upload_fv_fields", "stage_fv_fields", "commit_fv_fields",
     "upload_cloud_fields", "upload_poscorr_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
-    "download_particles", "evolve", "download_cell_fields", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
+    "download_particles", "evolve", "download_cell_fields", "download_cell_fields_async", "sync_downloads", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
     "kernel_launches", "last_evolve_ms", "profile", "set_graph_mode", "jit_source", "jit_compile", "rng_probe",
 ]
@@ -225,6 +225,8 @@ class Library:
         f("download_particles").argtypes = [vp, C.c_int64, C.POINTER(ParticlesStruct), C.POINTER(C.c_int64)]
         f("evolve").argtypes = [vp, C.c_int32, C.POINTER(StepReport)]
         f("download_cell_fields").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("download_cell_fields_async").argtypes = [vp, C.POINTER(CellFieldsStruct)]
+        f("sync_downloads").argtypes = [vp]
         f("set_autoignition_tables").argtypes = [vp, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, C.c_int32, C.POINTER(c_double_p)]
         f("upload_moments").argtypes = [vp, C.POINTER(CellFieldsStruct)]
         f("stage_fv_fields").argtypes = [vp, C.POINTER(FvFields)]
@@ -494,6 +496,16 @@ class CloudHandle:
         s.rho = _dp(out)
         self.lib.check(self.lib.fn("download_cell_fields")(self.h, C.byref(s)), "download_cell_fields")
         return out
+
+    def download_rho_async(self, out: np.ndarray):
+        """pdfb200_download_cell_fields_async for the mean density: queued behind the steps issued so far, lands in `out`
+        (a page-locked buffer) while the next evolve() runs; sync_downloads() waits for it."""
+        s = CellFieldsStruct()
+        s.rho = _dp(out)
+        self.lib.check(self.lib.fn("download_cell_fields_async")(self.h, C.byref(s)), "download_cell_fields_async")
+
+    def sync_downloads(self):
+        self.lib.check(self.lib.fn("sync_downloads")(self.h), "sync_downloads")
 
     def download_cell_fields(self, moments: bool = True) -> Dict[str, np.ndarray]:
         nc = self.mesh.n_cells

@@ -40,6 +40,9 @@ Cloud::~Cloud() {
     if (evArA) cudaEventDestroy(evArA);
     if (evArB) cudaEventDestroy(evArB);
     for (auto &e : evMark) if (e) cudaEventDestroy(e);
+    if (dlStream) { cudaStreamSynchronize(dlStream); cudaStreamDestroy(dlStream); }
+    if (evStepDone) cudaEventDestroy(evStepDone);
+    if (evDownloaded) cudaEventDestroy(evDownloaded);
     if (evStaged) cudaEventDestroy(evStaged);
     if (copyStream) cudaStreamDestroy(copyStream);
     if (stream) cudaStreamDestroy(stream);
@@ -220,6 +223,12 @@ int pdfb200_download_particles(pdfb200_cloud *c, int64_t maxn, pdfb200_particles
 }
 int pdfb200_evolve(pdfb200_cloud *c, int32_t nSteps, pdfb200_step_report *reports) { USE_DEVICE(c); return guarded([&] { H(c)->evolve(nSteps, reports); }); }
 int pdfb200_download_cell_fields(pdfb200_cloud *c, pdfb200_cell_fields *o) { USE_DEVICE(c); return guarded([&] { H(c)->downloadCellFields(*o); }); }
+int pdfb200_download_cell_fields_async(pdfb200_cloud *c, const pdfb200_cell_fields *o) {
+    if (!o) { g_err = "download_cell_fields_async: null argument"; return PDFB200_ERR_INVALID; }
+    USE_DEVICE(c);
+    return guarded([&] { H(c)->downloadCellFieldsAsync(*o); });
+}
+int pdfb200_sync_downloads(pdfb200_cloud *c) { USE_DEVICE(c); return guarded([&] { H(c)->syncDownloads(); }); }
 int pdfb200_upload_moments(pdfb200_cloud *c, const pdfb200_cell_fields *m) {
     if (!m) { g_err = "upload_moments: null argument"; return PDFB200_ERR_INVALID; }
     USE_DEVICE(c);

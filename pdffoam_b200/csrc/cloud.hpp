@@ -87,6 +87,11 @@ struct Cloud {
     DBuf<uint8_t> stg_UbFixed, stg_kbFixed;
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evStaged = nullptr;
+    // asynchronous read-back (pdfb200_download_cell_fields_async): own stream, ordered behind the library's stream by
+    // evStepDone; the step that overwrites the cell fields waits for evDownloaded
+    cudaStream_t dlStream = nullptr;
+    cudaEvent_t evStepDone = nullptr, evDownloaded = nullptr;
+    bool downloadPending = false;
     bool stagedPending = false;
     // cloud fields (cell + boundary)
     DBuf<double> rho_c, rho_b, rhoInst_c, pnd_c, pndInst_c, Updf_c, Updf_b, Tau_c, Tau_b, kpdf_c, kpdf_b;
@@ -165,6 +170,9 @@ struct Cloud {
     void uploadFv(const pdfb200_fv_fields &f);
     void stageFv(const pdfb200_fv_fields &f);
     void commitFv();
+    void downloadCellFieldsAsync(const pdfb200_cell_fields &o);
+    void syncDownloads();
+    void orderAfterDownloads();   // makes the library's stream wait for pending asynchronous downloads
     void uploadCloudFields(const pdfb200_cloud_fields &f);
     void uploadPoscorr(const pdfb200_poscorr_fields &f);
     void initMoments();

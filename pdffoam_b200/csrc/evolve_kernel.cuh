@@ -365,6 +365,18 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #ifndef K1_COMPACT_ACC
 #define K1_COMPACT_ACC 1
 #endif
+// 1: the state that is needed again after the first tet walk (position, velocity, mass, local time step) is parked in
+// thread-private shared-memory rows (two conflict-free wavefronts per access) instead of being read again through the
+// permutation (about seven 128-byte lines per warp and column, a third of them hitting L1); needs K1_NPARK = 12
+#ifndef K1_PARK_STATE
+#define K1_PARK_STATE 0
+#endif
+#define PK_UCORR 0
+#define PK_CO 3
+#define PK_POS 4
+#define PK_U 7
+#define PK_M 10
+#define PK_ETA 11
 // dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
 // (the correction velocity and the Courant number, which must survive the tet walks without occupying registers)
 // The specialised kernel carries the sum rows of the conserved scalars the case has, not of K1_MAXCONS (k1_layout.h:
@@ -501,11 +513,21 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 
         // the particle's mass at the start of the step: the stored one plus its share of the mass lost in the
         // previous step (mcParticleCloud.C:1363-1369; particles injected since then get none)
+#if K1_PARK_STATE
+        {
+            double mm = ldInD(A.in.m + slot);
+            if (anyLost && !injected) mm += A.lostShare[cell0];
+            park[PK_M * K1_THREADS] = mm;
+            park[PK_ETA * K1_THREADS] = ldInD(A.in.eta + slot);
+        }
+        auto massIn = [&]() { return park[PK_M * K1_THREADS]; };
+#else
         auto massIn = [&]() {
             double mm = reloadInD(A.in.m + slot);
             if (anyLost && !injected) mm += A.lostShare[cell0];
             return mm;
         };
+#endif
         int status = 0;   // 0 alive, 1 deleted at an open boundary, 2 lost
         // ---- E1 + E2 need the mass and the conserved scalars; both are read again at the mid-point ----
         {
@@ -523,7 +545,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         const double4 n4 = M.bfNormal[bf];
                         const V3 Cf = ld3(M.faceCentres, M.nInternalFaces + bf);
                         const double xp = dot3(mk(n4.x, n4.y, n4.z), Cf - pos);
-                        if (xp < ldInD(A.in.eta + slot) * (Un * deltaT)) {
+                        if (xp < (K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : ldInD(A.in.eta + slot)) * (Un * deltaT)) {
                             const double mpd = massPerDepth(M, pos, m);
                             accS[KACC_MASS_OUT * K1_THREADS] -= mpd;
                             for (int cs = 0; cs < P.nConserved; ++cs)
@@ -545,6 +567,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         loadTet(M, tet, T);
         int cell = cell0;
         V3 ctr = cellCentre(M, cell0);
+#if K1_PARK_STATE
+        park[PK_POS * K1_THREADS] = pos.x; park[(PK_POS + 1) * K1_THREADS] = pos.y; park[(PK_POS + 2) * K1_THREADS] = pos.z;
+#endif
         // ---- E3: position correction gather ----
         V3 Utrack;
         {
@@ -609,7 +634,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             park[0] = Ucorr.x; park[K1_THREADS] = Ucorr.y; park[2 * K1_THREADS] = Ucorr.z;
             // the velocity after E4 ("Uold") equals the stored one except on axisymmetric meshes, where
             // constrainParticle has rotated it: parked in this particle's (still unwritten) output slot
+#if K1_PARK_STATE
+            park[PK_U * K1_THREADS] = U.x; park[(PK_U + 1) * K1_THREADS] = U.y; park[(PK_U + 2) * K1_THREADS] = U.z;
+#else
             if (MESH_AXISYM(M)) { A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z; }
+#endif
         }
         bool reflected = false;
         int reflBf = -1;   // boundary face of the last open-boundary reflection (mcOpenBoundary.C:201-204)
@@ -623,7 +652,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 double stepFraction = 0.0;
                 if (phase == 0 && injected) { double u0, u1; rngUniform2(A.key, A.in.id[slot], step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
                 // phase 0 tracks with the old local time step, phase 1 with the new one (written to out.eta at the mid-point)
-                const double eta = (phase == 0) ? reloadInD(A.in.eta + slot) : reloadD(A.out.eta + i);
+                const double eta = K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : (phase == 0) ? reloadInD(A.in.eta + slot) : reloadD(A.out.eta + i);
                 const double trackTime = (phase == 0) ? eta * (deltaT / 2.) : eta * deltaT;
                 tEnd = (1.0 - stepFraction) * trackTime;
             }
@@ -738,14 +767,21 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     if (phase == 0) {
                         V3 Ur;
                         if (reflected) Ur = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
+                        else if (K1_PARK_STATE) Ur = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
                         else if (MESH_AXISYM(M)) Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
                         else Ur = mk(reloadInD(A.in.ux + slot), reloadInD(A.in.uy + slot), reloadInD(A.in.uz + slot));
                         Ur = reflectVec(Ur, nw);
                         A.out.px[i] = Ur.x; A.out.py[i] = Ur.y; A.out.pz[i] = Ur.z;
                     } else {
+#if K1_PARK_STATE
+                        V3 Ur = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
+                        Ur = reflectVec(Ur, nw);
+                        park[PK_U * K1_THREADS] = Ur.x; park[(PK_U + 1) * K1_THREADS] = Ur.y; park[(PK_U + 2) * K1_THREADS] = Ur.z;
+#else
                         V3 Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
                         Ur = reflectVec(Ur, nw);
                         A.out.ux[i] = Ur.x; A.out.uy[i] = Ur.y; A.out.uz[i] = Ur.z;
+#endif
                     }
                     Utrack = reflectVec(Utrack, nw);
                     reflected = true;
@@ -780,7 +816,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             }
             const double *aux = A.cellAux + (size_t)cell * A.auxStride;
             // the particle's scalars, read again (see reloadD)
-            const double etaOld = reloadInD(A.in.eta + slot);
+            const double etaOld = K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : reloadInD(A.in.eta + slot);
             double Omega = reloadInD(A.in.omega + slot), rho = reloadInD(A.in.rho + slot);
             double phi[NPHI];
 #pragma unroll
@@ -835,7 +871,8 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             }
             // the velocity before the half step ("Uold") and the velocity the half step ended with
             V3 Uold;
-            if (MESH_AXISYM(M)) Uold = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
+            if (K1_PARK_STATE) Uold = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
+            else if (MESH_AXISYM(M)) Uold = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
             else Uold = mk(reloadInD(A.in.ux + slot), reloadInD(A.in.uy + slot), reloadInD(A.in.uz + slot));
             V3 U = Uold;
             if (reflected) U = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
@@ -853,16 +890,20 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 U = U + (((deltaU + 0.5 * Acoef * deltaU * dTp) + diffUap * deltaT) + (Ubefore - UFap) * aux[0] * deltaT);
                 Co = fmax(Co, Omega);
             }
-            park[3 * K1_THREADS] = Co;
+            park[PK_CO * K1_THREADS] = Co;
             // local time stepping
             double eta;
             if (P.localTimeStepping == PDFB200_LTS_CELL) eta = val[NM_ETA];
             else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) eta = fmin(P.CFL / stabilise(deltaT * Co, PDF_VSMALL), P.ltsUpperBound);
             else eta = 1.0;
             A.out.eta[i] = eta;
+#if K1_PARK_STATE
+            park[PK_ETA * K1_THREADS] = eta;   // the second walk and the maxima of the report use the new local time step
+#endif
 
             // ---- E9: mid-point rule from the old position ----
-            pos = mk(reloadInD(A.in.px + slot), reloadInD(A.in.py + slot), reloadInD(A.in.pz + slot));
+            if (K1_PARK_STATE) pos = mk(park[PK_POS * K1_THREADS], park[(PK_POS + 1) * K1_THREADS], park[(PK_POS + 2) * K1_THREADS]);
+            else pos = mk(reloadInD(A.in.px + slot), reloadInD(A.in.py + slot), reloadInD(A.in.pz + slot));
             tet = tet0;
             loadTet(M, tet, T);
             cell = cell0;
@@ -877,7 +918,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 constrainParticle(M, deltaT, pos, U, Ucorr, Utrack);
                 park[0] = Ucorr.x; park[K1_THREADS] = Ucorr.y; park[2 * K1_THREADS] = Ucorr.z;
             }
+#if K1_PARK_STATE
+            park[PK_U * K1_THREADS] = U.x; park[(PK_U + 1) * K1_THREADS] = U.y; park[(PK_U + 2) * K1_THREADS] = U.z;   // written to out.u* at the end
+#else
             A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
+#endif
             reflected = false;   // from here on: "reflected during the full step" (not used further)
         }
         if (status != 0) {
@@ -894,6 +939,15 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             continue;
         }
         // ---- E11: mcOpenBoundary::correct(true) ----
+#if K1_PARK_STATE
+        V3 U = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
+        if (reflBf >= 0) {
+            const double4 n4 = M.bfNormal[reflBf];
+            const V3 reflBV = mk(n4.x, n4.y, n4.z) * A.Un[reflBf];
+            U = U + 2 * reflBV;
+        }
+        A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
+#else
         V3 U = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
         if (reflBf >= 0) {
             const double4 n4 = M.bfNormal[reflBf];
@@ -901,6 +955,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             U = U + 2 * reflBV;
             A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
         }
+#endif
 
         // ---- write back in sorted order (the scalars were written at the mid-point) ----
         A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
@@ -910,7 +965,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {
-            const double m = reloadD(A.out.m + i), eta = reloadD(A.out.eta + i);
+            const double m = K1_PARK_STATE ? park[PK_M * K1_THREADS] : reloadD(A.out.m + i), eta = K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : reloadD(A.out.eta + i);
             const double mpd = massPerDepth(M, pos, m);
             accS[KACC_DM_PLUS * K1_THREADS] += mpd;
             for (int cs = 0; cs < P.nConserved; ++cs)
@@ -921,7 +976,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             accM[ACC_UCORRMAX * K1_THREADS] = fmax(accM[ACC_UCORRMAX * K1_THREADS], mag3(Ucorr));
             accM[ACC_ETAMAX * K1_THREADS] = fmax(accM[ACC_ETAMAX * K1_THREADS], eta);
             accM[ACC_NEG_ETAMIN * K1_THREADS] = fmax(accM[ACC_NEG_ETAMIN * K1_THREADS], -eta);
-            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], park[3 * K1_THREADS]);
+            accM[ACC_COMAX * K1_THREADS] = fmax(accM[ACC_COMAX * K1_THREADS], park[PK_CO * K1_THREADS]);
         }
     }
 

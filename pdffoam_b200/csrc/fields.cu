@@ -499,6 +499,7 @@ void Cloud::commitFv() {
 }
 
 void Cloud::uploadCloudFields(const pdfb200_cloud_fields &f) {
+    orderAfterDownloads();
     dropGraphs();
     if (!f.rho || !f.rhob) throw std::runtime_error("upload_cloud_fields: rho missing");
     cudaStream_t s = stream;
@@ -527,6 +528,7 @@ void Cloud::uploadCloudFields(const pdfb200_cloud_fields &f) {
 }
 
 void Cloud::initMoments() {
+    orderAfterDownloads();
     dropGraphs();
     if (!haveFv || !haveCloudFields) throw std::logic_error("init_moments: upload the FV and cloud fields first");
     const size_t nc = nCells, nb = nBnd;
@@ -586,18 +588,47 @@ void fieldsFinalise(Cloud &c, double *partSum, double *partMax, int grid) {
     LAUNCH(&c, k_bnd_apply, gridFor(c.nBnd, 128), 128, 0, c.dm, F, c.prm.nPhi, c.nCov);
 }
 
+static void copyCellFields(Cloud &c, const pdfb200_cell_fields &o, cudaStream_t s) {
+    const size_t nc = c.nCells;
+    auto dl = [&](double *dst, const double *src, size_t n) { if (dst) CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, s)); };
+    dl(o.rho, c.rho_c.p, nc); dl(o.rhoInst, c.rhoInst_c.p, nc); dl(o.pnd, c.pnd_c.p, nc); dl(o.pndInst, c.pndInst_c.p, nc);
+    dl(o.U, c.Updf_c.p, nc * 3); dl(o.Tau, c.Tau_c.p, nc * 6); dl(o.k, c.kpdf_c.p, nc); dl(o.PaNIC, c.PaNIC.p, nc);
+    dl(o.mMom, c.mMom.p, nc); dl(o.VMom, c.VMom.p, nc); dl(o.UMom, c.UMom.p, nc * 3); dl(o.UUMom, c.UUMom.p, nc * 6);
+    for (int i = 0; i < c.prm.nPhi; ++i) { dl(o.Phi[i], c.Phi_c.p + i * nc, nc); dl(o.PhiMom[i], c.PhiMom.p + i * nc, nc); }
+    for (int i = 0; i < c.nCov; ++i) { dl(o.Cov[i], c.Cov_c.p + i * nc, nc); dl(o.PhiPhiMom[i], c.PhiPhiMom.p + i * nc, nc); }
+    for (int i = 0; i < c.prm.nPhi; ++i) { dl(o.UPhi[i], c.UPhi_c.p + i * nc * 3, nc * 3); dl(o.UPhiMom[i], c.UPhiMom.p + i * nc * 3, nc * 3); }
+}
+
 void Cloud::downloadCellFields(pdfb200_cell_fields &o) {
     if (!haveMoments) throw std::logic_error("download_cell_fields: moments not initialised");
-    cudaStream_t s = stream;
-    const size_t nc = nCells;
-    auto dl = [&](double *dst, const double *src, size_t n) { if (dst) CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, s)); };
-    dl(o.rho, rho_c.p, nc); dl(o.rhoInst, rhoInst_c.p, nc); dl(o.pnd, pnd_c.p, nc); dl(o.pndInst, pndInst_c.p, nc);
-    dl(o.U, Updf_c.p, nc * 3); dl(o.Tau, Tau_c.p, nc * 6); dl(o.k, kpdf_c.p, nc); dl(o.PaNIC, PaNIC.p, nc);
-    dl(o.mMom, mMom.p, nc); dl(o.VMom, VMom.p, nc); dl(o.UMom, UMom.p, nc * 3); dl(o.UUMom, UUMom.p, nc * 6);
-    for (int i = 0; i < prm.nPhi; ++i) { dl(o.Phi[i], Phi_c.p + i * nc, nc); dl(o.PhiMom[i], PhiMom.p + i * nc, nc); }
-    for (int i = 0; i < nCov; ++i) { dl(o.Cov[i], Cov_c.p + i * nc, nc); dl(o.PhiPhiMom[i], PhiPhiMom.p + i * nc, nc); }
-    for (int i = 0; i < prm.nPhi; ++i) { dl(o.UPhi[i], UPhi_c.p + i * nc * 3, nc * 3); dl(o.UPhiMom[i], UPhiMom.p + i * nc * 3, nc * 3); }
-    CUDA_CHECK(cudaStreamSynchronize(s));
+    copyCellFields(*this, o, stream);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void Cloud::downloadCellFieldsAsync(const pdfb200_cell_fields &o) {
+    if (!haveMoments) throw std::logic_error("download_cell_fields_async: moments not initialised");
+    if (!dlStream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&dlStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evStepDone, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&evDownloaded, cudaEventDisableTiming));
+    }
+    // behind everything issued on the library's stream so far, beside whatever is issued next
+    CUDA_CHECK(cudaEventRecord(evStepDone, stream));
+    CUDA_CHECK(cudaStreamWaitEvent(dlStream, evStepDone, 0));
+    copyCellFields(*this, o, dlStream);
+    CUDA_CHECK(cudaEventRecord(evDownloaded, dlStream));
+    downloadPending = true;
+}
+
+void Cloud::syncDownloads() {
+    if (dlStream) CUDA_CHECK(cudaStreamSynchronize(dlStream));
+    downloadPending = false;
+}
+
+void Cloud::orderAfterDownloads() {
+    if (!downloadPending) return;
+    CUDA_CHECK(cudaStreamWaitEvent(stream, evDownloaded, 0));
+    downloadPending = false;
 }
 
 // fields of an externally solved position correction (pdfb200_poscorr_fields): packed into rows of 12
@@ -633,6 +664,7 @@ __global__ void k_flux_from_means(int n, int nCells, const double *PhiMom, const
     st3(UPhiMom, j, (PhiMom[j] / fmax(mMom[c], PDF_SMALL)) * ld3(UMom, c));
 }
 void Cloud::uploadMoments(const pdfb200_cell_fields &m) {
+    orderAfterDownloads();
     if (!haveFv || !haveCloudFields) throw std::logic_error("upload_moments: upload the FV and cloud fields first");
     bool complete = m.mMom && m.VMom && m.UMom && m.UUMom;
     for (int i = 0; i < prm.nPhi; ++i) complete = complete && m.PhiMom[i];

@@ -1651,6 +1651,9 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
 
     // ---- time-averaging, mean fields, boundary conditions ----
     const int gF = std::min(gridFor(nCells, 256), numSMs * 8);
+    // a pending asynchronous read-back of the cell fields must have left before they are overwritten (not while a
+    // graph is being captured: evolve() orders the whole replay behind the copies instead)
+    if (ev) orderAfterDownloads();
     fieldsFinalise(*this, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, gF);
     LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
     LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
@@ -1736,18 +1739,20 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
 
     // Steps are issued in batches without waiting for the device in between: every step leaves its report in a ring on
     // the device, the host fetches the ring once per batch. One step per batch where the host has to see the entry
-    // count of every step (the (cell, tet) radix sort of a library) or time the all-reduce (several ranks).
+    // count of every step (the (cell, tet) radix sort of a library). With several ranks the all-reduce of every step is
+    // timed by the step's own pair of events, so their steps are batched as well.
     // Small clouds are launch-bound (a step is ~50 kernels of a few microseconds): there the step is captured once into
     // a CUDA graph per state-buffer parity and replayed (PDFB200_GRAPH=0/1 overrides; no per-region timing in that mode).
     static const int graphEnv = [] { const char *e = std::getenv("PDFB200_GRAPH"); return e ? std::atoi(e) : -1; }();
     const bool mayGraph = !radixPath && nRanks == 1 && (!hasInlet || inletCached);
     const int gm = graphMode >= 0 ? graphMode : graphEnv;
     const bool useGraph = mayGraph && (gm >= 0 ? gm != 0 : capacity <= 4000000);
-    const int batchMax = (radixPath || nRanks > 1) ? 1 : REPORT_RING;
+    const int batchMax = radixPath ? 1 : REPORT_RING;
     for (int done = 0; done < nSteps;) {
         const int nb = std::min(batchMax, nSteps - done);
         int zero = 0;
         CUDA_CHECK(cudaMemcpyAsync(&scal.p->ringIdx, &zero, sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (useGraph) orderAfterDownloads();
         for (int b = 0; b < nb; ++b) {
             if (useGraph) {
                 void *&ge = stepGraph[cur];
@@ -1784,10 +1789,11 @@ void Cloud::evolve(int nSteps, pdfb200_step_report *reports) {
         CUDA_CHECK(cudaMemcpyAsync(hRing, reportRing.p, (size_t)nb * sizeof(DevReport), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaMemcpyAsync(hScal, scal.p, sizeof(StepScalars), cudaMemcpyDeviceToHost, stream));
         CUDA_CHECK(cudaStreamSynchronize(stream));
-        float arMs = 0;
-        if (nRanks > 1) CUDA_CHECK(cudaEventElapsedTime(&arMs, evArA, evArB));
         for (int b = 0; b < nb; ++b) {
             const double *v = hRing + (size_t)b * 64;
+            // the all-reduce of step b sits between marks 4 and 5 (several ranks never replay a graph)
+            float arMs = 0;
+            if (nRanks > 1 && !useGraph) CUDA_CHECK(cudaEventElapsedTime(&arMs, evMarks[(size_t)b * 7 + 4], evMarks[(size_t)b * 7 + 5]));
             if (!useGraph) {
                 // per-region device times: prep+inject, evolve kernel, sort, bounds+moments, allreduce, finalise+control
                 for (int r = 0; r < 6; ++r) {

@@ -145,3 +145,29 @@ def test_ids_beyond_32_bits(device_lib, oracle_lib):
     a, b = low.download_particles(), hi1.download_particles()
     n = min(a["U"].shape[0], b["U"].shape[0])
     assert not np.allclose(np.sort(a["U"][:n, 0]), np.sort(b["U"][:n, 0]))
+
+
+def test_async_download_is_the_state_after_its_step(device_lib):
+    """pdfb200_download_cell_fields_async: the read-back queued after step n must deliver step n's field although
+    step n+1 is issued (and overwrites the field on the device) before the host waits for the copy"""
+    import torch
+    case = cases.synthetic_box(10, 6, 5, ppc=20, closed=False, number_control=True)
+    case.params.deltaT0 = 2e-3
+    a, b = case.make_cloud(device_lib), case.make_cloud(device_lib)
+    a.seed_particles(); b.seed_particles()
+    bufs = [torch.empty(case.mesh.n_cells, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    for mode in (0, 1):                 # plain launches, then the CUDA-graph replay
+        a.set_graph_mode(mode); b.set_graph_mode(mode)
+        ref = []
+        for n in range(6):
+            a.evolve(1); ref.append(a.download_rho().copy())
+        got = []
+        for n in range(6):
+            b.evolve(1)
+            if n > 0:
+                b.sync_downloads(); got.append(bufs[(n - 1) % 2].copy())
+            b.download_rho_async(bufs[n % 2])
+        b.sync_downloads(); got.append(bufs[5 % 2].copy())
+        for n in range(6):
+            assert np.array_equal(ref[n], got[n]), f"mode {mode}, step {n}"
+        assert not np.array_equal(ref[0], ref[5])

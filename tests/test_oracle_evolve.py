@@ -252,3 +252,24 @@ def test_naive_flamelet_relation(oracle_lib):
     z = Q["Phi"][0]
     np.testing.assert_allclose(Q["rho"], 1 - 3.2 * z * (1 - z), rtol=1e-15)
     np.testing.assert_allclose(Q["Phi"][1], 1e5 / Q["rho"], rtol=1e-15)
+
+
+def test_oracle_ids_are_64_bits_wide(oracle_lib):
+    """The particle id keys the random streams with both of its words (counter words 0 and 1 of Philox): ids that agree
+    in the low word evolve differently; the id counter starts above the largest id handed in."""
+    from pdffoam_b200 import cases
+    case = cases.synthetic_box(4, 3, 2, ppc=12, closed=True, number_control=True)
+    case.params.deltaT0 = 2e-3
+    P = case.random_particles(12, seed=2)
+    out = []
+    for base in (0, 1 << 32, (1 << 40) + 17):
+        Q = dict(P); Q["id"] = np.arange(P["m"].size, dtype=np.uint64) + np.uint64(base)
+        h = case.make_cloud(oracle_lib)
+        h.upload_particles(Q)
+        assert h.id_counter() == base + P["m"].size
+        h.evolve(2)
+        R = h.download_particles()
+        assert R["id"].dtype == np.uint64 and R["id"].min() >= base
+        o = np.argsort(R["id"])
+        out.append(R["U"][o][: P["m"].size // 2])
+    assert not np.allclose(out[0], out[1]) and not np.allclose(out[1], out[2])
