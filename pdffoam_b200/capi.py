@@ -504,6 +504,16 @@ class CloudHandle:
         s.rho = _dp(out)
         self.lib.check(self.lib.fn("download_cell_fields_async")(self.h, C.byref(s)), "download_cell_fields_async")
 
+    def download_fields_async(self, out: Dict[str, np.ndarray]):
+        """pdfb200_download_cell_fields_async for any of the plain cell fields (rho, rhoInst, pnd, pndInst, U, Tau, k,
+        PaNIC): out maps the field name to a contiguous float64 buffer (page-locked for a truly asynchronous copy)."""
+        s = CellFieldsStruct()
+        for k, a in out.items():
+            if k not in ("rho", "rhoInst", "pnd", "pndInst", "U", "Tau", "k", "PaNIC"):
+                raise KeyError(k)
+            setattr(s, k, _dp(a))
+        self.lib.check(self.lib.fn("download_cell_fields_async")(self.h, C.byref(s)), "download_cell_fields_async")
+
     def sync_downloads(self):
         self.lib.check(self.lib.fn("sync_downloads")(self.h), "sync_downloads")
 

@@ -148,26 +148,29 @@ def test_ids_beyond_32_bits(device_lib, oracle_lib):
 
 
 def test_async_download_is_the_state_after_its_step(device_lib):
-    """pdfb200_download_cell_fields_async: the read-back queued after step n must deliver step n's field although
-    step n+1 is issued (and overwrites the field on the device) before the host waits for the copy"""
+    """pdfb200_download_cell_fields_async: the read-back queued after step n must deliver step n's fields although
+    step n+1 is issued (and overwrites the fields on the device) before the host waits for the copy"""
     import torch
     case = cases.synthetic_box(10, 6, 5, ppc=20, closed=False, number_control=True)
     case.params.deltaT0 = 2e-3
     a, b = case.make_cloud(device_lib), case.make_cloud(device_lib)
     a.seed_particles(); b.seed_particles()
-    bufs = [torch.empty(case.mesh.n_cells, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    nc = case.mesh.n_cells
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    bufs = [dict(rho=pin(nc), U=pin(nc, 3), pndInst=pin(nc)) for _ in range(2)]
     for mode in (0, 1):                 # plain launches, then the CUDA-graph replay
         a.set_graph_mode(mode); b.set_graph_mode(mode)
         ref = []
         for n in range(6):
-            a.evolve(1); ref.append(a.download_rho().copy())
+            a.evolve(1); cf = a.download_cell_fields(moments=False); ref.append({k: cf[k].copy() for k in bufs[0]})
         got = []
         for n in range(6):
             b.evolve(1)
             if n > 0:
-                b.sync_downloads(); got.append(bufs[(n - 1) % 2].copy())
-            b.download_rho_async(bufs[n % 2])
-        b.sync_downloads(); got.append(bufs[5 % 2].copy())
+                b.sync_downloads(); got.append({k: v.copy() for k, v in bufs[(n - 1) % 2].items()})
+            b.download_fields_async(bufs[n % 2])
+        b.sync_downloads(); got.append({k: v.copy() for k, v in bufs[5 % 2].items()})
         for n in range(6):
-            assert np.array_equal(ref[n], got[n]), f"mode {mode}, step {n}"
-        assert not np.array_equal(ref[0], ref[5])
+            for k in bufs[0]:
+                assert np.array_equal(ref[n][k], got[n][k]), f"mode {mode}, step {n}, field {k}"
+        assert not np.array_equal(ref[0]["U"], ref[5]["U"]) and not np.array_equal(ref[4]["pndInst"], ref[5]["pndInst"])

@@ -38,9 +38,11 @@ def test_warped_hex_mesh_deterministic_and_stochastic(device_lib, oracle_lib):
     assert sum(r[0].nInjected for r in reps) > 0 and sum(r[0].nLost for r in reps) == 0
 
 
-def test_six_scalars(device_lib, oracle_lib):
-    """nPhi = PDFB200_MAX_PHI: the widest kernel instantiation, 21 covariances."""
-    case = cases.synthetic_box(6, 4, 3, ppc=16, closed=False, n_phi=6)
+@pytest.mark.parametrize("n_phi", [2, 4, 5, 6])
+def test_many_scalars(device_lib, oracle_lib, n_phi):
+    """every instantiation of the moments kernel beyond the common ones (one group of accumulators up to nPhi = 4, two
+    groups from 5 on); nPhi = PDFB200_MAX_PHI = 6 is the widest particle kernel, 21 covariances"""
+    case = cases.synthetic_box(6, 4, 3, ppc=16, closed=False, n_phi=n_phi)
     case.params.deltaT0 = 2e-3
     P = case.random_particles(16, seed=12)
     run_both(case, device_lib, oracle_lib, P, n_steps=5, rtol=1e-10, atol=1e-12)
