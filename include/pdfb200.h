@@ -372,6 +372,10 @@ int64_t pdfb200_kernel_launches(pdfb200_cloud *cloud);
  * [5] time-averaging + number control + step end; out[6] = steps, out[7] =
  * particle-steps processed. reset != 0 clears the accumulators.              */
 int pdfb200_profile(pdfb200_cloud *cloud, double out[8], int reset);
+/* Load balance of the particle kernel: the first call switches a recording hook on (nCtas = 0); later calls return,
+ * for the last launch of the particle kernel, three values per CTA: start and end (%globaltimer, ns) and the SM it ran
+ * on. out holds 3 * maxCtas values.                                                                                 */
+int pdfb200_profile_ctas(pdfb200_cloud *cloud, int64_t maxCtas, int64_t *out, int64_t *nCtas);
 /* How evolve() issues its steps. A step is about fifty kernels and never waits for the device in its middle (entry
  * counts, time step and flags stay on the device; the step reports are fetched once per batch of up to 64 steps).
  * For small clouds - the tutorial cases hold 1e5 particles, a step is then bound by launch overhead - the step is

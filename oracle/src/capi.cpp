@@ -209,6 +209,16 @@ int pdforacle_download_cell_fields_async(pdforacle_cloud *h, const pdfb200_cell_
 }
 int pdforacle_sync_downloads(pdforacle_cloud *) { return PDFB200_OK; }
 
+// diagnostics: histogram of the tet faces crossed by every particle in the full-step walk of the last evolve
+// (bin k: k crossings, last bin: >= nBins-1) and the largest count
+int pdforacle_debug_crossings(pdforacle_cloud *h, int nBins, int64_t *hist, int *maxSteps) {
+    int mx = 0;
+    for (int k = 0; k < nBins; ++k) hist[k] = 0;
+    for (const Particle &p : h->c.particles) { mx = std::max(mx, p.nSteps); ++hist[std::min(p.nSteps, nBins - 1)]; }
+    *maxSteps = mx;
+    return PDFB200_OK;
+}
+
 int64_t pdforacle_num_particles(pdforacle_cloud *h) { return (int64_t)h->c.particles.size(); }
 
 int pdforacle_download_particles(pdforacle_cloud *h, int64_t maxn, pdfb200_particles *out, int64_t *n) {

@@ -187,7 +187,7 @@ API_SYMBOLS = [
     "upload_cloud_fields", "upload_poscorr_fields", "init_moments", "seed_particles", "upload_particles", "num_particles",
     "download_particles", "evolve", "download_cell_fields", "download_cell_fields_async", "sync_downloads", "upload_moments", "step_counter", "set_step_counter", "id_counter", "set_id_counter", "delta_t", "set_delta_t",
     "comm_unique_id", "comm_init", "mesh_info_get", "download_tets", "download_geometry",
-    "kernel_launches", "last_evolve_ms", "profile", "set_graph_mode", "jit_source", "jit_compile", "rng_probe",
+    "kernel_launches", "last_evolve_ms", "profile", "profile_ctas", "set_graph_mode", "jit_source", "jit_compile", "rng_probe",
 ]
 
 
@@ -513,6 +513,16 @@ class CloudHandle:
                 raise KeyError(k)
             setattr(s, k, _dp(a))
         self.lib.check(self.lib.fn("download_cell_fields_async")(self.h, C.byref(s)), "download_cell_fields_async")
+
+    def profile_ctas(self) -> np.ndarray:
+        """pdfb200_profile_ctas: [nCtas, 3] = start ns, end ns, SM of every CTA of the last particle-kernel launch
+        (empty on the first call, which switches the recording on)."""
+        out = np.zeros((4096, 3), np.int64)
+        n = C.c_int64(0)
+        f = self.lib.fn("profile_ctas")
+        f.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        self.lib.check(f(self.h, 4096, out.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n)), "profile_ctas")
+        return out[: n.value]
 
     def sync_downloads(self):
         self.lib.check(self.lib.fn("sync_downloads")(self.h), "sync_downloads")

@@ -339,6 +339,22 @@ int pdfb200_download_geometry(pdfb200_cloud *c, double *fc, double *fa, double *
 
 int64_t pdfb200_kernel_launches(pdfb200_cloud *c) { return c->c.launches; }
 
+int pdfb200_profile_ctas(pdfb200_cloud *c, int64_t maxCtas, int64_t *out, int64_t *nCtas) {
+    USE_DEVICE(c);
+    return guarded([&] {
+        Cloud &C = c->c;
+        if (!C.ctaClock.n) {                 // first call switches the hook on: the next evolve() records
+            C.ctaClock.alloc((size_t)3 * C.numSMs * 16); C.ctaClock.zero(C.stream);
+            CUDA_CHECK(cudaStreamSynchronize(C.stream));
+            C.dropGraphs();
+            *nCtas = 0;
+            return;
+        }
+        const int64_t n = std::min<int64_t>(maxCtas, C.ctaClockGrid);
+        CUDA_CHECK(cudaMemcpy(out, C.ctaClock.p, (size_t)n * 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+        *nCtas = n;
+    });
+}
 int pdfb200_profile(pdfb200_cloud *c, double out[8], int reset) {
     Cloud &C = c->c;
     for (int r = 0; r < 6; ++r) out[r] = C.profMs[r];

@@ -92,6 +92,14 @@ struct Cloud {
     cudaStream_t dlStream = nullptr;
     cudaEvent_t evStepDone = nullptr, evDownloaded = nullptr;
     bool downloadPending = false;
+    // dynamic work distribution of the particle kernel: claim counter, per-chunk mass sums (evolve_kernel.cuh)
+    DBuf<int> k1WorkCtr;
+    DBuf<double> chunkSums, chunkPart;
+    bool k1Dynamic = K1_DYNAMIC != 0;
+    int k1Chunk = K1_CHUNK;
+    // pdfb200_profile_ctas: per-CTA start/end times of the last particle-kernel launch (allocated on first use)
+    DBuf<long long> ctaClock;
+    int ctaClockGrid = 0;
     bool stagedPending = false;
     // cloud fields (cell + boundary)
     DBuf<double> rho_c, rho_b, rhoInst_c, pnd_c, pndInst_c, Updf_c, Updf_b, Tau_c, Tau_b, kpdf_c, kpdf_b;

@@ -183,6 +183,38 @@ __device__ inline void st3(double *p, long long i, V3 v) { p[3 * i] = v.x; p[3 *
 // fused dot product of the tet walk: the same fma chain as oracle dotf()
 __device__ inline double dotf(double gx, double gy, double gz, V3 r) { return fma(gx, r.x, fma(gy, r.y, gz * r.z)); }
 
+// Sums of NACC per-lane accumulators over the lanes of a warp. A butterfly per accumulator (x += shfl_xor(x, 16), 8,
+// 4, 2, 1) costs 5 NACC 64-bit shuffles per cell, which made the shuffle pipe a bound of k_moments (2e6 cells x 80 at
+// nPhi = 1). Recursive halving instead: at distance 16 a lane hands half of its accumulators to its partner and takes
+// the partner's copies of the half it keeps, at distance 8 a quarter, ... - about NACC shuffles in total. Every
+// partial sum is formed from the same two operands as in the butterfly (own + partner's; floating-point addition
+// commutes), so the results are bit-identical to it. A group of C accumulators (a power of two <= 32) leaves
+// accumulator k in the lanes l with (l >> log2(32 / C)) == k.
+__host__ __device__ constexpr int pow2Ceil(int x) { int c = 1; while (c < x) c <<= 1; return c; }
+__host__ __device__ constexpr int log2Floor(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
+template <int C>
+__device__ __forceinline__ double laneSums(double (&v)[C], int lane) {
+    int n = C;   // folds to constants once the loop is unrolled
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+        if (n > 1) {
+            const int half = n >> 1;
+#pragma unroll
+            for (int k = 0; k < C / 2; ++k) {
+                if (k < half) {
+                    const double send = upper ? v[k] : v[k + half];
+                    const double keep = upper ? v[k + half] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            n = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        }
+    }
+    return v[0];
+}
 // rotationTensor(n1,n2) (OpenFOAM transform.H), row-major
 __host__ __device__ inline void rotationTensor(V3 n1, V3 n2, double T[9]) {
     const double s = dot3(n1, n2);

@@ -72,6 +72,9 @@ struct K1Args {
     double cEqMax;
     RngKey key;
     double *partSum, *partMax;
+    int *workCtr;          // dynamic work distribution (K1_DYNAMIC): next unclaimed entry (zeroed by k_step_begin)
+    double *chunkSums;     // [chunk][4 * K1_NC1] mass sums of every chunk (reduced in a fixed order, folded by k_chunk_fold)
+    long long *ctaClock;   // profiling hook (pdfb200_profile_ctas): per CTA {start, end, SM id}, or null
     int hasOpen;
 };
 
@@ -358,10 +361,7 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #ifndef K1_TRACK_R
 #define K1_TRACK_R 0
 #endif
-// 1: the permutation is requested one iteration ahead; 2: the cell and tet labels as well (see evolveBody)
-#ifndef K1_PF
-#define K1_PF 1
-#endif
+
 #ifndef K1_COMPACT_ACC
 #define K1_COMPACT_ACC 1
 #endif
@@ -438,6 +438,19 @@ __device__ __forceinline__ int reloadI(const int *p) {
     return v;
 }
 
+// The mass sums a warp has gathered in its thread-private rows (accS: row r of this thread at accS[r * K1_THREADS]),
+// reduced over the lanes in a fixed order, stored as one row of the host's layout (4 * K1_NC1 values) and reset. Out of
+// line: it runs once per chunk, and the particle kernel is sensitive to its instruction footprint.
+__device__ __noinline__ void flushMassSums(double *accS, int lane, double *row) {
+    constexpr int NS = 4 * KNC1, NSP2 = pow2Ceil(NS), NSSHIFT = log2Floor(32 / NSP2);
+    double v[NSP2];
+#pragma unroll
+    for (int r = 0; r < NSP2; ++r) { v[r] = r < NS ? accS[(r < NS ? r : 0) * K1_THREADS] : 0.0; if (r < NS) accS[r * K1_THREADS] = 0.0; }
+    const double x = laneSums<NSP2>(v, lane);
+    const int r = lane >> NSSHIFT;
+    if ((lane & ((1 << NSSHIFT) - 1)) == 0 && r < NS) row[(r / KNC1) * K1_NC1 + r % KNC1] = x;
+}
+
 // NPHI = compile-time bound on the particle scalars held in registers (nPhi <= NPHI)
 template <int NPHI>
 __device__ __forceinline__ void evolveBody(const K1Args &A) {
@@ -450,6 +463,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 #pragma unroll
     for (int k = 0; k < ACC_NMAX; ++k) accM[k * K1_THREADS] = -PDF_VGREAT;
 
+    if (A.ctaClock && threadIdx.x == 0) {   // written at once: no register may stay occupied through the kernel
+        long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        A.ctaClock[3 * blockIdx.x] = t0;
+    }
     const DMesh &M = A.M;
 #ifdef K1_JIT
     const JitP P{};
@@ -465,49 +483,59 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     const int nPhi = P.nPhi;
     const size_t nodeP = (size_t)M.nCells, nodeF = (size_t)M.nCells + M.nPoints;
 
-    // the slot of an entry comes through the permutation of the last sort: requested one iteration ahead so that
-    // the state loads of an iteration do not start with a dependent load. The request is unconditional (index
+    // Work distribution. Static (K1_DYNAMIC 0): the persistent CTAs stride over the entries in waves of
+    // gridDim.x * 128, every CTA the same number of trips, the four warps of a CTA side by side on 128 consecutive
+    // entries. Measured with pdfb200_profile_ctas: the five CTAs of an SM do not advance at the same rate (the warp
+    // schedulers favour the older warps), the CTA launched last on an SM needs 4-17 % longer for its share and the
+    // kernel ends with a tail of a few busy SMs - 14 % of its duration once number control has widened the spread of
+    // the per-cell populations (24.8 -> 21.3 ms there; on the freshly seeded cloud, where every cell holds exactly 64
+    // particles and the warps of a CTA share their cells' records in L1, the static waves are 2.5 % faster).
+    // Dynamic (K1_DYNAMIC 1, default): a warp claims the next K1_CHUNK entries from a counter (one atomic per chunk,
+    // issued one chunk ahead), so that slower warps take fewer chunks and all warps end within one chunk of each other;
+    // chunks are handed out in index order, which keeps the warps of the whole device on one moving window of the
+    // Morton-ordered cells. (Static waves for the first 13/16 of the entries and chunks for the rest: no better.)
+    // The mass sums of the report must not depend on which warp took which chunk: a warp reduces them over its lanes
+    // in a fixed order at the end of every chunk and stores a row per chunk (k_chunk_fold adds the rows in a fixed
+    // order); counts and maxima are exact in any order and stay in the thread-private rows.
+    // The slot of a sorted entry comes through the permutation of the last sort: requested one trip ahead so
+    // that the state loads of a trip do not start with a dependent load. The request is unconditional (index
     // clamped into the sorted range): a predicated load would be merged with the old value by a select right
     // behind it, which waits for the load at once (ncu: 3.7 % of the stall samples of the v3 kernel).
-    // K1_PF 2: the cell and tet labels of the next entry are requested one iteration ahead as well (the permutation
-    // two ahead), so that the tet record and the state columns can be requested at the top of an iteration.
-    const int gstride = gridDim.x * blockDim.x;
     const int permLast = max(nSorted - 1, 0);
-#if K1_PF >= 2
-    int pvNext, slotCur, cellCur, tetCur;
-    {
-        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-        const int ic = min(i0, max(total - 1, 0));
-        slotCur = (ic < nSorted) ? (int)A.perm[min(ic, permLast)] : (total > 0 ? nSlotsIn + (ic - nSorted) : 0);
-        pvNext = (int)A.perm[min(i0 + gstride, permLast)];
-        cellCur = A.in.cell[slotCur]; tetCur = A.in.tet[slotCur];
-    }
+    const int lane = threadIdx.x & 31;
+#if K1_DYNAMIC
+    // warp-uniform: cpos = first entry of this trip, cend = end of the chunk in hand (0: none yet), cfetch = lane 0's
+    // claim of the chunk after it
+    int cpos = 0, cend = 0, cfetch = 0;
+    if (lane == 0) cfetch = atomicAdd(A.workCtr, K1_CHUNK);
+    int slotNext = (int)A.perm[min(__shfl_sync(0xffffffffu, cfetch, 0) + lane, permLast)];
+    for (;;) {
+        if (cpos == cend) {
+            if (cend > 0) flushMassSums(accS, lane, A.chunkSums + (size_t)(cend / K1_CHUNK - 1) * (4 * K1_NC1));
+            cpos = __shfl_sync(0xffffffffu, cfetch, 0);
+            if (cpos >= total) break;
+            cend = cpos + K1_CHUNK;
+            if (lane == 0) cfetch = atomicAdd(A.workCtr, K1_CHUNK);   // the chunk after this one, claimed ahead
+        }
+        const int i = cpos + lane;
+        cpos += 32;
+        const int slotPerm = slotNext;
+        // (on the last trip of a chunk this waits for the claim made at the chunk's first trip)
+        slotNext = (int)A.perm[min((cpos == cend ? __shfl_sync(0xffffffffu, cfetch, 0) : cpos) + lane, permLast)];
 #else
+    const int gstride = gridDim.x * blockDim.x;
     int slotNext = (int)A.perm[min((int)(blockIdx.x * blockDim.x + threadIdx.x), permLast)];
-#endif
     for (int base = blockIdx.x * blockDim.x; base < total; base += gstride) {
         const int i = base + threadIdx.x;
-#if K1_PF >= 2
-        const int slot = slotCur, cell0 = cellCur, tet0 = tetCur;
-        {
-            const int iN = min(i + gstride, total - 1);
-            slotCur = (iN < nSorted) ? pvNext : nSlotsIn + (iN - nSorted);
-            pvNext = (int)A.perm[min(i + 2 * gstride, permLast)];
-            cellCur = A.in.cell[slotCur]; tetCur = A.in.tet[slotCur];
-        }
-        if (i >= total) continue;
-#else
         const int slotPerm = slotNext;
         slotNext = (int)A.perm[min(i + gstride, permLast)];
+#endif
         if (i >= total) continue;
         const int slot = (i < nSorted) ? slotPerm : nSlotsIn + (i - nSorted);
         const int cell0 = A.in.cell[slot];
-#endif
         if (cell0 < 0) { A.out.cell[i] = -1; continue; }
         V3 pos = mk(ldInD(A.in.px + slot), ldInD(A.in.py + slot), ldInD(A.in.pz + slot));
-#if K1_PF < 2
         const int tet0 = A.in.tet[slot];
-#endif
         int tet = tet0;
         const bool injected = (i >= nSorted + nInjStart);
 
@@ -982,8 +1010,14 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 
     // ---- deterministic CTA reduction of the thread-private accumulators ----
     __syncthreads();
+    if (A.ctaClock && threadIdx.x == 0) {
+        long long t1; unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        A.ctaClock[3 * blockIdx.x + 1] = t1; A.ctaClock[3 * blockIdx.x + 2] = (long long)sm;
+    }
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int warp = threadIdx.x >> 5;
         // warp w reduces rows w, w+4, ... of the host's layout (k1_layout.h); the rows of conserved scalars the
         // specialised kernel does not carry are written as zeros
         for (int k = warp; k < ACC_NSUM + ACC_NMAX; k += K1_THREADS / 32) {

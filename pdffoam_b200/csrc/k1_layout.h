@@ -7,6 +7,14 @@
 #ifndef K1_THREADS
 #define K1_THREADS 128
 #endif
+// 1: the warps of the particle kernel claim chunks of entries from a counter; 0: static waves (evolve_kernel.cuh)
+#ifndef K1_DYNAMIC
+#define K1_DYNAMIC 1
+#endif
+// entries a warp claims at a time under the dynamic work distribution of the particle kernel (a multiple of 32)
+#ifndef K1_CHUNK
+#define K1_CHUNK 64
+#endif
 #define K1_JIT_MIN_BLOCKS 5   // CTAs per SM the run-time specialised kernel is compiled for (96 registers; measured best of 3..6)
 #ifndef K1_MAXCONS
 #define K1_MAXCONS 3

@@ -273,38 +273,6 @@ __global__ void k_cs_finish(const int *total, StepScalars *sc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSorted = *total;
 }
 
-// Sums of NACC per-lane accumulators over the lanes of a warp. A butterfly per accumulator (x += shfl_xor(x, 16), 8,
-// 4, 2, 1) costs 5 NACC 64-bit shuffles per cell, which made the shuffle pipe a bound of k_moments (2e6 cells x 80 at
-// nPhi = 1). Recursive halving instead: at distance 16 a lane hands half of its accumulators to its partner and takes
-// the partner's copies of the half it keeps, at distance 8 a quarter, ... - about NACC shuffles in total. Every
-// partial sum is formed from the same two operands as in the butterfly (own + partner's; floating-point addition
-// commutes), so the results are bit-identical to it. A group of C accumulators (a power of two <= 32) leaves
-// accumulator k in the lanes l with (l >> log2(32 / C)) == k.
-__host__ __device__ constexpr int pow2Ceil(int x) { int c = 1; while (c < x) c <<= 1; return c; }
-__host__ __device__ constexpr int log2Floor(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
-template <int C>
-__device__ __forceinline__ double laneSums(double (&v)[C], int lane) {
-    int n = C;   // folds to constants once the loop is unrolled
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const bool upper = (lane & o) != 0;
-        if (n > 1) {
-            const int half = n >> 1;
-#pragma unroll
-            for (int k = 0; k < C / 2; ++k) {
-                if (k < half) {
-                    const double send = upper ? v[k] : v[k + half];
-                    const double keep = upper ? v[k + half] : v[k];
-                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                }
-            }
-            n = half;
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-        }
-    }
-    return v[0];
-}
 template <int NACC, int G0>
 __device__ __forceinline__ void reduceStoreGroups(const double (&a)[NACC], int lane, double *out) {
     if constexpr (G0 < NACC) {
@@ -1194,16 +1162,37 @@ __global__ void k_colsum_nc1(int n, const double *in, double *partial, const int
         for (int k = 0; k < K1_NC1; ++k) partial[blockIdx.x * K1_NC1 + k] = v[k];
 }
 
+// sums of the per-chunk mass sums of the particle kernel ([chunk][4 * K1_NC1]) in a fixed order: CTA b takes a fixed
+// contiguous range of chunks, thread (sub, col) every 16th chunk of it, then the 16 subs are added in order
+__global__ void k_chunk_fold(const StepScalars *sc, int chunk, const double *chunkSums, double *partial) {
+    constexpr int NC = 4 * K1_NC1;
+    __shared__ double sm[256];
+    const int nChunks = (sc->nEntries + chunk - 1) / chunk;
+    const int per = (nChunks + gridDim.x - 1) / gridDim.x;
+    const int lo = min(nChunks, (int)blockIdx.x * per), hi = min(nChunks, lo + per);
+    const int col = threadIdx.x % NC, sub = threadIdx.x / NC, nSub = blockDim.x / NC;
+    double x = 0.0;
+    for (int c = lo + sub; c < hi; c += nSub) x += chunkSums[(size_t)c * NC + col];
+    sm[threadIdx.x] = x;
+    __syncthreads();
+    if (sub == 0) {
+        double t = sm[col];
+        for (int j = 1; j < nSub; ++j) t += sm[j * NC + col];
+        partial[(size_t)blockIdx.x * NC + col] = t;
+    }
+}
+
 __global__ void k_set_slots(StepScalars *sc) {
     if (threadIdx.x == 0 && blockIdx.x == 0) sc->nSlots = sc->nEntries;
 }
 
 // after the injection: the entry count of the step, kept on the device for every later kernel; also empties the list
 // of lost particles and notes what the report needs from the state at this point
-__global__ void k_step_begin(StepScalars *sc, DevReport *rp, unsigned *lostCount) {
+__global__ void k_step_begin(StepScalars *sc, DevReport *rp, unsigned *lostCount, int *workCtr) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     sc->nEntries = sc->nSorted + sc->nTail;
     *lostCount = 0u;
+    *workCtr = 0;
     rp->v[RP_DT_USED] = sc->deltaT;
     rp->v[RP_N_ENTRIES] = (double)sc->nEntries;
     rp->v[RP_N_INJECTED] = (double)(sc->nTail - sc->nInjStart);
@@ -1306,6 +1295,13 @@ void Cloud::allocParticles() {
         double *idp; allocD(idp); s.id = reinterpret_cast<uint64_t *>(idp);   // 64-bit ids: a column as wide as a double
     }
     keysA.alloc(cap); keysB.alloc(cap); valsB.alloc(cap); iota.alloc(cap);
+    // dynamic work distribution of the particle kernel (evolve_kernel.cuh); PDFB200_K1_DYNAMIC=0 selects the static
+    // waves, PDFB200_K1_CHUNK the chunk size of a kernel specialised with -DK1_CHUNK=... (tuning experiments)
+    if (const char *e = std::getenv("PDFB200_K1_DYNAMIC")) k1Dynamic = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PDFB200_K1_CHUNK")) k1Chunk = std::max(32, std::atoi(e));
+    k1WorkCtr.alloc(1); k1WorkCtr.zero(stream);
+    chunkSums.alloc(((size_t)cap / k1Chunk + 2) * 4 * K1_NC1); chunkSums.zero(stream);   // rows of scalars the case does not conserve stay zero
+    chunkPart.alloc((size_t)numSMs * 4 * 4 * K1_NC1);
     LAUNCH(this, k_iota, gridFor((long long)cap, 256), 256, 0, iota.p, (int)cap);
     injPatchTail.alloc(cap);
     size_t tempBytes = 0;
@@ -1569,7 +1565,7 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
         CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_INJ, 0, K1_NC1 * sizeof(double), stream));
     }
     // entry count of the step (device side), empty lost-particle list
-    LAUNCH(this, k_step_begin, 1, 32, 0, scal.p, dRep, lostCount.p);
+    LAUNCH(this, k_step_begin, 1, 32, 0, scal.p, dRep, lostCount.p, k1WorkCtr.p);
 
     // ---- the fused particle kernel: persistent grid, the kernel reads the entry count itself ----
     K1Args A;
@@ -1580,9 +1576,12 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
     A.injPatchTail = injPatchTail.p;
     A.flChi = flChi.p; A.flZ = flZ.p; A.flFields = flFields.p; A.nChi = nChi; A.nZ = nZ; A.flCEq = flCEq.p; A.cEqMax = cEqMax;
     A.key = key; A.partSum = k1PartSum.p; A.partMax = k1PartMax.p; A.hasOpen = hasOpen;
+    A.ctaClock = ctaClock.n ? ctaClock.p : nullptr;
+    A.workCtr = k1Dynamic ? k1WorkCtr.p : nullptr; A.chunkSums = chunkSums.p;
     const int gridK1 = (int)std::max<long long>(1, std::min<long long>(gridFor(cap, K1_THREADS), (long long)numSMs * k1Blocks));
     // the lost mass of the previous step has been handed out (lostShare): its cells start empty again
     CUDA_CHECK(cudaMemsetAsync(lostMass.p, 0, nCells * sizeof(double), stream));
+    if (ctaClock.n) ctaClockGrid = std::min<long long>(gridK1, (long long)ctaClock.n / 3);
     mark(1);
     if (k1Jit) {
         void *kargs[] = {&A};
@@ -1595,6 +1594,12 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
     LAUNCH(this, k_lost_reduce, 1, 1024, 0, lostList.p, lostSorted.p, lostCount.p, (unsigned)lostList.n, lostMass.p, scal.p);
     LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
     LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
+    if (k1Dynamic) {
+        // the mass sums come chunk by chunk (fixed order inside a chunk, fixed order over the chunks)
+        const int gC = numSMs * 4;
+        LAUNCH(this, k_chunk_fold, gC, 256, 0, scal.p, k1Chunk, chunkSums.p, chunkPart.p);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gC, 4 * K1_NC1, chunkPart.p, dRep->v + RP_K1SUM, 0);
+    }
     cur ^= 1;
 
     // ---- sort by cell + segment bounds ----
