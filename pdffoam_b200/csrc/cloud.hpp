@@ -95,8 +95,8 @@ struct Cloud {
     // dynamic work distribution of the particle kernel: claim counter, per-chunk mass sums (evolve_kernel.cuh)
     DBuf<int> k1WorkCtr;
     DBuf<double> chunkSums, chunkPart;
-    bool k1Dynamic = K1_DYNAMIC != 0;
-    int k1Chunk = K1_CHUNK;
+    int k1Dynamic = K1_DYNAMIC;   // 0 static waves, 1 chunks claimed per warp
+    int k1Chunk = K1_CHUNK;       // entries per row of chunkSums
     // pdfb200_profile_ctas: per-CTA start/end times of the last particle-kernel launch (allocated on first use)
     DBuf<long long> ctaClock;
     int ctaClockGrid = 0;

@@ -493,7 +493,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
     // Dynamic (K1_DYNAMIC 1, default): a warp claims the next K1_CHUNK entries from a counter (one atomic per chunk,
     // issued one chunk ahead), so that slower warps take fewer chunks and all warps end within one chunk of each other;
     // chunks are handed out in index order, which keeps the warps of the whole device on one moving window of the
-    // Morton-ordered cells. (Static waves for the first 13/16 of the entries and chunks for the rest: no better.)
+    // Morton-ordered cells. (Static waves for the first 13/16 of the entries and chunks for the rest: no better. Blocks
+    // of 128 entries claimed per CTA through a ring in shared memory, so that its four warps stay on neighbouring
+    // entries: 19.9 / 21.8 ms, no better either - profiles/README.md.)
     // The mass sums of the report must not depend on which warp took which chunk: a warp reduces them over its lanes
     // in a fixed order at the end of every chunk and stores a row per chunk (k_chunk_fold adds the rows in a fixed
     // order); counts and maxima are exact in any order and stay in the thread-private rows.

@@ -861,7 +861,7 @@ __global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, co
 }
 
 // one warp per flagged cell
-__global__ void k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
+__global__ void __launch_bounds__(256, 4) k_nc_apply(DMesh M, pdfb200_params P, PState S, const uint32_t *perm, const int *cellStart,
                            const int *cellEnd, const int *flag, const int *nClone, const int *cloneOffset,
                            double *PaNIC, StepScalars *sc, RngKey key, int rank, int nRanks, long long capacity,
                            double *ncDelta, int *ncCounts /* [2]: cloned, eliminated */, uint32_t *cloneSrc, const int *list,
@@ -1297,10 +1297,10 @@ void Cloud::allocParticles() {
     keysA.alloc(cap); keysB.alloc(cap); valsB.alloc(cap); iota.alloc(cap);
     // dynamic work distribution of the particle kernel (evolve_kernel.cuh); PDFB200_K1_DYNAMIC=0 selects the static
     // waves, PDFB200_K1_CHUNK the chunk size of a kernel specialised with -DK1_CHUNK=... (tuning experiments)
-    if (const char *e = std::getenv("PDFB200_K1_DYNAMIC")) k1Dynamic = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PDFB200_K1_DYNAMIC")) k1Dynamic = std::atoi(e);
     if (const char *e = std::getenv("PDFB200_K1_CHUNK")) k1Chunk = std::max(32, std::atoi(e));
     k1WorkCtr.alloc(1); k1WorkCtr.zero(stream);
-    chunkSums.alloc(((size_t)cap / k1Chunk + 2) * 4 * K1_NC1); chunkSums.zero(stream);   // rows of scalars the case does not conserve stay zero
+    chunkSums.alloc(((size_t)cap / k1Chunk + 8) * 4 * K1_NC1); chunkSums.zero(stream);   // rows of scalars the case does not conserve stay zero
     chunkPart.alloc((size_t)numSMs * 4 * 4 * K1_NC1);
     LAUNCH(this, k_iota, gridFor((long long)cap, 256), 256, 0, iota.p, (int)cap);
     injPatchTail.alloc(cap);
