@@ -453,6 +453,15 @@ def run_ours(args):
         st_prof = h.profile(reset=True)
         st_psteps = float(sum(r.nParticles for r in st_reps))
 
+    rank_times = None
+    if world > 1 and st_prof is not None:
+        # per-rank view of the stationary step: device time and the regions' times (the all-reduce region contains the
+        # wait for the slowest rank)
+        mine = torch.tensor([st_ms / max(args.steps, 1)] + [st_prof[k] / max(st_prof["steps"], 1) for k in
+                            ("prep_ms", "evolve_kernel_ms", "sort_ms", "moments_ms", "allreduce_ms", "finalise_ms")], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_times = [[round(float(x), 2) for x in t.tolist()] for t in allr]
     vals = torch.tensor([dev_ms, wall, e2e_wall, st_ms], dtype=torch.float64, device="cuda")
     sums = torch.tensor([psteps_local, e2e_psteps, st_psteps], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -500,6 +509,8 @@ def run_ours(args):
                 "breakdown_ms_per_step": {k: v / max(st_prof["steps"], 1) for k, v in st_prof.items() if k.endswith("_ms")},
                 "roofline_frac": (bpp * st_kp / (st_k * 1e-3) / 1e9 / peak) if st_k > 0 else None,
                 "note": "same workload and code, timed after the cloud has become statistically stationary (number control active in a third of the cells)"}
+            if rank_times is not None:
+                line["stationary_state"]["per_rank_ms"] = {"columns": ["step", "prep", "evolve_kernel", "sort", "moments", "allreduce_incl_wait", "finalise"], "rows": rank_times}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, ppc_per_gpu(args, 1))

@@ -811,7 +811,10 @@ void Cloud::particleNumberControl() {
             const int npGlobal = (int)std::round(PaNIC[c]);
             int n = Npc - npGlobal;
             n = std::min(npGlobal, n);
-            if (nRanks > 1) n = (int)std::min<double>(nLocal[c], std::floor((double)n * nLocal[c] / npGlobal + 0.5));
+            // particle-sharded runs (no counterpart in the reference): every rank steers its own share of the cell towards
+            // 1/nRanks of the population the cell has after cloning. (Shares proportional to the local counts have no
+            // restoring force: the ranks' holdings drift apart like competing species - 6 % after 400 steps on 4 ranks.)
+            if (nRanks > 1) n = (int)std::min<double>(nLocal[c], std::max(0., std::floor((double)(npGlobal + n) / nRanks - nLocal[c] + 0.5)));
             auto &lst = addr[c];
             std::sort(lst.begin(), lst.end(), [&](size_t a, size_t b) {
                 // weights rounded to single precision, ties by id: see cloneWeight in pdffoam_b200/csrc/particles.cu
@@ -838,6 +841,8 @@ void Cloud::particleNumberControl() {
             std::vector<size_t> popA, popB;
             double mA = 0., mB = 0.;
             double P = (2. * nx) / ncur;
+            // particle-sharded runs: the rank removes what it holds above its share Npc / nRanks of the cell
+            if (nRanks > 1) P = std::min(1., 2. * std::max(0., nLocal[c] - (double)Npc / nRanks) / std::max(nLocal[c], 1));
             for (size_t idx : addr[c]) {
                 Particle &p = particles[idx];
                 double u1, u2;

@@ -852,7 +852,10 @@ __global__ void k_nc_classify(DMesh M, pdfb200_params P, const double *PaNIC, co
     if (fl == 1) {
         n = min(np, Npc - np);
         const int nLocal = cellEnd[c] - cellStart[c];
-        if (nRanks > 1) n = (int)fmin((double)nLocal, floor((double)n * nLocal / np + 0.5));
+        // particle-sharded runs (no counterpart in the reference): every rank steers its own share of the cell towards
+        // 1/nRanks of the population the cell has after cloning. (Shares proportional to the local counts have no
+        // restoring force: the ranks' holdings drift apart like competing species - 6 % after 400 steps on 4 ranks.)
+        if (nRanks > 1) n = (int)fmin((double)nLocal, fmax(0., floor((double)(np + n) / nRanks - nLocal + 0.5)));
         n = min(n, nLocal);
     }
     flag[c] = fl; nClone[c] = n;
@@ -950,7 +953,9 @@ __global__ void __launch_bounds__(256, 4) k_nc_apply(DMesh M, pdfb200_params P, 
             // eliminateParticles (:1143-1221)
             const int ncur = (int)round(PaNIC[c]);
             const int nx = ncur - P.particlesPerCell;
-            const double Psel = (2. * nx) / ncur;
+            double Psel = (2. * nx) / ncur;
+            // particle-sharded runs: the rank removes what it holds above its share Npc / nRanks of the cell
+            if (nRanks > 1) Psel = fmin(1., 2. * fmax(0., cnt - (double)P.particlesPerCell / nRanks) / max(cnt, 1));
             double mA = 0., mB = 0.;
             // selection state of this lane's first four entries (all of them when inRegs)
             int slotv[4]; double u2v[4]; bool selv[4];
