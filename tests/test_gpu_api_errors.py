@@ -174,3 +174,20 @@ def test_async_download_is_the_state_after_its_step(device_lib):
             for k in bufs[0]:
                 assert np.array_equal(ref[n][k], got[n][k]), f"mode {mode}, step {n}, field {k}"
         assert not np.array_equal(ref[0]["U"], ref[5]["U"]) and not np.array_equal(ref[4]["pndInst"], ref[5]["pndInst"])
+
+
+def test_profile_ctas_reports_every_cta_of_the_particle_kernel(device_lib):
+    """pdfb200_profile_ctas: the first call arms the hook, later calls return start, end and SM of every CTA of the last
+    launch of the particle kernel; arming it must not change the results"""
+    case = cases.synthetic_box(12, 8, 6, ppc=32, closed=False, number_control=True)
+    case.params.deltaT0 = 2e-3
+    a, b = case.make_cloud(device_lib), case.make_cloud(device_lib)
+    a.seed_particles(); b.seed_particles()
+    assert b.profile_ctas().shape[0] == 0
+    a.evolve(3); b.evolve(3)
+    t = b.profile_ctas()
+    assert t.shape[0] > 0 and np.all(t[:, 1] >= t[:, 0]) and np.all(t[:, 2] >= 0) and np.all(t[:, 2] < 1024)
+    Pa, Pb = a.download_particles(), b.download_particles()
+    oa, ob = np.argsort(Pa["id"]), np.argsort(Pb["id"])
+    for k in ("pos", "U", "m"):
+        assert np.array_equal(Pa[k][oa], Pb[k][ob]), k
