@@ -356,27 +356,13 @@ __device__ __forceinline__ double courantNo(const DMesh &M, int cell, V3 Utrack)
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 4
 #endif
-// 1: the walk keeps the start point relative to the cell centre (r) instead of the centre itself; measured slower
-// (21.2 against 18.7 ms per launch, profiles/README.md), kept as an option
-#ifndef K1_TRACK_R
-#define K1_TRACK_R 0
-#endif
-
 #ifndef K1_COMPACT_ACC
 #define K1_COMPACT_ACC 1
 #endif
-// 1: the state that is needed again after the first tet walk (position, velocity, mass, local time step) is parked in
-// thread-private shared-memory rows (two conflict-free wavefronts per access) instead of being read again through the
-// permutation (about seven 128-byte lines per warp and column, a third of them hitting L1); needs K1_NPARK = 12
-#ifndef K1_PARK_STATE
-#define K1_PARK_STATE 0
-#endif
+// parking rows (the correction velocity and the Courant number; parking position, velocity, mass and local time step as
+// well instead of re-reading them through the permutation was measured slower: profiles/README.md)
 #define PK_UCORR 0
 #define PK_CO 3
-#define PK_POS 4
-#define PK_U 7
-#define PK_M 10
-#define PK_ETA 11
 // dynamic shared memory: thread-private accumulators + K1_NPARK thread-private parking rows
 // (the correction velocity and the Courant number, which must survive the tet walks without occupying registers)
 // The specialised kernel carries the sum rows of the conserved scalars the case has, not of K1_MAXCONS (k1_layout.h:
@@ -407,30 +393,9 @@ __device__ __forceinline__ double reloadD(const double *p) {
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// K1_STATE_NA 1: the gathered loads of the input state do not allocate in L1 (a warp touches about seven 128-byte
-// lines per column and uses a third of each; twenty resident warps would flood the L1 that the tet and node records
-// of the warp's cells should stay in)
-#ifndef K1_STATE_NA
-#define K1_STATE_NA 0
-#endif
-__device__ __forceinline__ double ldInD(const double *p) {
-#if K1_STATE_NA
-    double v;
-    asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
-}
 // the same for the input state, which the kernel never writes
 __device__ __forceinline__ double reloadInD(const double *p) {
-#if K1_STATE_NA
-    double v;
-    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-#else
     return reloadD(p);
-#endif
 }
 __device__ __forceinline__ int reloadI(const int *p) {
     int v;
@@ -536,28 +501,18 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
         const int slot = (i < nSorted) ? slotPerm : nSlotsIn + (i - nSorted);
         const int cell0 = A.in.cell[slot];
         if (cell0 < 0) { A.out.cell[i] = -1; continue; }
-        V3 pos = mk(ldInD(A.in.px + slot), ldInD(A.in.py + slot), ldInD(A.in.pz + slot));
+        V3 pos = mk(A.in.px[slot], A.in.py[slot], A.in.pz[slot]);
         const int tet0 = A.in.tet[slot];
         int tet = tet0;
         const bool injected = (i >= nSorted + nInjStart);
 
         // the particle's mass at the start of the step: the stored one plus its share of the mass lost in the
         // previous step (mcParticleCloud.C:1363-1369; particles injected since then get none)
-#if K1_PARK_STATE
-        {
-            double mm = ldInD(A.in.m + slot);
-            if (anyLost && !injected) mm += A.lostShare[cell0];
-            park[PK_M * K1_THREADS] = mm;
-            park[PK_ETA * K1_THREADS] = ldInD(A.in.eta + slot);
-        }
-        auto massIn = [&]() { return park[PK_M * K1_THREADS]; };
-#else
         auto massIn = [&]() {
             double mm = reloadInD(A.in.m + slot);
             if (anyLost && !injected) mm += A.lostShare[cell0];
             return mm;
         };
-#endif
         int status = 0;   // 0 alive, 1 deleted at an open boundary, 2 lost
         // ---- E1 + E2 need the mass and the conserved scalars; both are read again at the mid-point ----
         {
@@ -575,11 +530,11 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         const double4 n4 = M.bfNormal[bf];
                         const V3 Cf = ld3(M.faceCentres, M.nInternalFaces + bf);
                         const double xp = dot3(mk(n4.x, n4.y, n4.z), Cf - pos);
-                        if (xp < (K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : ldInD(A.in.eta + slot)) * (Un * deltaT)) {
+                        if (xp < A.in.eta[slot] * (Un * deltaT)) {
                             const double mpd = massPerDepth(M, pos, m);
                             accS[KACC_MASS_OUT * K1_THREADS] -= mpd;
                             for (int cs = 0; cs < P.nConserved; ++cs)
-                                accS[(KACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * ldInD(A.in.phi[PRM_AT(P, conserved, cs)] + slot);
+                                accS[(KACC_MASS_OUT + 1 + cs) * K1_THREADS] -= mpd * A.in.phi[PRM_AT(P, conserved, cs)][slot];
                             status = 1;
                         }
                     }
@@ -590,20 +545,17 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             const double mpd = massPerDepth(M, pos, m);
             accS[KACC_DM_MINUS * K1_THREADS] -= mpd;
             for (int cs = 0; cs < P.nConserved; ++cs)
-                accS[(KACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * ldInD(A.in.phi[PRM_AT(P, conserved, cs)] + slot);
+                accS[(KACC_DM_MINUS + 1 + cs) * K1_THREADS] -= mpd * A.in.phi[PRM_AT(P, conserved, cs)][slot];
         }
         // the walk state: tet record, the cell the tet belongs to and its centre (vertex d)
         TetL T;
         loadTet(M, tet, T);
         int cell = cell0;
         V3 ctr = cellCentre(M, cell0);
-#if K1_PARK_STATE
-        park[PK_POS * K1_THREADS] = pos.x; park[(PK_POS + 1) * K1_THREADS] = pos.y; park[(PK_POS + 2) * K1_THREADS] = pos.z;
-#endif
         // ---- E3: position correction gather ----
         V3 Utrack;
         {
-            V3 U = mk(ldInD(A.in.ux + slot), ldInD(A.in.uy + slot), ldInD(A.in.uz + slot));
+            V3 U = mk(A.in.ux[slot], A.in.uy[slot], A.in.uz[slot]);
             V3 Ucorr = mk(0, 0, 0);
             if (P.positionCorrection != PDFB200_POSCORR_NONE) {
                 // the interpolated vector: limitedSimple UPosCorr (Ucorrection += it, .C:187-192), simple grad(phi), external G0
@@ -664,11 +616,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             park[0] = Ucorr.x; park[K1_THREADS] = Ucorr.y; park[2 * K1_THREADS] = Ucorr.z;
             // the velocity after E4 ("Uold") equals the stored one except on axisymmetric meshes, where
             // constrainParticle has rotated it: parked in this particle's (still unwritten) output slot
-#if K1_PARK_STATE
-            park[PK_U * K1_THREADS] = U.x; park[(PK_U + 1) * K1_THREADS] = U.y; park[(PK_U + 2) * K1_THREADS] = U.z;
-#else
             if (MESH_AXISYM(M)) { A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z; }
-#endif
         }
         bool reflected = false;
         int reflBf = -1;   // boundary face of the last open-boundary reflection (mcOpenBoundary.C:201-204)
@@ -682,7 +630,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 double stepFraction = 0.0;
                 if (phase == 0 && injected) { double u0, u1; rngUniform2(A.key, A.in.id[slot], step, RNG_INLET_STEPFRAC, 0, u0, u1); stepFraction = u0; }
                 // phase 0 tracks with the old local time step, phase 1 with the new one (written to out.eta at the mid-point)
-                const double eta = K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : (phase == 0) ? reloadInD(A.in.eta + slot) : reloadD(A.out.eta + i);
+                const double eta = (phase == 0) ? reloadInD(A.in.eta + slot) : reloadD(A.out.eta + i);
                 const double trackTime = (phase == 0) ? eta * (deltaT / 2.) : eta * deltaT;
                 tEnd = (1.0 - stepFraction) * trackTime;
             }
@@ -701,9 +649,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 // changes cell; the centre itself is not kept through the loop (read again after it)
                 V3 r = pos - ctr;
                 for (;;) {
-#if !K1_TRACK_R
                     r = pos - ctr;
-#endif
                     double p0, p1, p2, p3;
                     baryAt(T, r, p0, p1, p2, p3);
                     const double q0 = dotf(T.g0, T.g1, T.g2, dx), q1 = dotf(T.g3, T.g4, T.g5, dx), q2 = dotf(T.g6, T.g7, T.g8, dx);
@@ -738,11 +684,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                         tet = (best == 3) ? T.n3 : nb;
                         // across the mesh face: the cell changes, and with it the centre the tets hang on
                         // (requested together with the next record, not after it)
-#if K1_TRACK_R
-                        if (best == 3) { cell = T.nbrCell; r = pos - cellCentre(M, cell); }
-#else
                         if (best == 3) { cell = T.nbrCell; ctr = cellCentre(M, cell); }
-#endif
                         loadTet(M, tet, T);
                         entry = best ^ (((best == 1) | (best == 2)) ? 3 : 0);   // the shared face is opposite c (b) in the tet across b (c)
                         continue;
@@ -797,21 +739,14 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                     if (phase == 0) {
                         V3 Ur;
                         if (reflected) Ur = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
-                        else if (K1_PARK_STATE) Ur = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
                         else if (MESH_AXISYM(M)) Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
                         else Ur = mk(reloadInD(A.in.ux + slot), reloadInD(A.in.uy + slot), reloadInD(A.in.uz + slot));
                         Ur = reflectVec(Ur, nw);
                         A.out.px[i] = Ur.x; A.out.py[i] = Ur.y; A.out.pz[i] = Ur.z;
                     } else {
-#if K1_PARK_STATE
-                        V3 Ur = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
-                        Ur = reflectVec(Ur, nw);
-                        park[PK_U * K1_THREADS] = Ur.x; park[(PK_U + 1) * K1_THREADS] = Ur.y; park[(PK_U + 2) * K1_THREADS] = Ur.z;
-#else
                         V3 Ur = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
                         Ur = reflectVec(Ur, nw);
                         A.out.ux[i] = Ur.x; A.out.uy[i] = Ur.y; A.out.uz[i] = Ur.z;
-#endif
                     }
                     Utrack = reflectVec(Utrack, nw);
                     reflected = true;
@@ -820,9 +755,6 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 }
                 dt *= tf;
                 tEnd -= dt;
-#if K1_TRACK_R
-                ctr = cellCentre(M, cell);
-#endif
             }
             if (status != 0) break;
             if (phase == 1) break;
@@ -846,7 +778,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             }
             const double *aux = A.cellAux + (size_t)cell * A.auxStride;
             // the particle's scalars, read again (see reloadD)
-            const double etaOld = K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : reloadInD(A.in.eta + slot);
+            const double etaOld = reloadInD(A.in.eta + slot);
             double Omega = reloadInD(A.in.omega + slot), rho = reloadInD(A.in.rho + slot);
             double phi[NPHI];
 #pragma unroll
@@ -901,8 +833,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             }
             // the velocity before the half step ("Uold") and the velocity the half step ended with
             V3 Uold;
-            if (K1_PARK_STATE) Uold = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
-            else if (MESH_AXISYM(M)) Uold = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
+            if (MESH_AXISYM(M)) Uold = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
             else Uold = mk(reloadInD(A.in.ux + slot), reloadInD(A.in.uy + slot), reloadInD(A.in.uz + slot));
             V3 U = Uold;
             if (reflected) U = mk(reloadD(A.out.px + i), reloadD(A.out.py + i), reloadD(A.out.pz + i));
@@ -927,13 +858,9 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             else if (P.localTimeStepping == PDFB200_LTS_PARTICLE) eta = fmin(P.CFL / stabilise(deltaT * Co, PDF_VSMALL), P.ltsUpperBound);
             else eta = 1.0;
             A.out.eta[i] = eta;
-#if K1_PARK_STATE
-            park[PK_ETA * K1_THREADS] = eta;   // the second walk and the maxima of the report use the new local time step
-#endif
 
             // ---- E9: mid-point rule from the old position ----
-            if (K1_PARK_STATE) pos = mk(park[PK_POS * K1_THREADS], park[(PK_POS + 1) * K1_THREADS], park[(PK_POS + 2) * K1_THREADS]);
-            else pos = mk(reloadInD(A.in.px + slot), reloadInD(A.in.py + slot), reloadInD(A.in.pz + slot));
+            pos = mk(reloadInD(A.in.px + slot), reloadInD(A.in.py + slot), reloadInD(A.in.pz + slot));
             tet = tet0;
             loadTet(M, tet, T);
             cell = cell0;
@@ -948,11 +875,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
                 constrainParticle(M, deltaT, pos, U, Ucorr, Utrack);
                 park[0] = Ucorr.x; park[K1_THREADS] = Ucorr.y; park[2 * K1_THREADS] = Ucorr.z;
             }
-#if K1_PARK_STATE
-            park[PK_U * K1_THREADS] = U.x; park[(PK_U + 1) * K1_THREADS] = U.y; park[(PK_U + 2) * K1_THREADS] = U.z;   // written to out.u* at the end
-#else
             A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
-#endif
             reflected = false;   // from here on: "reflected during the full step" (not used further)
         }
         if (status != 0) {
@@ -969,15 +892,6 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             continue;
         }
         // ---- E11: mcOpenBoundary::correct(true) ----
-#if K1_PARK_STATE
-        V3 U = mk(park[PK_U * K1_THREADS], park[(PK_U + 1) * K1_THREADS], park[(PK_U + 2) * K1_THREADS]);
-        if (reflBf >= 0) {
-            const double4 n4 = M.bfNormal[reflBf];
-            const V3 reflBV = mk(n4.x, n4.y, n4.z) * A.Un[reflBf];
-            U = U + 2 * reflBV;
-        }
-        A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
-#else
         V3 U = mk(reloadD(A.out.ux + i), reloadD(A.out.uy + i), reloadD(A.out.uz + i));
         if (reflBf >= 0) {
             const double4 n4 = M.bfNormal[reflBf];
@@ -985,7 +899,6 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
             U = U + 2 * reflBV;
             A.out.ux[i] = U.x; A.out.uy[i] = U.y; A.out.uz[i] = U.z;
         }
-#endif
 
         // ---- write back in sorted order (the scalars were written at the mid-point) ----
         A.out.px[i] = pos.x; A.out.py[i] = pos.y; A.out.pz[i] = pos.z;
@@ -995,7 +908,7 @@ __device__ __forceinline__ void evolveBody(const K1Args &A) {
 
         // ---- E15 particle sums / maxima (before particle-number control) ----
         {
-            const double m = K1_PARK_STATE ? park[PK_M * K1_THREADS] : reloadD(A.out.m + i), eta = K1_PARK_STATE ? park[PK_ETA * K1_THREADS] : reloadD(A.out.eta + i);
+            const double m = reloadD(A.out.m + i), eta = reloadD(A.out.eta + i);
             const double mpd = massPerDepth(M, pos, m);
             accS[KACC_DM_PLUS * K1_THREADS] += mpd;
             for (int cs = 0; cs < P.nConserved; ++cs)
