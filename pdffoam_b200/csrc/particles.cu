@@ -34,17 +34,21 @@ __global__ void k_locate(DMesh M, int n, PState S) {
 // fold per-CTA partial rows in index order (one thread per column)
 // launched with (32, 8) threads: warp w folds rows w, w+8, ... of column threadIdx.x, then
 // the eight partials are combined in warp order (fixed order -> deterministic)
+#define FOLD_Y 32
 __global__ void k_fold_rows(int nRows, int nCols, const double *rows, double *out, int isMax) {
-    __shared__ double part[8][33];
+    // blockDim = (32, FOLD_Y): thread (k, w) folds rows w, w + FOLD_Y, ... of column k, then row 0 of the block folds the
+    // FOLD_Y partial results in order. One CTA: the inputs are a few hundred rows, the kernel is a chain of latencies
+    // (93 dependent trips with 8 rows of threads on the 740 rows of the particle kernel; 24 with 32).
+    __shared__ double part[FOLD_Y][33];
     const int k = threadIdx.x, w = threadIdx.y;
     double x = isMax ? -PDF_VGREAT : 0.0;
     if (k < nCols)
-        for (int r = w; r < nRows; r += 8) { const double y = rows[(size_t)r * nCols + k]; x = isMax ? fmax(x, y) : x + y; }
+        for (int r = w; r < nRows; r += FOLD_Y) { const double y = rows[(size_t)r * nCols + k]; x = isMax ? fmax(x, y) : x + y; }
     part[w][k] = x;
     __syncthreads();
     if (w == 0 && k < nCols) {
         double t = part[0][k];
-        for (int j = 1; j < 8; ++j) t = isMax ? fmax(t, part[j][k]) : t + part[j][k];
+        for (int j = 1; j < FOLD_Y; ++j) t = isMax ? fmax(t, part[j][k]) : t + part[j][k];
         out[k] = t;
     }
 }
@@ -1565,7 +1569,7 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
         LAUNCH(this, k_inject_finish, 1, 32, 0, nBnd, scanTmp.p, scal.p, cap, nRanks);
         const int gI = std::min(gridFor(nBnd, 256), numSMs * 2);
         LAUNCH(this, k_colsum_nc1, gI, 256, 0, nBnd, injSums.p, k1PartSum.p);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gI, K1_NC1, k1PartSum.p, dRep->v + RP_INJ, 0);
     } else {
         CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_INJ, 0, K1_NC1 * sizeof(double), stream));
     }
@@ -1597,13 +1601,13 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
     }
     mark(2);
     LAUNCH(this, k_lost_reduce, 1, 1024, 0, lostList.p, lostSorted.p, lostCount.p, (unsigned)lostList.n, lostMass.p, scal.p);
-    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
-    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gridK1, ACC_NSUM, k1PartSum.p, dRep->v + RP_K1SUM, 0);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gridK1, ACC_NMAX, k1PartMax.p, dRep->v + RP_K1MAX, 1);
     if (k1Dynamic) {
         // the mass sums come chunk by chunk (fixed order inside a chunk, fixed order over the chunks)
-        const int gC = numSMs * 4;
+        const int gC = (int)std::max<long long>(1, std::min<long long>(numSMs * 4, (cap / k1Chunk + 63) / 64));   // >= 64 chunks per CTA
         LAUNCH(this, k_chunk_fold, gC, 256, 0, scal.p, k1Chunk, chunkSums.p, chunkPart.p);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gC, 4 * K1_NC1, chunkPart.p, dRep->v + RP_K1SUM, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gC, 4 * K1_NC1, chunkPart.p, dRep->v + RP_K1SUM, 0);
     }
     cur ^= 1;
 
@@ -1647,7 +1651,7 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
         const int gM = std::min(gridFor(nCells, MIX_WARPS), numSMs * 8);
         LAUNCH(this, k_mix_curl, gM, MIX_WARPS * 32, 0, dm, prm, S[cur], valsB.p,
                cellStart.p, cellEnd.p, scal.p, key, keysA.p, valsA.p, cellPartSum.p);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gM, K1_MAXCONS, cellPartSum.p, dRep->v + RP_MIXDELTA, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gM, K1_MAXCONS, cellPartSum.p, dRep->v + RP_MIXDELTA, 0);
     } else {
         CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_MIXDELTA, 0, K1_MAXCONS * sizeof(double), stream));
     }
@@ -1665,8 +1669,8 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
     // graph is being captured: evolve() orders the whole replay behind the copies instead)
     if (ev) orderAfterDownloads();
     fieldsFinalise(*this, cellPartSum.p, cellPartSum.p + (size_t)gF * 3, gF);
-    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
-    LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gF, 3, cellPartSum.p, dRep->v + RP_CELLSUM, 0);
+    LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gF, 2, cellPartSum.p + (size_t)gF * 3, dRep->v + RP_CELLMAX, 1);
 
     // ---- particle-number control ----
     CUDA_CHECK(cudaMemsetAsync(ncCounts.p, 0, 2 * sizeof(int), stream));
@@ -1688,10 +1692,10 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
         // fold ncDelta over cells deterministically: per-CTA partials, then rows
         const int gR = std::min(gridFor(nCells, 256), numSMs * 4);
         LAUNCH(this, k_colsum_nc1, gR, 256, 0, nCells, ncDelta.p, k1PartSum.p);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_NCDELTA, 0);
         if (axisym) {
             LAUNCH(this, k_colsum_nc1, gR, 256, 0, 0, cloneDelta.p, k1PartSum.p, scanTmp.p + 1);
-            LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_CLONEDELTA, 0);
+            LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gR, K1_NC1, k1PartSum.p, dRep->v + RP_CLONEDELTA, 0);
         } else {
             CUDA_CHECK(cudaMemsetAsync(dRep->v + RP_CLONEDELTA, 0, K1_NC1 * sizeof(double), stream));
         }
@@ -1709,7 +1713,7 @@ void Cloud::enqueueStep(void *k1Jit, size_t k1JitSmem, int k1Blocks, cudaEvent_t
         // after k_step_end: nSorted / nTail / nSlots describe the particles the next step starts from
         const int gB = numSMs * 4;
         LAUNCH(this, k_lost_balance, gB, 256, 0, dm, prm, S[cur], valsB.p, scal.p, lostCount.p, lostShare.p, k1PartSum.p);
-        LAUNCH(this, k_fold_rows, 1, dim3(32, 8), 0, gB, K1_NC1, k1PartSum.p, dRep->v + RP_LOSTSUM, 0);
+        LAUNCH(this, k_fold_rows, 1, dim3(32, FOLD_Y), 0, gB, K1_NC1, k1PartSum.p, dRep->v + RP_LOSTSUM, 0);
     }
     LAUNCH(this, k_report_out, 1, 64, 0, scal.p, dRep, dRing, REPORT_RING);
     mark(6);
